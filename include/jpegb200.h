@@ -1,0 +1,93 @@
+/* jpegb200.h — C ABI of libjpegb200.so, the B200 (sm_100a) JPEG encode path.
+ *
+ * Plain C: pointers, sizes and ints only; no CUDA or torch types.  This is what a reference-side
+ * binding links against.  The seven reference entry points of include/encoder.h and include/brain.h
+ * (implemented in main/encoder.c and main/brain.c of this repo) are thin callers of the
+ * "stage" functions below; batch users call jpegb200_encode_batch* directly.
+ *
+ * Every function returns 0 on success and a negative value on failure unless stated otherwise;
+ * jpegb200_last_error() then describes the failure (thread-local string).  There is no CPU
+ * fallback anywhere: without a usable CUDA device every call fails.
+ *
+ * Pixel order is B,G,R interleaved, 3 bytes per pixel, as in the reference (encoder.c:133-135).
+ * Crop and frame dimensions must be multiples of 16 (reference constraint).
+ */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jpegb200_ctx jpegb200_ctx;
+
+/* Context = one GPU, its streams and its reusable workspaces.  One context per GPU per host thread. */
+int jpegb200_create(jpegb200_ctx **ctx, int device);
+void jpegb200_destroy(jpegb200_ctx *ctx);
+const char *jpegb200_last_error(void);
+
+/* frames_per_wave: jobs that share one chain of launches (default 8);
+ * lanes: independent streams/workspaces the waves rotate over (default 3). */
+int jpegb200_configure(jpegb200_ctx *ctx, int frames_per_wave, int lanes);
+
+/* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
+uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
+
+/* ---- batched encode, device resident (the fast path) -------------------------------------------
+ * Replaces n x { rgb_to_dct (encoder.c:158) ; init_huffman (:360) ; write_jpg (:549) } with
+ * dims = {0,0,w,h} on n independent frames.
+ *   d_bgr        device pointer, frame i at d_bgr + i*frame_stride, rows w*3 bytes apart; 16-byte aligned
+ *   d_out        device pointer, finished JFIF stream of frame i at d_out + i*slot
+ *   d_sizes      device pointer, n uint32: bytes written per frame (0 = slot or scratch too small)
+ *   stream       cudaStream_t (as void*) to order against; NULL = default stream
+ * Asynchronous with respect to the host. */
+int jpegb200_encode_batch(jpegb200_ctx *ctx, const uint8_t *d_bgr, int n, int w, int h, size_t frame_stride,
+                          uint8_t *d_out, size_t slot, uint32_t *d_sizes, void *stream);
+
+/* Same work, HOST buffers in and out (pinned memory recommended): host->device copies, kernels and
+ * device->host copies are pipelined over the context's lanes.  Synchronous: returns when h_out and
+ * h_sizes are complete. */
+int jpegb200_encode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_bgr, int n, int w, int h, uint8_t *h_out,
+                               size_t slot, uint32_t *h_sizes);
+
+/* Encode `nareas` crops (x,y,w,h quadruples in host memory) of ONE device-resident frame; what
+ * app_main does per detected region (main.c:142-153).  Asynchronous like jpegb200_encode_batch. */
+int jpegb200_encode_regions(jpegb200_ctx *ctx, const uint8_t *d_frame, int frame_w, int frame_h, const int *areas_xywh,
+                            int nareas, uint8_t *d_out, size_t slot, uint32_t *d_sizes, void *stream);
+
+/* ---- stage functions with HOST buffers (synchronous) — bound by main/encoder.c ------------------ */
+
+/* rgb_to_dct (encoder.c:158-178): crop (x,y,w,h) of a frame_w-wide BGR frame -> Y[w*h], Cb[w*h/4], Cr[w*h/4]. */
+int jpegb200_stage_dct(jpegb200_ctx *ctx, const uint8_t *bgr, int frame_w, int frame_h, int x, int y, int w, int h,
+                       int16_t *Y, int16_t *Cb, int16_t *Cr);
+/* init_huffman (encoder.c:360-381): planes -> luma[2], chroma[2] (arrays of the reference's huff_code). */
+int jpegb200_stage_huffman(jpegb200_ctx *ctx, const int16_t *Y, const int16_t *Cb, const int16_t *Cr, int w, int h,
+                           void *luma2, void *chroma2);
+/* write_jpg (encoder.c:549-644): planes + tables -> JFIF bytes in jpg[0..cap); returns the size, 0 on failure. */
+size_t jpegb200_stage_write(jpegb200_ctx *ctx, uint8_t *jpg, size_t cap, const int16_t *Y, const int16_t *Cb,
+                            const int16_t *Cr, int w, int h, const void *luma2, const void *chroma2);
+
+/* Test hook: k_build_huffman on caller histograms (ntab x 257 ints in, ntab huff_code out); see tests/. */
+int jpegb200_debug_build_tables(jpegb200_ctx *ctx, const int *freq, int ntab, void *huff_out);
+
+/* ---- comparator (brain.c), HOST buffers (synchronous) — bound by main/brain.c -------------------- */
+
+/* subsample (brain.c:16-44): BGR frame -> RGB (frame_w/4 x frame_h/4). */
+int jpegb200_subsample(jpegb200_ctx *ctx, const uint8_t *bgr, int frame_w, int frame_h, uint8_t *sub);
+/* compare (brain.c:110-235): fills outs_xywh[400] (100 boxes, unused = -1); returns the region count (>= 0) or < 0. */
+int jpegb200_compare(jpegb200_ctx *ctx, const uint8_t *sub, const uint8_t *saved, int frame_w, int frame_h, int *outs_xywh);
+/* enlargeAdjust (brain.c:244-261) on one (xmin,ymin,xmax,ymax) box, in place. */
+int jpegb200_enlarge_adjust(jpegb200_ctx *ctx, int *area_xywh, int frame_w, int frame_h);
+
+/* Fused steady-state iteration of app_main (main.c:137-162) on the device: sub-sample the new frame,
+ * compare with the saved sub-sampled frame kept in the context, encode every changed region, then
+ * store the new sub-sampled frame.  `h_frame` is a host BGR frame.  Outputs: region rectangles
+ * (outs_xywh[400]), per-region JFIF streams at h_out + i*slot and their sizes.  Returns the region count.
+ * seed != 0: only sub-sample and store (the start-up step, main.c:125-128); returns 0. */
+int jpegb200_compare_encode(jpegb200_ctx *ctx, const uint8_t *h_frame, int frame_w, int frame_h, int seed, int *outs_xywh,
+                            uint8_t *h_out, size_t slot, uint32_t *h_sizes, uint8_t *h_sub_optional);
+
+#ifdef __cplusplus
+}
+#endif

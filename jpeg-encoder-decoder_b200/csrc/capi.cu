@@ -1,0 +1,666 @@
+// capi.cu — the C ABI of libjpegb200.so (include/jpegb200.h): contexts, workspaces, the chain of
+// launches of one wave, the pipelined host path and the stage-level entry points that the drop-in
+// main/encoder.c and main/brain.c bind.  No CPU arithmetic on pixel or coefficient data happens here.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/jpegb200.h"
+#include "jpegb200_internal.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return -1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaError_t e = cudaFree(p); if (e != cudaSuccess) return e; p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// Sizes of one wave's workspace.
+struct WaveDims {
+  size_t njobs = 0, coefs = 0, blocks = 0, chunks = 0, scratch_words = 0, tiles = 0;
+};
+
+struct Lane {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr, sizes_ready = nullptr;
+  DevBuf jobs, state_hist, coef, mask, dcraw, blkbits, chunk_bits, chunk_base, huff, enc, scratch, tile_ff;
+  DevBuf in, out, sizes;      // host-path staging on the device
+  PinBuf h_jobs, h_sizes;
+  JbWs ws{};
+  // host path bookkeeping of the wave in flight
+  int pending_first = -1, pending_n = 0;
+  size_t sh_bytes = 0;        // bytes of the state+histogram block laid out by the last ensure()
+
+  cudaError_t ensure(const WaveDims& d) {
+    cudaError_t e;
+    if ((e = jobs.ensure(d.njobs * sizeof(JbJob))) != cudaSuccess) return e;
+    if ((e = state_hist.ensure(d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int)))) != cudaSuccess) return e;
+    if ((e = coef.ensure(d.coefs * sizeof(int16_t))) != cudaSuccess) return e;
+    if ((e = mask.ensure(d.blocks * sizeof(uint64_t))) != cudaSuccess) return e;
+    if ((e = dcraw.ensure(d.blocks * sizeof(int16_t))) != cudaSuccess) return e;
+    if ((e = blkbits.ensure(d.blocks * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = chunk_bits.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = chunk_base.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = huff.ensure(d.njobs * 4 * sizeof(JbHuff))) != cudaSuccess) return e;
+    if ((e = enc.ensure(d.njobs * 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = scratch.ensure(d.scratch_words * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = tile_ff.ensure(d.tiles * sizeof(uint32_t))) != cudaSuccess) return e;
+    sh_bytes = d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int));
+    ws.jobs = (JbJob*)jobs.p;
+    ws.state = (JbJobState*)state_hist.p;
+    ws.hist = (int*)((char*)state_hist.p + d.njobs * sizeof(JbJobState));
+    ws.coef = (int16_t*)coef.p;
+    ws.mask = (uint64_t*)mask.p;
+    ws.dcraw = (int16_t*)dcraw.p;
+    ws.blkbits = (uint32_t*)blkbits.p;
+    ws.chunk_bits = (uint32_t*)chunk_bits.p;
+    ws.chunk_base = (uint32_t*)chunk_base.p;
+    ws.huff = (JbHuff*)huff.p;
+    ws.enc = (uint32_t*)enc.p;
+    ws.scratch = (uint32_t*)scratch.p;
+    ws.tile_ff = (uint32_t*)tile_ff.p;
+    return cudaSuccess;
+  }
+  void release() {
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &blkbits, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &in, &out, &sizes})
+      b->release();
+    h_jobs.release();
+    h_sizes.release();
+    if (done) cudaEventDestroy(done);
+    if (sizes_ready) cudaEventDestroy(sizes_ready);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// Per-job workspace footprint for a w x h crop whose output slot holds `slot` bytes.
+struct JobDims {
+  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg;
+};
+JobDims job_dims(int w, int h, size_t slot) {
+  JobDims d;
+  uint32_t nby = jb_nby(w, h), nbc = jb_nbc(w, h);
+  d.coefs = 64u * (nby + 2 * nbc);
+  d.blocks = nby + 2 * nbc;
+  d.chunks = jb_chunks(nby) + 2 * jb_chunks(nbc);
+  // un-stuffed scan bits never exceed the finished file; three scans add alignment slack
+  size_t words = (slot + 3) / 4 + 3 * 8;
+  words = (words + 3) & ~(size_t)3;
+  d.scratch_words = (uint32_t)words;
+  d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
+  return d;
+}
+
+__global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t frame_stride, int w, int h, uint8_t* out0, size_t slot,
+                            JobDims d) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  JbJob j;
+  j.src = src0 + (size_t)i * frame_stride;
+  j.pitch = 3u * (uint32_t)w;
+  j.x = 0; j.y = 0; j.w = w; j.h = h;
+  j.coef_off = (uint32_t)i * d.coefs;
+  j.blk_off = (uint32_t)i * d.blocks;
+  j.chunk_off = (uint32_t)i * d.chunks;
+  j.tile_off = (uint32_t)i * 3u * d.tiles_per_seg;
+  j.tiles_per_seg = d.tiles_per_seg;
+  j.scratch_off = (uint32_t)i * d.scratch_words;
+  j.scratch_cap = d.scratch_words;
+  j.out = out0 + (size_t)i * slot;
+  j.out_cap = slot > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)slot;
+  j.src_bytes = 3u * (uint32_t)w * (uint32_t)h;
+  jobs[i] = j;
+}
+
+}  // namespace
+
+struct jpegb200_ctx {
+  int device = 0;
+  int frames_per_wave = 8;
+  std::vector<Lane> lanes;
+  cudaEvent_t fork = nullptr;
+  uint64_t launches = 0;
+  // comparator state
+  DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_bits, cmp_outs;
+  PinBuf cmp_host;
+  bool have_saved = false;
+  int saved_w = 0, saved_h = 0;
+};
+
+namespace {
+
+int make_lanes(jpegb200_ctx* c, int n) {
+  for (auto& l : c->lanes) l.release();
+  c->lanes.clear();
+  c->lanes.resize(n);
+  for (auto& l : c->lanes) {
+    CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.sizes_ready, cudaEventDisableTiming));
+  }
+  return 0;
+}
+
+enum ChainFrom { FROM_PIXELS, FROM_PLANES_STATS, FROM_PLANES_WRITE };
+
+// Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
+int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
+              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes) {
+  cudaStream_t st = l.stream;
+  const JbWs& ws = l.ws;
+  CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
+  if (from == FROM_PIXELS) {
+    jb_launch_dct(ws, njobs, max_w, max_h, st);
+    c->launches++;
+  } else {
+    jb_launch_plane_masks(ws, njobs, max_blocks, st);
+    c->launches++;
+  }
+  if (from != FROM_PLANES_WRITE) {
+    jb_launch_symbol_stats(ws, njobs, max_chunks, from == FROM_PIXELS ? 1 : 0, st);
+    c->launches++;
+    if (stop_after_dct) { CK(cudaGetLastError()); return 0; }
+    jb_launch_build_huffman(ws, njobs, st);
+    c->launches++;
+    if (stop_after_tables) { CK(cudaGetLastError()); return 0; }
+  }
+  jb_launch_pack_tables(ws, njobs, st);
+  jb_launch_block_bits(ws, njobs, max_chunks, st);
+  jb_launch_scan(ws, njobs, st);
+  jb_launch_pack(ws, njobs, max_chunks, st);
+  jb_launch_count_ff(ws, njobs, 8, st);
+  jb_launch_layout(ws, njobs, d_sizes, st);
+  jb_launch_stuff(ws, njobs, 8, st);
+  c->launches += 7;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int check_dims(int w, int h) {
+  if (w <= 0 || h <= 0 || (w % 16) || (h % 16)) return fail("dimensions %dx%d must be positive multiples of 16", w, h);
+  if ((size_t)w * h > (size_t)1 << 27) return fail("crop %dx%d too large", w, h);
+  return 0;
+}
+
+// Upload explicit job descriptors (regions / stage calls) through the lane's pinned staging buffer.
+int upload_jobs(Lane& l, const std::vector<JbJob>& jobs) {
+  CK(cudaEventSynchronize(l.done));          // the staging buffer may still feed an earlier copy
+  CK(l.h_jobs.ensure(jobs.size() * sizeof(JbJob)));
+  memcpy(l.h_jobs.p, jobs.data(), jobs.size() * sizeof(JbJob));
+  CK(cudaMemcpyAsync(l.ws.jobs, l.h_jobs.p, jobs.size() * sizeof(JbJob), cudaMemcpyHostToDevice, l.stream));
+  CK(cudaEventRecord(l.done, l.stream));
+  return 0;
+}
+
+// Lay out `n` heterogeneous jobs in one lane workspace.
+int plan_jobs(Lane& l, std::vector<JbJob>& jobs, const std::vector<size_t>& slots, int* max_w, int* max_h, uint32_t* max_blocks,
+              uint32_t* max_chunks) {
+  WaveDims wd;
+  wd.njobs = jobs.size();
+  *max_w = *max_h = 0; *max_blocks = *max_chunks = 0;
+  for (size_t i = 0; i < jobs.size(); i++) {
+    JobDims d = job_dims(jobs[i].w, jobs[i].h, slots[i]);
+    jobs[i].coef_off = (uint32_t)wd.coefs;
+    jobs[i].blk_off = (uint32_t)wd.blocks;
+    jobs[i].chunk_off = (uint32_t)wd.chunks;
+    jobs[i].tile_off = (uint32_t)wd.tiles;
+    jobs[i].tiles_per_seg = d.tiles_per_seg;
+    jobs[i].scratch_off = (uint32_t)wd.scratch_words;
+    jobs[i].scratch_cap = d.scratch_words;
+    wd.coefs += d.coefs; wd.blocks += d.blocks; wd.chunks += d.chunks; wd.tiles += 3 * (size_t)d.tiles_per_seg;
+    wd.scratch_words += d.scratch_words;
+    *max_w = std::max(*max_w, jobs[i].w); *max_h = std::max(*max_h, jobs[i].h);
+    *max_blocks = std::max(*max_blocks, d.blocks); *max_chunks = std::max(*max_chunks, d.chunks);
+  }
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large for 32-bit offsets");
+  CK(l.ensure(wd));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* jpegb200_last_error(void) { return g_err; }
+
+int jpegb200_create(jpegb200_ctx** out, int device) {
+  if (!out) return fail("null ctx pointer");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (%s); libjpegb200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail("device %d out of range (0..%d)", device, ndev - 1);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; libjpegb200 is built for sm_100a only", device, prop.major, prop.minor);
+  jpegb200_ctx* c = new jpegb200_ctx();
+  c->device = device;
+  if (make_lanes(c, 3) != 0) { delete c; return -1; }
+  if (cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return fail("cudaEventCreate failed"); }
+  *out = c;
+  return 0;
+}
+
+void jpegb200_destroy(jpegb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& l : c->lanes) l.release();
+  for (DevBuf* b : {&c->cmp_frame, &c->cmp_sub, &c->cmp_saved, &c->cmp_bits, &c->cmp_outs}) b->release();
+  c->cmp_host.release();
+  if (c->fork) cudaEventDestroy(c->fork);
+  delete c;
+}
+
+int jpegb200_configure(jpegb200_ctx* c, int frames_per_wave, int lanes) {
+  if (!c) return fail("null ctx");
+  if (frames_per_wave < 1 || frames_per_wave > 4096 || lanes < 1 || lanes > 16) return fail("bad configuration");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  c->frames_per_wave = frames_per_wave;
+  if ((int)c->lanes.size() != lanes) return make_lanes(c, lanes);
+  return 0;
+}
+
+uint64_t jpegb200_launch_count(const jpegb200_ctx* c) { return c ? c->launches : 0; }
+
+int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, int h, size_t frame_stride, uint8_t* d_out, size_t slot,
+                          uint32_t* d_sizes, void* stream) {
+  if (!c || !d_bgr || !d_out || !d_sizes) return fail("null argument");
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  if (((uintptr_t)d_bgr | frame_stride) & 15) return fail("d_bgr and frame_stride must be 16-byte aligned");
+  if (frame_stride < (size_t)3 * w * h) return fail("frame_stride smaller than a frame");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t user = (cudaStream_t)stream;
+  const JobDims jd = job_dims(w, h, slot);
+  const int G = c->frames_per_wave;
+  WaveDims wd;
+  const size_t g = (size_t)std::min(G, n);
+  wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
+  wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
+  const int nwaves = (n + G - 1) / G;
+  const int nl = std::min<int>((int)c->lanes.size(), nwaves);
+  for (int i = 0; i < nl; i++) CK(c->lanes[i].ensure(wd));
+  CK(cudaEventRecord(c->fork, user));
+  for (int i = 0; i < nl; i++) CK(cudaStreamWaitEvent(c->lanes[i].stream, c->fork, 0));
+  for (int k = 0; k < nwaves; k++) {
+    Lane& l = c->lanes[k % nl];
+    const int first = k * G, cnt = std::min(G, n - first);
+    k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, d_bgr + (size_t)first * frame_stride, frame_stride, w, h,
+                                                          d_out + (size_t)first * slot, slot, jd);
+    c->launches++;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first)) return -1;
+  }
+  for (int i = 0; i < nl; i++) {
+    CK(cudaEventRecord(c->lanes[i].done, c->lanes[i].stream));
+    CK(cudaStreamWaitEvent(user, c->lanes[i].done, 0));
+  }
+  return 0;
+}
+
+int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int w, int h, uint8_t* h_out, size_t slot, uint32_t* h_sizes) {
+  if (!c || !h_bgr || !h_out || !h_sizes) return fail("null argument");
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  CK(cudaSetDevice(c->device));
+  const size_t frame = (size_t)3 * w * h;
+  const size_t dslot = (slot + 15) & ~(size_t)15;
+  const JobDims jd = job_dims(w, h, slot);
+  const int G = c->frames_per_wave;
+  const size_t g = (size_t)std::min(G, n);
+  WaveDims wd;
+  wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
+  wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
+  const int nwaves = (n + G - 1) / G;
+  const int nl = std::min<int>((int)c->lanes.size(), nwaves);
+  for (int i = 0; i < nl; i++) {
+    Lane& l = c->lanes[i];
+    CK(l.ensure(wd));
+    CK(l.in.ensure(g * frame));
+    CK(l.out.ensure(g * dslot));
+    CK(l.sizes.ensure(g * sizeof(uint32_t)));
+    CK(l.h_sizes.ensure(g * sizeof(uint32_t)));
+    l.pending_first = -1;
+  }
+  // Retire the wave in flight on a lane: wait for its sizes, then fetch exactly the bytes produced.
+  auto retire = [&](Lane& l) -> int {
+    if (l.pending_first < 0) return 0;
+    CK(cudaEventSynchronize(l.sizes_ready));
+    const uint32_t* sz = (const uint32_t*)l.h_sizes.p;
+    for (int i = 0; i < l.pending_n; i++) {
+      h_sizes[l.pending_first + i] = sz[i];
+      if (sz[i]) CK(cudaMemcpyAsync(h_out + (size_t)(l.pending_first + i) * slot, (uint8_t*)l.out.p + (size_t)i * dslot, sz[i],
+                                    cudaMemcpyDeviceToHost, l.stream));
+    }
+    l.pending_first = -1;
+    return 0;
+  };
+  for (int k = 0; k < nwaves; k++) {
+    Lane& l = c->lanes[k % nl];
+    if (retire(l)) return -1;
+    const int first = k * G, cnt = std::min(G, n - first);
+    CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
+    k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, (const uint8_t*)l.in.p, frame, w, h, (uint8_t*)l.out.p, dslot, jd);
+    c->launches++;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p)) return -1;
+    CK(cudaMemcpyAsync(l.h_sizes.p, l.sizes.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
+    CK(cudaEventRecord(l.sizes_ready, l.stream));
+    l.pending_first = first;
+    l.pending_n = cnt;
+  }
+  for (int i = 0; i < nl; i++) if (retire(c->lanes[i])) return -1;
+  for (int i = 0; i < nl; i++) CK(cudaStreamSynchronize(c->lanes[i].stream));
+  return 0;
+}
+
+int jpegb200_encode_regions(jpegb200_ctx* c, const uint8_t* d_frame, int frame_w, int frame_h, const int* areas, int nareas, uint8_t* d_out,
+                            size_t slot, uint32_t* d_sizes, void* stream) {
+  if (!c || !d_frame || !areas || !d_out || !d_sizes) return fail("null argument");
+  if (nareas <= 0) return 0;
+  if (check_dims(frame_w, frame_h)) return -1;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t user = (cudaStream_t)stream;
+  Lane& l = c->lanes[0];
+  std::vector<JbJob> jobs(nareas);
+  std::vector<size_t> slots(nareas, slot);
+  for (int i = 0; i < nareas; i++) {
+    const int x = areas[4 * i], y = areas[4 * i + 1], w = areas[4 * i + 2], h = areas[4 * i + 3];
+    if (check_dims(w, h)) return -1;
+    if (x < 0 || y < 0 || x + w > frame_w || y + h > frame_h) return fail("region %d (%d,%d,%d,%d) outside the %dx%d frame", i, x, y, w, h, frame_w, frame_h);
+    JbJob& j = jobs[i];
+    memset(&j, 0, sizeof j);
+    j.src = d_frame; j.pitch = 3u * (uint32_t)frame_w;
+    j.x = x; j.y = y; j.w = w; j.h = h;
+    j.out = d_out + (size_t)i * slot;
+    j.out_cap = (uint32_t)std::min<size_t>(slot, 0xFFFFFFFFu);
+    j.src_bytes = 3u * (uint32_t)frame_w * (uint32_t)frame_h;
+  }
+  int mw, mh; uint32_t mb, mc;
+  CK(cudaEventRecord(c->fork, user));
+  CK(cudaStreamWaitEvent(l.stream, c->fork, 0));
+  CK(cudaStreamSynchronize(l.stream));       // the workspace may be re-allocated below
+  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc)) return -1;
+  if (upload_jobs(l, jobs)) return -1;
+  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes)) return -1;
+  CK(cudaEventRecord(l.done, l.stream));
+  CK(cudaStreamWaitEvent(user, l.done, 0));
+  return 0;
+}
+
+// ---- stage functions (host buffers, synchronous) -------------------------------------------------
+
+int jpegb200_stage_dct(jpegb200_ctx* c, const uint8_t* bgr, int frame_w, int frame_h, int x, int y, int w, int h, int16_t* Y, int16_t* Cb,
+                       int16_t* Cr) {
+  if (!c || !bgr || !Y || !Cb || !Cr) return fail("null argument");
+  if (check_dims(w, h)) return -1;
+  if (frame_w <= 0 || x < 0 || y < 0 || x + w > frame_w || (frame_h > 0 && y + h > frame_h)) return fail("crop outside the frame");
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[0];
+  CK(cudaStreamSynchronize(l.stream));
+  const size_t pitch = (size_t)3 * frame_w, rows_bytes = pitch * h;
+  CK(l.in.ensure(rows_bytes));
+  std::vector<JbJob> jobs(1);
+  std::vector<size_t> slots(1, (size_t)3 * w * h + 4096);
+  JbJob& j = jobs[0];
+  memset(&j, 0, sizeof j);
+  j.src = (const uint8_t*)l.in.p; j.pitch = (uint32_t)pitch;
+  j.x = x; j.y = 0; j.w = w; j.h = h;                      // only rows y..y+h-1 are uploaded
+  j.out = nullptr; j.out_cap = 0; j.src_bytes = (uint32_t)rows_bytes;
+  int mw, mh; uint32_t mb, mc;
+  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc)) return -1;
+  j.src = (const uint8_t*)l.in.p;
+  CK(cudaMemcpyAsync(l.in.p, bgr + pitch * y, rows_bytes, cudaMemcpyHostToDevice, l.stream));
+  if (upload_jobs(l, jobs)) return -1;
+  if (run_chain(c, l, 1, mw, mh, mb, mc, FROM_PIXELS, true, false, nullptr)) return -1;
+  const size_t n = (size_t)w * h;
+  CK(cudaMemcpyAsync(Y, l.ws.coef, n * 2, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaMemcpyAsync(Cb, l.ws.coef + n, n / 2, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaMemcpyAsync(Cr, l.ws.coef + n + n / 4, n / 2, cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
+  return 0;
+}
+
+static int upload_planes(jpegb200_ctx* c, Lane& l, const int16_t* Y, const int16_t* Cb, const int16_t* Cr, int w, int h, size_t slot, uint8_t* d_out,
+                         int* mw, int* mh, uint32_t* mb, uint32_t* mc) {
+  std::vector<JbJob> jobs(1);
+  std::vector<size_t> slots(1, slot);
+  JbJob& j = jobs[0];
+  memset(&j, 0, sizeof j);
+  j.w = w; j.h = h;
+  if (plan_jobs(l, jobs, slots, mw, mh, mb, mc)) return -1;
+  j.out = d_out;
+  j.out_cap = (uint32_t)std::min<size_t>(slot, 0xFFFFFFFFu);
+  const size_t n = (size_t)w * h;
+  CK(cudaMemcpyAsync(l.ws.coef, Y, n * 2, cudaMemcpyHostToDevice, l.stream));
+  CK(cudaMemcpyAsync(l.ws.coef + n, Cb, n / 2, cudaMemcpyHostToDevice, l.stream));
+  CK(cudaMemcpyAsync(l.ws.coef + n + n / 4, Cr, n / 2, cudaMemcpyHostToDevice, l.stream));
+  return upload_jobs(l, jobs);
+}
+
+int jpegb200_stage_huffman(jpegb200_ctx* c, const int16_t* Y, const int16_t* Cb, const int16_t* Cr, int w, int h, void* luma2, void* chroma2) {
+  if (!c || !Y || !Cb || !Cr || !luma2 || !chroma2) return fail("null argument");
+  if (check_dims(w, h)) return -1;
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[0];
+  CK(cudaStreamSynchronize(l.stream));
+  int mw, mh; uint32_t mb, mc;
+  if (upload_planes(c, l, Y, Cb, Cr, w, h, 4096, nullptr, &mw, &mh, &mb, &mc)) return -1;
+  if (run_chain(c, l, 1, mw, mh, mb, mc, FROM_PLANES_STATS, false, true, nullptr)) return -1;
+  CK(cudaMemcpyAsync(luma2, l.ws.huff, 2 * sizeof(JbHuff), cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaMemcpyAsync(chroma2, l.ws.huff + 2, 2 * sizeof(JbHuff), cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
+  JbJobState st;
+  CK(cudaMemcpy(&st, l.ws.state, sizeof st, cudaMemcpyDeviceToHost));
+  if (st.error) return fail("device reported error flags 0x%x while building tables", st.error);
+  return 0;
+}
+
+size_t jpegb200_stage_write(jpegb200_ctx* c, uint8_t* jpg, size_t cap, const int16_t* Y, const int16_t* Cb, const int16_t* Cr, int w, int h,
+                            const void* luma2, const void* chroma2) {
+  if (!c || !jpg || !Y || !Cb || !Cr || !luma2 || !chroma2) { fail("null argument"); return 0; }
+  if (check_dims(w, h)) return 0;
+  if (cudaSetDevice(c->device) != cudaSuccess) { fail("cudaSetDevice failed"); return 0; }
+  Lane& l = c->lanes[0];
+  if (cudaStreamSynchronize(l.stream) != cudaSuccess) { fail("stream sync failed"); return 0; }
+  const size_t slot = std::min<size_t>(cap, (size_t)3 * w * h + 4096);
+  if (l.out.ensure(slot + 16) != cudaSuccess || l.sizes.ensure(16) != cudaSuccess) { fail("out of device memory"); return 0; }
+  int mw, mh; uint32_t mb, mc;
+  if (upload_planes(c, l, Y, Cb, Cr, w, h, slot, (uint8_t*)l.out.p, &mw, &mh, &mb, &mc)) return 0;
+  if (cudaMemcpyAsync(l.ws.huff, luma2, 2 * sizeof(JbHuff), cudaMemcpyHostToDevice, l.stream) != cudaSuccess ||
+      cudaMemcpyAsync(l.ws.huff + 2, chroma2, 2 * sizeof(JbHuff), cudaMemcpyHostToDevice, l.stream) != cudaSuccess) { fail("table upload failed"); return 0; }
+  if (run_chain(c, l, 1, mw, mh, mb, mc, FROM_PLANES_WRITE, false, false, (uint32_t*)l.sizes.p)) return 0;
+  uint32_t size = 0;
+  if (cudaMemcpyAsync(&size, l.sizes.p, 4, cudaMemcpyDeviceToHost, l.stream) != cudaSuccess || cudaStreamSynchronize(l.stream) != cudaSuccess) {
+    fail("encode failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return 0;
+  }
+  if (!size) { fail("output does not fit in %zu bytes", cap); return 0; }
+  if (cudaMemcpy(jpg, l.out.p, size, cudaMemcpyDeviceToHost) != cudaSuccess) { fail("download failed"); return 0; }
+  return size;
+}
+
+// Test hook: run the device table builder on caller-supplied histograms (ntab x 257 ints; slot 256 is
+// forced to 1 like encoder.c:367) and return ntab huff_code structs.  Lets the parity suite fuzz
+// k_build_huffman directly against the oracle.
+int jpegb200_debug_build_tables(jpegb200_ctx* c, const int* freq, int ntab, void* huff_out) {
+  if (!c || !freq || !huff_out || ntab <= 0) return fail("bad argument");
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[0];
+  CK(cudaStreamSynchronize(l.stream));
+  WaveDims wd;
+  wd.njobs = (size_t)(ntab + 3) / 4;
+  wd.coefs = wd.blocks = wd.chunks = wd.scratch_words = wd.tiles = 16;
+  CK(l.ensure(wd));
+  CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, l.stream));
+  CK(cudaMemcpyAsync(l.ws.hist, freq, (size_t)ntab * 257 * sizeof(int), cudaMemcpyHostToDevice, l.stream));
+  jb_launch_build_huffman(l.ws, (int)wd.njobs, l.stream);
+  c->launches++;
+  CK(cudaMemcpyAsync(huff_out, l.ws.huff, (size_t)ntab * sizeof(JbHuff), cudaMemcpyDeviceToHost, l.stream));
+  CK(cudaStreamSynchronize(l.stream));
+  return 0;
+}
+
+// ---- comparator -----------------------------------------------------------------------------------
+
+int jpegb200_subsample(jpegb200_ctx* c, const uint8_t* bgr, int fw, int fh, uint8_t* sub) {
+  if (!c || !bgr || !sub) return fail("null argument");
+  if (check_dims(fw, fh)) return -1;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->lanes[0].stream;
+  const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
+  CK(c->cmp_frame.ensure(fb));
+  CK(c->cmp_sub.ensure(sb));
+  CK(cudaMemcpyAsync(c->cmp_frame.p, bgr, fb, cudaMemcpyHostToDevice, st));
+  jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, st);
+  c->launches++;
+  CK(cudaMemcpyAsync(sub, c->cmp_sub.p, sb, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+static int compare_on_device(jpegb200_ctx* c, const uint8_t* d_sub, const uint8_t* d_saved, int fw, int fh, int* outs_xywh, cudaStream_t st) {
+  const int sw = fw / 4, sh = fh / 4, wpr = (sw + 31) / 32;
+  CK(c->cmp_bits.ensure((size_t)wpr * sh * 4));
+  CK(c->cmp_outs.ensure(401 * sizeof(int)));
+  CK(c->cmp_host.ensure(401 * sizeof(int)));
+  jb_launch_diff_mask(d_sub, d_saved, sw, sh, (uint32_t*)c->cmp_bits.p, st);
+  jb_launch_regions((const uint32_t*)c->cmp_bits.p, fw, fh, (int*)c->cmp_outs.p, (int*)c->cmp_outs.p + 400, st);
+  c->launches += 2;
+  CK(cudaMemcpyAsync(c->cmp_host.p, c->cmp_outs.p, 401 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(outs_xywh, c->cmp_host.p, 400 * sizeof(int));
+  return ((int*)c->cmp_host.p)[400];
+}
+
+int jpegb200_compare(jpegb200_ctx* c, const uint8_t* sub, const uint8_t* saved, int fw, int fh, int* outs_xywh) {
+  if (!c || !sub || !saved || !outs_xywh) return fail("null argument");
+  if (check_dims(fw, fh)) return -1;
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->lanes[0].stream;
+  const size_t sb = (size_t)3 * fw * fh / 16;
+  CK(c->cmp_sub.ensure(sb));
+  DevBuf tmp;
+  CK(tmp.ensure(sb));
+  CK(cudaMemcpyAsync(c->cmp_sub.p, sub, sb, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(tmp.p, saved, sb, cudaMemcpyHostToDevice, st));
+  int n = compare_on_device(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)tmp.p, fw, fh, outs_xywh, st);
+  tmp.release();
+  return n;
+}
+
+int jpegb200_enlarge_adjust(jpegb200_ctx* c, int* area, int fw, int fh) {
+  if (!c || !area) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->lanes[0].stream;
+  CK(c->cmp_outs.ensure(401 * sizeof(int)));
+  CK(cudaMemcpyAsync(c->cmp_outs.p, area, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+  jb_launch_enlarge_adjust((int*)c->cmp_outs.p, fw, fh, st);
+  c->launches++;
+  CK(cudaMemcpyAsync(area, c->cmp_outs.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int jpegb200_compare_encode(jpegb200_ctx* c, const uint8_t* h_frame, int fw, int fh, int seed, int* outs_xywh, uint8_t* h_out, size_t slot,
+                            uint32_t* h_sizes, uint8_t* h_sub) {
+  if (!c || !h_frame) return fail("null argument");
+  if (check_dims(fw, fh)) return -1;
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[0];
+  cudaStream_t st = l.stream;
+  const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
+  CK(c->cmp_frame.ensure(fb));
+  CK(c->cmp_sub.ensure(sb));
+  CK(c->cmp_saved.ensure(sb));
+  if (c->have_saved && (c->saved_w != fw || c->saved_h != fh)) c->have_saved = false;
+  CK(cudaMemcpyAsync(c->cmp_frame.p, h_frame, fb, cudaMemcpyHostToDevice, st));
+  jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, st);
+  c->launches++;
+  if (h_sub) CK(cudaMemcpyAsync(h_sub, c->cmp_sub.p, sb, cudaMemcpyDeviceToHost, st));
+  int n = 0;
+  if (!seed) {
+    if (!c->have_saved) return fail("compare_encode called before a seed frame was stored");
+    if (!outs_xywh || !h_out || !h_sizes) return fail("null output argument");
+    n = compare_on_device(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)c->cmp_saved.p, fw, fh, outs_xywh, st);
+    if (n < 0) return n;
+    const int nenc = std::min(n, JB_MAX_REGIONS);
+    if (nenc > 0) {
+      // a >99-region overflow returns raw sub-pixel boxes (brain.c:158-170); only encode well-formed crops
+      std::vector<int> ok;
+      for (int i = 0; i < nenc; i++) {
+        const int* a = outs_xywh + 4 * i;
+        bool good = a[0] >= 0 && a[1] >= 0 && a[2] > 0 && a[3] > 0 && a[2] % 16 == 0 && a[3] % 16 == 0 && a[0] + a[2] <= fw && a[1] + a[3] <= fh;
+        h_sizes[i] = 0;
+        if (good) ok.push_back(i);
+      }
+      if (!ok.empty()) {
+        const size_t dslot = (slot + 15) & ~(size_t)15;
+        CK(l.out.ensure(ok.size() * dslot));
+        CK(l.sizes.ensure(ok.size() * 4));
+        std::vector<int> areas;
+        for (int i : ok) areas.insert(areas.end(), outs_xywh + 4 * i, outs_xywh + 4 * i + 4);
+        if (jpegb200_encode_regions(c, (const uint8_t*)c->cmp_frame.p, fw, fh, areas.data(), (int)ok.size(), (uint8_t*)l.out.p, dslot,
+                                    (uint32_t*)l.sizes.p, st))
+          return -1;
+        std::vector<uint32_t> sz(ok.size());
+        CK(cudaMemcpyAsync(sz.data(), l.sizes.p, ok.size() * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (size_t k = 0; k < ok.size(); k++) {
+          h_sizes[ok[k]] = sz[k];
+          if (sz[k]) CK(cudaMemcpyAsync(h_out + (size_t)ok[k] * slot, (uint8_t*)l.out.p + k * dslot, sz[k], cudaMemcpyDeviceToHost, st));
+        }
+      }
+    }
+  }
+  CK(cudaMemcpyAsync(c->cmp_saved.p, c->cmp_sub.p, sb, cudaMemcpyDeviceToDevice, st));   // store(), brain.c:51-58
+  CK(cudaStreamSynchronize(st));
+  c->have_saved = true; c->saved_w = fw; c->saved_h = fh;
+  return n;
+}
+
+}  // extern "C"

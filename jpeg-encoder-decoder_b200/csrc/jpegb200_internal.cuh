@@ -1,0 +1,114 @@
+// jpegb200_internal.cuh — shared declarations of the sm_100a JPEG encode path.
+//
+// Vocabulary (reference main/encoder.c):
+//   job      one encode: a (x,y,w,h) crop of a BGR frame  ->  one JFIF file
+//   segment  one of the three non-interleaved scans of a job (Y, Cb, Cr; encoder.c:605-635)
+//   block    8x8 coefficient block, 64 int16 in zig-zag order, 128 B (encoder.c:81-112)
+//   chunk    256 consecutive blocks of one segment = the unit of work of the entropy kernels
+//   wave     the jobs that share one workspace and one chain of launches
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define JB_CHUNK_BLOCKS 256        // blocks per entropy-coding CTA (one block per thread)
+#define JB_STUFF_TILE 4096         // bytes of un-stuffed scan data per byte-stuffing CTA
+#define JB_MAX_REGIONS 100         // brain.c:115,158
+
+// One Huffman table exactly as the reference lays it out (include/structs.h:5-13), plus nothing.
+struct JbHuff {
+  int sym_freq[257];
+  int code_len[257];
+  int next[257];
+  int code_len_freq[32];
+  int sym_sorted[256];
+  int sym_code_len[256];
+  int sym_code[256];
+};
+static_assert(sizeof(JbHuff) == 6284, "huff_code layout");
+
+// Job descriptor (device memory, one per job of a wave).
+struct JbJob {
+  const uint8_t* src;   // frame base, B,G,R interleaved
+  uint32_t pitch;       // bytes per frame row (3 * frame width; encoder.c:132 uses the global WIDTH)
+  int x, y, w, h;       // crop, w and h multiples of 16
+  uint32_t coef_off;    // first int16 of this job's Y plane inside ws.coef (Cb at +w*h, Cr at +w*h*5/4)
+  uint32_t blk_off;     // first block id of this job (Y blocks, then Cb, then Cr) in ws.mask / ws.dcraw / ws.blkbits
+  uint32_t chunk_off;   // first chunk id of this job (Y chunks, then Cb, then Cr)
+  uint32_t tile_off;    // first byte-stuffing tile id of this job (3 segments x tiles_per_seg)
+  uint32_t tiles_per_seg;
+  uint32_t scratch_off; // first 32-bit word of this job's un-stuffed bitstream area in ws.scratch
+  uint32_t scratch_cap; // words available there
+  uint8_t* out;         // destination slot of the finished JFIF stream
+  uint32_t out_cap;     // bytes available there
+  uint32_t src_bytes;   // bytes readable from src (bounds the over-fetch of the aligned loader)
+};
+
+// Per-job results of the scan / layout kernels.
+struct JbJobState {
+  uint32_t seg_bits[3];      // entropy-coded bits per scan, before stuffing and padding
+  uint32_t seg_word[3];      // word offset of each scan inside the job's scratch area
+  uint32_t seg_out[3];       // byte offset of each scan's entropy data inside the output slot
+  uint32_t seg_ff[3];        // number of 0xFF data bytes (= stuffed zero bytes) per scan
+  uint32_t size;             // total bytes of the JFIF stream (0 on error)
+  uint32_t error;            // JB_ERR_* bits
+};
+
+enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4 };
+
+// Workspace of one wave (all device pointers).
+struct JbWs {
+  JbJob* jobs;
+  JbJobState* state;
+  int16_t* coef;        // zig-zagged quantised coefficients, DC differenced after k_symbol_stats
+  uint64_t* mask;       // per block: bit p set <=> zig-zag position p (1..63) is non-zero
+  int16_t* dcraw;       // per block: DC before differencing
+  uint32_t* blkbits;    // per block: exclusive prefix of code bits inside its chunk
+  uint32_t* chunk_bits; // per chunk: total bits
+  uint32_t* chunk_base; // per chunk: bit offset inside its segment
+  int* hist;            // per job: 4 x 257 symbol counts (luma DC, luma AC, chroma DC, chroma AC)
+  JbHuff* huff;         // per job: 4 tables in the same order
+  uint32_t* enc;        // per job: 4 x 256 packed (code << 5 | len)
+  uint32_t* scratch;    // un-stuffed scan bits, big-endian bytes
+  uint32_t* tile_ff;    // per tile: 0xFF count, then (after k_layout) exclusive prefix inside the segment
+};
+
+__host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
+__host__ __device__ inline uint32_t jb_nbc(int w, int h) { return (uint32_t)(w * h) / 256u; }
+__host__ __device__ inline uint32_t jb_chunks(uint32_t nblk) { return (nblk + JB_CHUNK_BLOCKS - 1) / JB_CHUNK_BLOCKS; }
+
+// Locate segment `s` of a job: block range, coefficient base.
+struct JbSeg {
+  uint32_t nblk;      // blocks in the segment
+  uint32_t blk0;      // id of its first block
+  uint32_t coef0;     // index of its first coefficient
+  uint32_t chunk0;    // id of its first chunk
+};
+__host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
+  uint32_t nby = jb_nby(j.w, j.h), nbc = jb_nbc(j.w, j.h);
+  uint32_t cy = jb_chunks(nby), cc = jb_chunks(nbc);
+  JbSeg g;
+  g.nblk = s == 0 ? nby : nbc;
+  g.blk0 = j.blk_off + (s == 0 ? 0u : s == 1 ? nby : nby + nbc);
+  g.coef0 = j.coef_off + 64u * (s == 0 ? 0u : s == 1 ? nby : nby + nbc);
+  g.chunk0 = j.chunk_off + (s == 0 ? 0u : s == 1 ? cy : cy + cc);
+  return g;
+}
+
+// ---- launchers (each enqueues on `st`; defined in the k_*.cu files) -------------------------------
+void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
+void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
+void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
+void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_block_bits(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
+void jb_launch_scan(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
+void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
+void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);
+void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
+
+// comparator (brain.c)
+void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, cudaStream_t st);
+void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, int sh, uint32_t* d_bits, cudaStream_t st);
+void jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs /*100*4*/, int* d_n, cudaStream_t st);
+void jb_launch_enlarge_adjust(int* d_area, int w, int h, cudaStream_t st);

@@ -1,0 +1,212 @@
+// k_huffman.cu — stage 2 of the encoder on sm_100a: symbol statistics and the four per-image
+// optimal Huffman tables (reference main/encoder.c:180-381).
+//
+//   k_symbol_stats   one thread per 8x8 block: DC prediction (encoder.c:168-177), DC category and
+//                    AC run/size symbols (encoder.c:303-358) accumulated in shared-memory histograms,
+//                    then merged into the job's four 257-bin histograms.
+//   k_build_huffman  one warp per table: exact replay of init_huff_table (encoder.c:180-301) — the
+//                    two-least-frequent selection with its (freq asc, index desc) tie-break, chain
+//                    merging, the 16-bit length limiter, the reserved code point, sym_sorted and
+//                    the canonical codes — leaving every field of huff_code as the reference does.
+#include "jpegb200_internal.cuh"
+#include "walk.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int dc_from_raw) {
+  __shared__ int h_dc[16];
+  __shared__ int h_ac[256];
+  const JbJob job = ws.jobs[blockIdx.y];
+  const uint32_t cy = jb_chunks(jb_nby(job.w, job.h)), cc = jb_chunks(jb_nbc(job.w, job.h));
+  uint32_t c = blockIdx.x;
+  if (c >= cy + 2 * cc) return;
+  const int s = c < cy ? 0 : (c < cy + cc ? 1 : 2);
+  c -= (s == 0 ? 0 : s == 1 ? cy : cy + cc);
+  const JbSeg seg = jb_seg(job, s);
+  const int tid = threadIdx.x;
+  if (tid < 16) h_dc[tid] = 0;
+  h_ac[tid] = 0;
+  __syncthreads();
+
+  const uint32_t b = c * JB_CHUNK_BLOCKS + tid;
+  if (b < seg.nblk) {
+    int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
+    int dc;
+    if (dc_from_raw) {                                   // encoder.c:168-177, plane-wide prediction
+      int cur = ws.dcraw[seg.blk0 + b];
+      int prev = b ? ws.dcraw[seg.blk0 + b - 1] : 0;
+      dc = cur - prev;
+      blk[0] = (int16_t)dc;
+    } else {
+      dc = blk[0];
+    }
+    atomicAdd(&h_dc[jb_category(dc)], 1);
+    struct V {
+      int* h;
+      __device__ void zrl(int n) { atomicAdd(&h[0xF0], n); }
+      __device__ void ac(int run, int v) { atomicAdd(&h[(run << 4) | jb_category(v)], 1); }
+      __device__ void eob() { atomicAdd(&h[0], 1); }
+    } vis{h_ac};
+    jb_walk_block(ws.mask[seg.blk0 + b], blk, vis);
+  }
+  __syncthreads();
+  int* g = ws.hist + (size_t)blockIdx.y * 4 * 257 + (s ? 2 * 257 : 0);
+  if (tid < 16 && h_dc[tid]) atomicAdd(&g[tid], h_dc[tid]);
+  if (h_ac[tid]) atomicAdd(&g[257 + tid], h_ac[tid]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One warp per table.  Shared-memory state per warp mirrors huff_code plus a tail[] array that
+// replaces the reference's walk to the end of v1's chain.
+struct TabSmem {
+  int freq[257 + 31];    // padded so that every lane can read 9 strided entries
+  int len[257 + 31];
+  int next[257];
+  int tail[257];
+  int grp[257 + 31];     // representative (chain head) of each symbol
+};
+
+constexpr int TAB_WARPS = 4;
+
+__global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int ntables) {
+  __shared__ TabSmem sm_all[TAB_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * TAB_WARPS + warp;
+  if (t >= ntables) return;
+  TabSmem& sm = sm_all[warp];
+  const int job = t >> 2, which = t & 3;
+  const int* hist = ws.hist + (size_t)t * 257;
+  JbHuff* hc = ws.huff + t;
+  JbJobState* state = ws.state + job;
+  (void)which;
+
+  for (int k = lane; k < 257 + 31; k += 32) {
+    int f = 0;
+    if (k < 256) f = hist[k];
+    else if (k == 256) f = 1;                          // reserved code point, encoder.c:367
+    sm.freq[k] = f;
+    sm.len[k] = 0;
+    sm.grp[k] = k;
+    if (k < 257) { sm.next[k] = -1; sm.tail[k] = k; }
+  }
+  __syncwarp();
+
+  // -- merge loop (encoder.c:190-228).  key = (freq, 511 - index): smallest key = least frequent,
+  //    ties to the LATER index, exactly the reference's ascending scan with '<='.
+  for (;;) {
+    unsigned long long best1 = ~0ull, best2 = ~0ull;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      int k = lane + 32 * j;
+      int f = sm.freq[k];
+      unsigned long long key = f ? (((unsigned long long)(unsigned)f << 32) | (unsigned)(511 - k)) : ~0ull;
+      if (key < best1) { best2 = best1; best1 = key; }
+      else if (key < best2) best2 = key;
+    }
+    // warp-wide two smallest
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, best1, o);
+      unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, best2, o);
+      unsigned long long lo = best1 < o1 ? best1 : o1;
+      unsigned long long hi = best1 < o1 ? o1 : best1;          // the larger of the two minima
+      unsigned long long m2 = best2 < o2 ? best2 : o2;
+      best1 = lo;
+      best2 = hi < m2 ? hi : m2;
+    }
+    if (best2 == ~0ull) break;
+    const int v1 = 511 - (int)(unsigned)(best1 & 0xFFFFFFFFull);
+    const int v2 = 511 - (int)(unsigned)(best2 & 0xFFFFFFFFull);
+    // every member of both chains gets one bit longer and now belongs to v1
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      int k = lane + 32 * j;
+      int g = sm.grp[k];
+      if (g == v1 || g == v2) { sm.len[k]++; sm.grp[k] = v1; }
+    }
+    if (lane == 0) {
+      sm.freq[v1] += sm.freq[v2];
+      sm.freq[v2] = 0;
+      sm.next[sm.tail[v1]] = v2;
+      sm.tail[v1] = sm.tail[v2];
+    }
+    __syncwarp();
+  }
+
+  // The rest is short and strictly sequential: lane 0 replays it, the warp copies results out.
+  __shared__ int s_clf[TAB_WARPS][32];
+  __shared__ int s_sorted[TAB_WARPS][256];
+  __shared__ int s_slen[TAB_WARPS][256];
+  __shared__ int s_code[TAB_WARPS][256];
+  int* clf = s_clf[warp];
+  int* sorted = s_sorted[warp];
+  int* slen = s_slen[warp];
+  int* code = s_code[warp];
+  for (int k = lane; k < 256; k += 32) { sorted[k] = -1; slen[k] = 0; code[k] = -1; }
+  clf[lane] = 0;
+  __syncwarp();
+  if (lane == 0) {
+    bool overflow = false;
+    for (int k = 0; k < 257; k++) {
+      int l = sm.len[k];
+      if (l > 31) { overflow = true; l = 31; }         // the reference would write past code_len_freq[32]
+      if (l) clf[l]++;
+    }
+    if (overflow) atomicOr(&state->error, (uint32_t)JB_ERR_CODELEN);
+    for (int i = 31; i > 16; i--)                        // encoder.c:239-254
+      while (clf[i] > 0) {
+        int j = i - 2;
+        while (clf[j] <= 0) j--;
+        clf[i] -= 2; clf[i - 1]++; clf[j + 1] += 2; clf[j]--;
+      }
+    { int i = 16; while (i > 0 && clf[i] == 0) i--; clf[i]--; }   // encoder.c:255-258
+    int n = 0;
+    for (int l = 1; l < 32; l++)                         // encoder.c:262-268
+      for (int k = 0; k < 256; k++) if (sm.len[k] == l) sorted[n++] = k;
+    int k = 0, cd = 0;
+    for (int l = 1; l <= 16; l++) {                      // encoder.c:271-276 and :280-300
+      for (int c = 0; c < clf[l] && k < 256 && sorted[k] >= 0; c++) { slen[sorted[k]] = l; code[sorted[k]] = cd++; k++; }
+      cd <<= 1;
+    }
+    if (k < 256 && sorted[k] < 0) sorted[255] = 0;       // encoder.c:277 writes sym_code_len[-1] == sym_sorted[255]
+  }
+  __syncwarp();
+  for (int k = lane; k < 257; k += 32) {
+    hc->sym_freq[k] = sm.freq[k];
+    hc->code_len[k] = sm.len[k];
+    hc->next[k] = sm.next[k];
+  }
+  hc->code_len_freq[lane] = clf[lane];
+  for (int k = lane; k < 256; k += 32) {
+    hc->sym_sorted[k] = sorted[k];
+    hc->sym_code_len[k] = slen[k];
+    hc->sym_code[k] = code[k];
+  }
+}
+
+// Pack (code, length) of every symbol for the entropy kernels; also used after the drop-in
+// write_jpg uploaded caller-provided tables.
+__global__ void k_pack_tables(JbWs ws, int ntables) {
+  const int t = blockIdx.x;
+  if (t >= ntables) return;
+  const JbHuff* hc = ws.huff + t;
+  const int k = threadIdx.x;
+  int l = hc->sym_code_len[k];
+  uint32_t e = 0;
+  if (l > 0 && l <= 16) e = ((uint32_t)hc->sym_code[k] << 5) | (uint32_t)l;
+  ws.enc[(size_t)t * 256 + k] = e;
+}
+
+}  // namespace
+
+void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st) {
+  k_symbol_stats<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
+}
+void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st) {
+  int nt = njobs * 4;
+  k_build_huffman<<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
+}
+void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st) {
+  k_pack_tables<<<njobs * 4, 256, 0, st>>>(ws, njobs * 4);
+}

@@ -1,0 +1,69 @@
+"""CPU suite, part 2: the drop-in boundary.  No compute calls (there is no GPU here):
+the library loads, exports every symbol the headers declare, and fails loudly without a device."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+pkg = importlib.import_module("jpeg-encoder-decoder_b200")
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\([^;{]*\)\s*;", txt)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(pkg.LIB_PATH):
+        pkg.build()
+    return pkg.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = set(_declared("jpegb200.h") + _declared("encoder.h") + _declared("brain.h"))
+    assert {"rgb_to_dct", "init_huffman", "write_jpg", "subsample", "store", "compare", "enlargeAdjust"} <= names
+    assert {"jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_compare_encode"} <= names
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert set(pkg.C_ABI_SYMBOLS) | set(pkg.REFERENCE_SYMBOLS) <= names
+
+
+def test_struct_layouts_match_reference_abi():
+    assert C.sizeof(pkg.HuffCode) == 6284          # reference include/structs.h:5-13, 1571 ints
+    assert C.sizeof(pkg.Area) == 16
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_device_is_a_loud_error(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.JpegB200Error, match="no CPU fallback"):
+        pkg.Encoder()
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing shipped may import, link or execute oracle/ (task rule ③)."""
+    bad = []
+    for base in ("jpeg-encoder-decoder_b200", "main", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            if "_obj" in dp or "__pycache__" in dp:
+                continue
+            for f in fs:
+                if f.endswith((".so", ".o", ".log", ".pyc")):
+                    continue
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                if re.search(r"liboracle|libref|cpu_checkers|oracle/_|#include\s+\"[^\"]*oracle", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad

@@ -1,0 +1,372 @@
+"""GPU suite: byte-for-byte parity of libjpegb200.so (through its C ABI) with the oracle and with the
+committed outputs of the reference.  Integer/byte work: the bar is bit-exact everywhere."""
+import ctypes as C
+import hashlib
+import importlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, sha
+from cpu_checkers import HUFF_FIELDS
+
+pytestmark = pytest.mark.gpu
+pkg = importlib.import_module("jpeg-encoder-decoder_b200")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pkg.RefAPI()
+
+
+@pytest.fixture(scope="module")
+def enc():
+    e = pkg.Encoder(0)
+    yield e
+    e.close()
+
+
+def _same_tables(a, b, tag):
+    for nm in ("luma", "chroma"):
+        for i in range(2):
+            for k in HUFF_FIELDS:
+                assert np.array_equal(a[nm][i][k], b[nm][i][k]), (tag, nm, i, k)
+
+
+def _check_against_oracle(api, oracle, img, area=None, tag=""):
+    got, want = api.encode(img, area), oracle.encode(img, area)
+    for p in ("Y", "Cb", "Cr"):
+        bad = int((got[p] != want[p]).sum())
+        assert bad == 0, (tag, p, "mismatching coefficients", bad, "max |d|", int(np.abs(got[p].astype(int) - want[p]).max()))
+    _same_tables(got, want, tag)
+    assert got["jpg"].tobytes() == want["jpg"].tobytes(), tag
+    return got
+
+
+# ------------------------------------------------------------------ reference entry points, sample images
+
+@pytest.mark.parametrize("key,src,order", [
+    ("sample_64x64_bgr", "64", "bgr"), ("sample_64x64_raw", "64", "raw"),
+    ("sample_640x640_bgr", "640", "bgr"), ("sample_640x640_raw", "640", "raw"),
+    ("sample_640x640_diffs_bgr", "640_diffs", "bgr"), ("sample_640x640_diffs_raw", "640_diffs", "raw")])
+def test_samples_byte_identical(api, oracle, frames, golden, key, src, order):
+    img = frames.sample_bgr(src) if order == "bgr" else frames.sample_rgb(src)
+    got = _check_against_oracle(api, oracle, img, tag=key)
+    g = golden["encode"][key]
+    assert (got["jpg"].size, sha(got["jpg"])) == (g["bytes"], g["sha256"])
+    assert sha(got["Y"].tobytes() + got["Cb"].tobytes() + got["Cr"].tobytes()) == g["planes_sha256"]
+    path = os.path.join(GOLD, key + ".jpg")
+    if os.path.exists(path):
+        assert got["jpg"].tobytes() == open(path, "rb").read()
+
+
+def test_stage_dumps_64(api, frames):
+    st = np.load(os.path.join(GOLD, "stages_64x64_bgr.npz"))
+    got = api.encode(frames.sample_bgr("64"))
+    for p in ("Y", "Cb", "Cr"):
+        assert np.array_equal(got[p], st[p]), p
+    for nm in ("luma", "chroma"):
+        for i in range(2):
+            for k in HUFF_FIELDS:
+                assert np.array_equal(got[nm][i][k], st[f"{nm}{i}_{k}"]), (nm, i, k)
+
+
+def test_write_jpg_writes_the_file_too(api, frames, tmp_path, golden):
+    p = str(tmp_path / "o.jpg")
+    got = api.encode(frames.sample_bgr("64"), path=p)
+    assert open(p, "rb").read() == got["jpg"].tobytes()
+    assert sha(got["jpg"]) == golden["encode"]["sample_64x64_bgr"]["sha256"]
+
+
+@pytest.mark.parametrize("key,w,h", [("tile_1920x1280_bgr", 1920, 1280), ("tile_3840x2160_bgr", 3840, 2160)])
+def test_tiles_byte_identical(api, frames, golden, key, w, h):
+    got = api.encode(frames.tile_bgr(w, h))
+    g = golden["encode"][key]
+    assert (got["jpg"].size, sha(got["jpg"])) == (g["bytes"], g["sha256"])
+    assert sha(got["Y"].tobytes() + got["Cb"].tobytes() + got["Cr"].tobytes()) == g["planes_sha256"]
+
+
+def test_crops_byte_identical(api, oracle, frames):
+    img = frames.sample_bgr("640_diffs")
+    for area in [(2, 36, 112, 432), (358, 66, 256, 336), (406, 476, 192, 160), (146, 412, 176, 144), (0, 0, 16, 16),
+                 (624, 624, 16, 16), (3, 5, 48, 32), (101, 7, 528, 16), (16, 32, 144, 48), (5, 0, 272, 640)]:
+        _check_against_oracle(api, oracle, img, area, tag=str(area))
+
+
+def _rand_img(rng, h, w, kind):
+    if kind == 0:
+        return rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    if kind == 1:   # grey: every pixel sits on an exact-integer colour boundary
+        return np.repeat(rng.integers(0, 256, (h, w, 1), dtype=np.uint8), 3, axis=2)
+    if kind == 2:   # flat 8x8 blocks: DC/(8*16) coincidences -> the exact-division path
+        v = rng.integers(0, 256, (h // 8, w // 8, 3), dtype=np.uint8)
+        return np.ascontiguousarray(np.kron(v, np.ones((8, 8, 1), np.uint8)))
+    if kind == 3:   # flat grey blocks: both at once
+        v = np.repeat(rng.integers(0, 256, (h // 8, w // 8, 1), dtype=np.uint8), 3, axis=2)
+        return np.ascontiguousarray(np.kron(v, np.ones((8, 8, 1), np.uint8)))
+    if kind == 4:   # extremes
+        return (rng.integers(0, 2, (h, w, 3), dtype=np.uint8) * 255).astype(np.uint8)
+    base = rng.integers(0, 256, (1, 1, 3)).astype(np.int32)
+    g = base + (np.arange(w)[None, :, None] * int(rng.integers(-2, 3)) + np.arange(h)[:, None, None] * int(rng.integers(-2, 3)))
+    return np.clip(g + rng.integers(-3, 4, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def test_random_images_vs_oracle(api, oracle):
+    rng = np.random.default_rng(2024)
+    sizes = [(16, 16), (48, 16), (16, 48), (144, 32), (128, 128), (272, 64), (320, 240), (400, 112)]
+    for it in range(48):
+        w, h = sizes[it % len(sizes)]
+        _check_against_oracle(api, oracle, _rand_img(rng, h, w, it % 6), tag=f"it{it} {w}x{h} kind{it % 6}")
+
+
+def test_constant_and_saturated_frames(api, oracle):
+    for v in (0, 1, 127, 128, 129, 254, 255):
+        _check_against_oracle(api, oracle, np.full((32, 48, 3), v, np.uint8), tag=f"const{v}")
+    img = np.zeros((64, 64, 3), np.uint8)
+    img[::2, ::2] = 255      # highest-frequency checkerboard: long codes, many 0xFF bytes
+    _check_against_oracle(api, oracle, img, tag="checker")
+
+
+@pytest.mark.parametrize("key", ["noise_64x64_f3", "ramp_64x64_f3", "noise_320x240_f3", "ramp_320x240_f3", "noise_48x16_f3",
+                                 "ramp_48x16_f3"])
+def test_small_synthetic_golden(api, frames, golden, key):
+    kind, dims, f = key.split("_")
+    w, h = map(int, dims.split("x"))
+    got = api.encode(frames.GENERATORS[kind](int(f[1:]), w, h))
+    g = golden["synthetic"][key]
+    assert (got["jpg"].size, sha(got["jpg"])) == (g["bytes"], g["sha256"])
+
+
+# ------------------------------------------------------------------ device table builder, direct fuzz
+
+def test_table_builder_fuzz(enc, oracle):
+    rng = np.random.default_rng(7)
+    freqs = []
+    for it in range(600):
+        nsym = int(rng.integers(1, 255 if it % 3 else 20))     # <=254: beyond that the reference itself is UB
+        f = np.zeros(257, np.int64)
+        idx = rng.choice(256, nsym, replace=False)
+        style = it % 5
+        if style == 0:
+            f[idx] = rng.integers(1, 4, nsym)
+        elif style == 1:
+            f[idx] = rng.integers(1, 100000, nsym)
+        elif style == 2:
+            f[idx] = np.minimum(1.6 ** np.minimum(np.arange(nsym), 40), 2 ** 20).astype(np.int64)
+        elif style == 3:
+            f[idx] = 1
+        else:
+            f[idx] = rng.geometric(0.02, nsym)
+        f[256] = 1
+        freqs.append(f)
+    freqs = np.array(freqs, np.int32)
+    got = enc.build_tables(freqs)
+    for it in range(len(freqs)):
+        want = oracle.build_table(freqs[it])
+        for k in HUFF_FIELDS:
+            assert np.array_equal(got[it][k], want[k]), (it, k)
+
+
+# ------------------------------------------------------------------ batched C ABI
+
+def _torch_batch(frames_np):
+    import torch
+    return torch.from_numpy(frames_np).cuda()
+
+
+def test_batch_device_matches_oracle_and_golden(enc, oracle, frames, golden):
+    import torch
+    w, h = 1920, 1280
+    idx = {"natural": [0, 1, 121, 1023], "noise": [0, 1], "ramp": [0, 1]}
+    imgs, keys = [], []
+    for kind, fs in idx.items():
+        for f in fs:
+            imgs.append(frames.GENERATORS[kind](f, w, h))
+            keys.append(f"{kind}_{w}x{h}_f{f}")
+    batch = np.stack(imgs)
+    d_in = _torch_batch(batch)
+    slot = w * h
+    d_out = torch.zeros((len(imgs), slot), dtype=torch.uint8, device="cuda")
+    d_sizes = torch.zeros(len(imgs), dtype=torch.int32, device="cuda")
+    enc.configure(3, 2)      # several waves over two lanes, last wave ragged
+    enc.encode_batch_ptr(d_in.data_ptr(), len(imgs), w, h, w * h * 3, d_out.data_ptr(), slot, d_sizes.data_ptr(),
+                         torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    sizes = d_sizes.cpu().numpy()
+    out = d_out.cpu().numpy()
+    for i, key in enumerate(keys):
+        g = golden["synthetic"].get(key)
+        jpg = out[i, : sizes[i]]
+        if g:
+            assert (int(sizes[i]), sha(jpg)) == (g["bytes"], g["sha256"]), key
+    # and two of them against the oracle directly
+    for i in (1, 4):
+        assert out[i, : sizes[i]].tobytes() == oracle.encode(imgs[i])["jpg"].tobytes(), keys[i]
+    enc.configure(8, 3)
+
+
+def test_batch_host_equals_device_path(enc, oracle, frames):
+    rng = np.random.default_rng(5)
+    w, h = 320, 240
+    batch = np.stack([_rand_img(rng, h, w, k % 6) for k in range(21)])
+    enc.configure(4, 3)
+    jpgs = enc.encode_frames(batch)
+    for k in range(len(batch)):
+        assert jpgs[k] == oracle.encode(batch[k])["jpg"].tobytes(), k
+    enc.configure(8, 3)
+
+
+def test_batch_4k_golden(enc, frames, golden):
+    w, h = 3840, 2160 - 2160 % 16    # 2160 = 135 * 16
+    imgs = np.stack([frames.natural_frame(0, 3840, 2160), frames.noise_frame(0, 3840, 2160), frames.natural_frame(7, 3840, 2160)])
+    jpgs = enc.encode_frames(imgs, slot=3840 * 2160)
+    for j, key in zip(jpgs, ["natural_3840x2160_f0", "noise_3840x2160_f0", "natural_3840x2160_f7"]):
+        g = golden["synthetic"][key]
+        assert (len(j), sha(j)) == (g["bytes"], g["sha256"]), key
+
+
+def test_slot_too_small_reports_zero_size(enc, frames):
+    import torch
+    img = frames.noise_frame(1, 64, 64)
+    d_in = _torch_batch(img[None])
+    d_out = torch.zeros((1, 1024), dtype=torch.uint8, device="cuda")
+    d_sizes = torch.full((1,), 7, dtype=torch.int32, device="cuda")
+    enc.encode_batch_ptr(d_in.data_ptr(), 1, 64, 64, 64 * 64 * 3, d_out.data_ptr(), 1024, d_sizes.data_ptr(), 0)
+    torch.cuda.synchronize()
+    assert int(d_sizes[0]) == 0
+
+
+def test_bad_dimensions_are_rejected(enc):
+    with pytest.raises(pkg.JpegB200Error, match="multiples of 16"):
+        enc.encode_batch_host(np.zeros((1, 20, 16, 3), np.uint8), 4096)
+
+
+def test_full_batch_properties(enc, frames):
+    """BASELINE size (1024 x 1920x1280, natural class) through size-independent properties:
+    (a) frame f and f+9600 wrap to the same pixels -> identical streams; (b) every stream is a
+    decodable baseline JPEG whose pixels match the input (PSNR), (c) all sizes non-zero and < slot;
+    (d) a checksum over all streams is reproducible across two runs with different wave/lane shapes."""
+    import torch
+    from PIL import Image
+    w, h, n = 1920, 1280, 1024
+    tile = torch.from_numpy(frames.tile_bgr(w, h)).cuda()
+    d_in = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+    for f in range(n):
+        dx, dy = frames.natural_shift(f, w, h)
+        d_in[f] = torch.roll(tile, shifts=(dy, dx), dims=(0, 1))
+    slot = 512 * 1024
+    digests = []
+    for (G, L) in ((8, 3), (5, 2)):
+        enc.configure(G, L)
+        d_out = torch.zeros((n, slot), dtype=torch.uint8, device="cuda")
+        d_sizes = torch.zeros(n, dtype=torch.int32, device="cuda")
+        enc.encode_batch_ptr(d_in.data_ptr(), n, w, h, w * h * 3, d_out.data_ptr(), slot, d_sizes.data_ptr(),
+                             torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        sizes = d_sizes.cpu().numpy()
+        assert (sizes > 0).all() and (sizes < slot).all()
+        out = d_out.cpu().numpy()
+        hsh = hashlib.sha256()
+        for f in range(n):
+            hsh.update(out[f, : sizes[f]].tobytes())
+        digests.append(hsh.hexdigest())
+    assert digests[0] == digests[1]
+    # (a) frame 0 == the un-shifted tile, whose reference output is a committed golden
+    import json
+    g = json.load(open(os.path.join(GOLD, "golden.json")))["encode"]["tile_1920x1280_bgr"]
+    assert (int(sizes[0]), sha(out[0, : sizes[0]])) == (g["bytes"], g["sha256"])
+    # (b) decode a few and compare with the input
+    for f in (0, 37, 500, 1023):
+        im = np.asarray(Image.open(io.BytesIO(out[f, : sizes[f]].tobytes())).convert("RGB")).astype(np.float64)
+        src = d_in[f].cpu().numpy()[..., ::-1].astype(np.float64)
+        psnr = 10 * np.log10(255.0 ** 2 / np.mean((im - src) ** 2))
+        assert psnr > 28.0, (f, psnr)
+    enc.configure(8, 3)
+
+
+# ------------------------------------------------------------------ comparator
+
+def test_comparator_golden_flow(api, enc, frames, golden):
+    g = golden["comparator"]["640_A_vs_diffs"]
+    A, B = frames.sample_bgr("640"), frames.sample_bgr("640_diffs")
+    subA, subB = api.subsample(A), api.subsample(B)
+    assert sha(b"P6\n160 160\n255\n" + subA.tobytes()) == g["subA_ppm_sha256"]
+    assert sha(b"P6\n160 160\n255\n" + subB.tobytes()) == g["subB_ppm_sha256"]
+    saved = api.store(subA, 640, 640)
+    assert np.array_equal(saved, subA)
+    n, outs = api.compare(subB, saved, 640, 640)
+    assert n == g["n"] and [list(o) for o in outs[:n]] == g["regions"]
+    assert all(o == (-1, -1, -1, -1) for o in outs[n:])
+    for i in range(n):
+        jpg = api.encode(B, outs[i])["jpg"].tobytes()
+        assert jpg == open(os.path.join(GOLD, f"region{i}_640.jpg"), "rb").read()
+    # the fused device path (app_main's loop body)
+    enc.compare_encode(A, seed=True)
+    regions, jpgs, sub = enc.compare_encode(B)
+    assert [list(r) for r in regions] == g["regions"]
+    assert np.array_equal(sub, subB)
+    for i, j in enumerate(jpgs):
+        assert sha(j) == g["jpgs"][i]["sha256"]
+    # identical frame next: nothing changed
+    regions, jpgs, _ = enc.compare_encode(B)
+    assert regions == []
+
+
+def test_subsample_ppm_file(api, frames, tmp_path, golden):
+    p = str(tmp_path / "sub.ppm")
+    api.subsample(frames.sample_bgr("640"), path=p)
+    assert sha(open(p, "rb").read()) == golden["comparator"]["640_A_vs_diffs"]["subA_ppm_sha256"]
+
+
+def test_comparator_micro_cases(api, golden):
+    for nm, case in golden["comparator"]["micro_128"].items():
+        if nm == "dark_on_bright":
+            s = np.full((32, 32, 3), 255, np.uint8)
+            s[4:16, 4:16] = 0
+            n, outs = api.compare(s, np.full((32, 32, 3), 255, np.uint8), 128, 128)
+        else:
+            s = np.zeros((32, 32, 3), np.uint8)
+            for r in case["rects"]:
+                s[r[2]:r[3] + 1, r[0]:r[1] + 1] = 255
+            n, outs = api.compare(s, np.zeros_like(s), 128, 128)
+        assert n == case["n"] and [list(o) for o in outs[:n]] == case["regions"], nm
+
+
+def test_comparator_fuzz_vs_oracle(api, oracle):
+    rng = np.random.default_rng(99)
+    for it in range(120):
+        W, H = 16 * int(rng.integers(2, 21)), 16 * int(rng.integers(2, 16))
+        sw, sh = W // 4, H // 4
+        saved = rng.integers(0, 256, (sh, sw, 3), dtype=np.uint8)
+        sub = saved.copy()
+        style = it % 4
+        if style == 0:
+            for _ in range(int(rng.integers(1, 8))):
+                x0, y0 = int(rng.integers(0, sw)), int(rng.integers(0, sh))
+                x1, y1 = min(sw, x0 + int(rng.integers(1, 20))), min(sh, y0 + int(rng.integers(1, 20)))
+                sub[y0:y1, x0:x1] = rng.integers(0, 256, 3, dtype=np.uint8)
+        elif style == 1:    # salt: many tiny regions -> the >99 overflow path
+            m = rng.random((sh, sw)) < float(rng.uniform(0.01, 0.3))
+            sub[m] = 255 - sub[m]
+        elif style == 2:    # perturbations around the 600 threshold
+            sub = np.clip(sub.astype(np.int32) + rng.integers(-14, 15, sub.shape), 0, 255).astype(np.uint8)
+        else:               # right/bottom edge runs
+            sub[:, sw - int(rng.integers(1, 4)):] = 255 - sub[:, sw - 3:][:, :1]
+            sub[sh - 1, :] = 255 - sub[sh - 1, :]
+        assert api.compare(sub, saved, W, H) == oracle.compare(sub, saved, W, H), (it, W, H)
+
+
+def test_enlarge_adjust_and_subsample_vs_oracle(api, oracle):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (64, 96, 3), dtype=np.uint8)
+    assert np.array_equal(api.subsample(img), oracle.subsample(img))
+    for _ in range(40):
+        W, H = 16 * int(rng.integers(2, 40)), 16 * int(rng.integers(2, 40))
+        x0, y0 = int(rng.integers(0, W // 4)), int(rng.integers(0, H // 4))
+        x1, y1 = int(rng.integers(x0, W // 4)), int(rng.integers(y0, H // 4))
+        assert api.enlarge_adjust((x0, y0, x1, y1), W, H) == oracle.enlarge_adjust((x0, y0, x1, y1), W, H)

@@ -34,6 +34,11 @@ int jpegb200_configure(jpegb200_ctx *ctx, int frames_per_wave, int lanes);
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
 
+/* CUDA-event timing of the dominant kernel (k_bgr_to_coef) on the stream it is launched on: switch on,
+ * run, then read the summed duration and the number of launches timed (also resets the record). */
+int jpegb200_set_timing(jpegb200_ctx *ctx, int on);
+int jpegb200_get_timing(jpegb200_ctx *ctx, double *ms_total, uint64_t *launches);
+
 /* ---- batched encode, device resident (the fast path) -------------------------------------------
  * Replaces n x { rgb_to_dct (encoder.c:158) ; init_huffman (:360) ; write_jpg (:549) } with
  * dims = {0,0,w,h} on n independent frames.

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/jpegb200.h"
@@ -161,6 +162,9 @@ struct jpegb200_ctx {
   std::vector<Lane> lanes;
   cudaEvent_t fork = nullptr;
   uint64_t launches = 0;
+  // optional CUDA-event timing of the dominant kernel (k_bgr_to_coef), one event pair per launch
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed, spare;
   // comparator state
   DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_bits, cmp_outs;
   PinBuf cmp_host;
@@ -191,7 +195,14 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (from == FROM_PIXELS) {
+    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+    if (c->timing) {
+      if (!c->spare.empty()) { ev = c->spare.back(); c->spare.pop_back(); }
+      else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
+      CK(cudaEventRecord(ev.first, st));
+    }
     jb_launch_dct(ws, njobs, max_w, max_h, st);
+    if (c->timing) { CK(cudaEventRecord(ev.second, st)); c->timed.push_back(ev); }
     c->launches++;
   } else {
     jb_launch_plane_masks(ws, njobs, max_blocks, st);
@@ -305,6 +316,29 @@ int jpegb200_configure(jpegb200_ctx* c, int frames_per_wave, int lanes) {
 }
 
 uint64_t jpegb200_launch_count(const jpegb200_ctx* c) { return c ? c->launches : 0; }
+
+int jpegb200_set_timing(jpegb200_ctx* c, int on) {
+  if (!c) return fail("null ctx");
+  c->timing = on != 0;
+  return 0;
+}
+
+int jpegb200_get_timing(jpegb200_ctx* c, double* ms_total, uint64_t* launches) {
+  if (!c || !ms_total || !launches) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  double sum = 0;
+  for (auto& ev : c->timed) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    sum += ms;
+    c->spare.push_back(ev);
+  }
+  *ms_total = sum;
+  *launches = c->timed.size();
+  c->timed.clear();
+  return 0;
+}
 
 int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, int h, size_t frame_stride, uint8_t* d_out, size_t slot,
                           uint32_t* d_sizes, void* stream) {

@@ -36,8 +36,11 @@ uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
 
 /* CUDA-event timing of the dominant kernel (k_bgr_to_coef) on the stream it is launched on: switch on,
  * run, then read the summed duration and the number of launches timed (also resets the record). */
-int jpegb200_set_timing(jpegb200_ctx *ctx, int on);
+int jpegb200_set_timing(jpegb200_ctx *ctx, int level);   /* 0 off, 1 = k_bgr_to_coef, 2 = every stage */
 int jpegb200_get_timing(jpegb200_ctx *ctx, double *ms_total, uint64_t *launches);
+/* Per-stage sums; index: 0 dct, 1 plane masks, 2 symbol stats, 3 huffman build, 4 table pack, 5 block bits,
+ * 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff.  ms and n have 16 entries. */
+int jpegb200_get_stage_timing(jpegb200_ctx *ctx, double *ms, uint64_t *n);
 
 /* ---- batched encode, device resident (the fast path) -------------------------------------------
  * Replaces n x { rgb_to_dct (encoder.c:158) ; init_huffman (:360) ; write_jpg (:549) } with

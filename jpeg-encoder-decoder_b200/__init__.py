@@ -25,7 +25,7 @@ ROOT = os.path.dirname(_HERE)
 
 C_ABI_SYMBOLS = [
     "jpegb200_create", "jpegb200_destroy", "jpegb200_last_error", "jpegb200_configure", "jpegb200_launch_count",
-    "jpegb200_set_timing", "jpegb200_get_timing",
+    "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing",
     "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_regions",
     "jpegb200_stage_dct", "jpegb200_stage_huffman", "jpegb200_stage_write", "jpegb200_debug_build_tables",
     "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode",

@@ -163,8 +163,9 @@ struct jpegb200_ctx {
   cudaEvent_t fork = nullptr;
   uint64_t launches = 0;
   // optional CUDA-event timing of the dominant kernel (k_bgr_to_coef), one event pair per launch
-  bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed, spare;
+  int timing = 0;             // 0 off, 1 = k_bgr_to_coef only, 2 = every stage
+  std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
   // comparator state
   DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_bits, cmp_outs;
   PinBuf cmp_host;
@@ -173,6 +174,8 @@ struct jpegb200_ctx {
 };
 
 namespace {
+
+enum ChainFrom { FROM_PIXELS, FROM_PLANES_STATS, FROM_PLANES_WRITE };
 
 int make_lanes(jpegb200_ctx* c, int n) {
   for (auto& l : c->lanes) l.release();
@@ -186,7 +189,29 @@ int make_lanes(jpegb200_ctx* c, int n) {
   return 0;
 }
 
-enum ChainFrom { FROM_PIXELS, FROM_PLANES_STATS, FROM_PLANES_WRITE };
+// Stage ids for the optional per-kernel CUDA-event timing (jpegb200_get_stage_timing).
+enum Stage { ST_DCT = 0, ST_MASKS, ST_STATS, ST_HUFF, ST_TABLES, ST_BITS, ST_SCAN, ST_PACK, ST_COUNTFF, ST_LAYOUT, ST_STUFF, ST_COUNT };
+
+struct StageTimer {
+  jpegb200_ctx* c;
+  cudaStream_t st;
+  int stage;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
+  bool on;
+  StageTimer(jpegb200_ctx* c_, cudaStream_t st_, int stage_) : c(c_), st(st_), stage(stage_) {
+    on = c->timing == 2 || (c->timing == 1 && stage == ST_DCT);
+    if (!on) return;
+    if (!c->spare.empty()) { ev = c->spare.back(); c->spare.pop_back(); }
+    else { cudaEventCreate(&ev.first); cudaEventCreate(&ev.second); }
+    cudaEventRecord(ev.first, st);
+  }
+  ~StageTimer() {
+    c->launches++;
+    if (!on) return;
+    cudaEventRecord(ev.second, st);
+    c->timed.push_back({stage, ev});
+  }
+};
 
 // Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
 int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
@@ -194,36 +219,21 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
-  if (from == FROM_PIXELS) {
-    std::pair<cudaEvent_t, cudaEvent_t> ev{nullptr, nullptr};
-    if (c->timing) {
-      if (!c->spare.empty()) { ev = c->spare.back(); c->spare.pop_back(); }
-      else { CK(cudaEventCreate(&ev.first)); CK(cudaEventCreate(&ev.second)); }
-      CK(cudaEventRecord(ev.first, st));
-    }
-    jb_launch_dct(ws, njobs, max_w, max_h, st);
-    if (c->timing) { CK(cudaEventRecord(ev.second, st)); c->timed.push_back(ev); }
-    c->launches++;
-  } else {
-    jb_launch_plane_masks(ws, njobs, max_blocks, st);
-    c->launches++;
-  }
+  if (from == FROM_PIXELS) { StageTimer t(c, st, ST_DCT); jb_launch_dct(ws, njobs, max_w, max_h, st); }
+  else { StageTimer t(c, st, ST_MASKS); jb_launch_plane_masks(ws, njobs, max_blocks, st); }
   if (from != FROM_PLANES_WRITE) {
-    jb_launch_symbol_stats(ws, njobs, max_chunks, from == FROM_PIXELS ? 1 : 0, st);
-    c->launches++;
+    { StageTimer t(c, st, ST_STATS); jb_launch_symbol_stats(ws, njobs, max_chunks, from == FROM_PIXELS ? 1 : 0, st); }
     if (stop_after_dct) { CK(cudaGetLastError()); return 0; }
-    jb_launch_build_huffman(ws, njobs, st);
-    c->launches++;
+    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, st); }
     if (stop_after_tables) { CK(cudaGetLastError()); return 0; }
   }
-  jb_launch_pack_tables(ws, njobs, st);
-  jb_launch_block_bits(ws, njobs, max_chunks, st);
-  jb_launch_scan(ws, njobs, st);
-  jb_launch_pack(ws, njobs, max_chunks, st);
-  jb_launch_count_ff(ws, njobs, 8, st);
-  jb_launch_layout(ws, njobs, d_sizes, st);
-  jb_launch_stuff(ws, njobs, 8, st);
-  c->launches += 7;
+  { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
+  { StageTimer t(c, st, ST_BITS); jb_launch_block_bits(ws, njobs, max_chunks, st); }
+  { StageTimer t(c, st, ST_SCAN); jb_launch_scan(ws, njobs, st); }
+  { StageTimer t(c, st, ST_PACK); jb_launch_pack(ws, njobs, max_chunks, st); }
+  { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
+  { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
+  { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, 8, st); }
   CK(cudaGetLastError());
   return 0;
 }
@@ -317,26 +327,35 @@ int jpegb200_configure(jpegb200_ctx* c, int frames_per_wave, int lanes) {
 
 uint64_t jpegb200_launch_count(const jpegb200_ctx* c) { return c ? c->launches : 0; }
 
-int jpegb200_set_timing(jpegb200_ctx* c, int on) {
+int jpegb200_set_timing(jpegb200_ctx* c, int level) {
   if (!c) return fail("null ctx");
-  c->timing = on != 0;
+  c->timing = level < 0 ? 0 : level > 2 ? 2 : level;
+  return 0;
+}
+
+int jpegb200_get_stage_timing(jpegb200_ctx* c, double* ms /*[16]*/, uint64_t* n /*[16]*/) {
+  if (!c || !ms || !n) return fail("null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  for (int i = 0; i < 16; i++) { ms[i] = 0; n[i] = 0; }
+  for (auto& rec : c->timed) {
+    float t = 0;
+    CK(cudaEventElapsedTime(&t, rec.second.first, rec.second.second));
+    ms[rec.first] += t;
+    n[rec.first]++;
+    c->spare.push_back(rec.second);
+  }
+  c->timed.clear();
   return 0;
 }
 
 int jpegb200_get_timing(jpegb200_ctx* c, double* ms_total, uint64_t* launches) {
-  if (!c || !ms_total || !launches) return fail("null argument");
-  CK(cudaSetDevice(c->device));
-  CK(cudaDeviceSynchronize());
-  double sum = 0;
-  for (auto& ev : c->timed) {
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
-    sum += ms;
-    c->spare.push_back(ev);
-  }
-  *ms_total = sum;
-  *launches = c->timed.size();
-  c->timed.clear();
+  double ms[16];
+  uint64_t n[16];
+  if (!ms_total || !launches) return fail("null argument");
+  if (jpegb200_get_stage_timing(c, ms, n)) return -1;
+  *ms_total = ms[0];
+  *launches = n[0];
   return 0;
 }
 

@@ -31,6 +31,12 @@ const char *jpegb200_last_error(void);
  * lanes: independent streams/workspaces the waves rotate over (default 3). */
 int jpegb200_configure(jpegb200_ctx *ctx, int frames_per_wave, int lanes);
 
+/* DCT arithmetic: 0 (default) = FP32 filter transform + literal FP64 recomputation of every block the
+ * filter cannot decide (same bytes); 1 = literal FP64 chain of encoder.c:87-108 for every block. */
+int jpegb200_set_exact_dct(jpegb200_ctx *ctx, int on);
+/* Diagnostics: blocks that the last wave of `lane` sent to the literal chain. */
+int jpegb200_debug_fix_count(jpegb200_ctx *ctx, int lane, uint32_t *count);
+
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
 
@@ -39,7 +45,7 @@ uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
 int jpegb200_set_timing(jpegb200_ctx *ctx, int level);   /* 0 off, 1 = k_bgr_to_coef, 2 = every stage */
 int jpegb200_get_timing(jpegb200_ctx *ctx, double *ms_total, uint64_t *launches);
 /* Per-stage sums; index: 0 dct, 1 plane masks, 2 symbol stats, 3 huffman build, 4 table pack, 5 block bits,
- * 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff.  ms and n have 16 entries. */
+ * 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff, 11 fix-up of undecided blocks.  ms and n have 16 entries. */
 int jpegb200_get_stage_timing(jpegb200_ctx *ctx, double *ms, uint64_t *n);
 
 /* ---- batched encode, device resident (the fast path) -------------------------------------------

@@ -66,7 +66,7 @@ struct WaveDims {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr, sizes_ready = nullptr;
-  DevBuf jobs, state_hist, coef, mask, dcraw, blkbits, chunk_bits, chunk_base, huff, enc, scratch, tile_ff;
+  DevBuf jobs, state_hist, coef, mask, dcraw, blkbits, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
@@ -77,7 +77,8 @@ struct Lane {
   cudaError_t ensure(const WaveDims& d) {
     cudaError_t e;
     if ((e = jobs.ensure(d.njobs * sizeof(JbJob))) != cudaSuccess) return e;
-    if ((e = state_hist.ensure(d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int)))) != cudaSuccess) return e;
+    if ((e = state_hist.ensure(d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int)) + 16)) != cudaSuccess) return e;
+    if ((e = fix.ensure(d.blocks * sizeof(uint2))) != cudaSuccess) return e;
     if ((e = coef.ensure(d.coefs * sizeof(int16_t))) != cudaSuccess) return e;
     if ((e = mask.ensure(d.blocks * sizeof(uint64_t))) != cudaSuccess) return e;
     if ((e = dcraw.ensure(d.blocks * sizeof(int16_t))) != cudaSuccess) return e;
@@ -88,7 +89,7 @@ struct Lane {
     if ((e = enc.ensure(d.njobs * 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = scratch.ensure(d.scratch_words * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = tile_ff.ensure(d.tiles * sizeof(uint32_t))) != cudaSuccess) return e;
-    sh_bytes = d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int));
+    sh_bytes = d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int)) + 16;
     ws.jobs = (JbJob*)jobs.p;
     ws.state = (JbJobState*)state_hist.p;
     ws.hist = (int*)((char*)state_hist.p + d.njobs * sizeof(JbJobState));
@@ -102,10 +103,12 @@ struct Lane {
     ws.enc = (uint32_t*)enc.p;
     ws.scratch = (uint32_t*)scratch.p;
     ws.tile_ff = (uint32_t*)tile_ff.p;
+    ws.fix_count = (uint32_t*)((char*)state_hist.p + sh_bytes - 16);
+    ws.fix_list = (uint2*)fix.p;
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &blkbits, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &blkbits, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &in, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -159,6 +162,7 @@ __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t fram
 struct jpegb200_ctx {
   int device = 0;
   int frames_per_wave = 8;
+  int exact_dct = 0;          // 1 = literal FP64 chain for every block (the on-device checker of the fast path)
   std::vector<Lane> lanes;
   cudaEvent_t fork = nullptr;
   uint64_t launches = 0;
@@ -190,7 +194,7 @@ int make_lanes(jpegb200_ctx* c, int n) {
 }
 
 // Stage ids for the optional per-kernel CUDA-event timing (jpegb200_get_stage_timing).
-enum Stage { ST_DCT = 0, ST_MASKS, ST_STATS, ST_HUFF, ST_TABLES, ST_BITS, ST_SCAN, ST_PACK, ST_COUNTFF, ST_LAYOUT, ST_STUFF, ST_COUNT };
+enum Stage { ST_DCT = 0, ST_MASKS, ST_STATS, ST_HUFF, ST_TABLES, ST_BITS, ST_SCAN, ST_PACK, ST_COUNTFF, ST_LAYOUT, ST_STUFF, ST_FIX, ST_COUNT };
 
 struct StageTimer {
   jpegb200_ctx* c;
@@ -219,7 +223,13 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
-  if (from == FROM_PIXELS) { StageTimer t(c, st, ST_DCT); jb_launch_dct(ws, njobs, max_w, max_h, st); }
+  if (from == FROM_PIXELS) {
+    if (c->exact_dct) { StageTimer t(c, st, ST_DCT); jb_launch_dct(ws, njobs, max_w, max_h, st); }
+    else {
+      { StageTimer t(c, st, ST_DCT); jb_launch_dct_fast(ws, njobs, max_w, max_h, st); }
+      { StageTimer t(c, st, ST_FIX); jb_launch_fix_blocks(ws, st); }
+    }
+  }
   else { StageTimer t(c, st, ST_MASKS); jb_launch_plane_masks(ws, njobs, max_blocks, st); }
   if (from != FROM_PLANES_WRITE) {
     { StageTimer t(c, st, ST_STATS); jb_launch_symbol_stats(ws, njobs, max_chunks, from == FROM_PIXELS ? 1 : 0, st); }
@@ -326,6 +336,22 @@ int jpegb200_configure(jpegb200_ctx* c, int frames_per_wave, int lanes) {
 }
 
 uint64_t jpegb200_launch_count(const jpegb200_ctx* c) { return c ? c->launches : 0; }
+
+int jpegb200_set_exact_dct(jpegb200_ctx* c, int on) {
+  if (!c) return fail("null ctx");
+  c->exact_dct = on != 0;
+  return 0;
+}
+
+int jpegb200_debug_fix_count(jpegb200_ctx* c, int lane, uint32_t* count) {
+  if (!c || !count || lane < 0 || lane >= (int)c->lanes.size()) return fail("bad argument");
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[lane];
+  CK(cudaStreamSynchronize(l.stream));
+  *count = 0;
+  if (l.ws.fix_count) CK(cudaMemcpy(count, l.ws.fix_count, 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 int jpegb200_set_timing(jpegb200_ctx* c, int level) {
   if (!c) return fail("null ctx");

@@ -70,6 +70,8 @@ struct JbWs {
   uint32_t* enc;        // per job: 4 x 256 packed (code << 5 | len)
   uint32_t* scratch;    // un-stuffed scan bits, big-endian bytes
   uint32_t* tile_ff;    // per tile: 0xFF count, then (after k_layout) exclusive prefix inside the segment
+  uint32_t* fix_count;  // per wave: number of entries in fix_list (zeroed with the state block)
+  uint2* fix_list;      // per wave: (job, block id inside the job) of blocks the fast DCT could not decide
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -96,6 +98,8 @@ __host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
 
 // ---- launchers (each enqueues on `st`; defined in the k_*.cu files) -------------------------------
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
+void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
+void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st);
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
 void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st);

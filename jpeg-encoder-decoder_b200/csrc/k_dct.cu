@@ -24,6 +24,8 @@
 // conflict-free shared-memory buffer.
 #include "jpegb200_internal.cuh"
 #include "tables.cuh"
+#include "fast_tables.cuh"
+#include <utility>
 
 namespace {
 
@@ -297,12 +299,370 @@ __global__ void k_plane_masks(JbWs ws) {
   if (valid && i == 0) ws.mask[job.blk_off + blk] = (uint64_t)wv | ((uint64_t)other << 32);
 }
 
+
+// =================================================================================================
+// Fast path: k_bgr_to_coef_fast + k_fix_blocks.
+//
+// The reference's value of a coefficient is v = RN-chain(...) (encoder.c:87-108); the output is trunc(v).
+// The fast kernel computes d*K with an FP32 Arai-Agui-Nakajima flow whose worst-case distance from v is
+// 3.8e-5 (tools/analysis/aan_error_bound.py mirrors the code below operation for operation).  The
+// two products d*KLO and d*KHI (K(1 -+ 2^-14)) therefore bracket v whenever |v| >= 1 - 4e-5; when both
+// floor to the same integer that integer decides trunc(v).  A block with any coefficient whose two floors differ is
+// appended to the wave's fix list and recomputed by k_fix_blocks with the literal FP64 chain (block_dct).
+// DC is an exact rational (sum/128, sum/136) that ties once in ~128 blocks, so it is always taken through
+// the literal chain (S*s)*s/4/q (encoder.c:104-108), which costs a handful of FP64 operations per block.
+//
+// Colour: 1000*Y and 31250*{Cb,Cr} are dot products of the packed B,G,R bytes (IDP.2A straight from the
+// 32-bit words, no unpacking); floor(n/D) is one FFMA.RZ against 2^23 with an upward-rounded reciprocal
+// and remainder-zero candidates are screened with one IMAD (both verified exhaustively in
+// tools/analysis/colour_fastpath_check.py).  A patch with a candidate replays ycc_pixel (exact).
+constexpr int FT_MCUS = 16;            // MCUs per tile, consecutive in raster order over the crop
+constexpr int FT_THREADS = 128;
+constexpr int FT_BLK_PITCH = 68;       // floats per staged 8x8 block (64 + 4: conflict-free LDS.128 across lanes)
+
+struct __align__(16) FastSmem {
+  uint32_t raw[FT_MCUS][16][12];       // BGR bytes of each MCU: 16 rows x 48 B
+  float yf[64][FT_BLK_PITCH];          // luma samples - 128, slot = (block row of the MCU)*32 + mcu*2 + (block column)
+  float cf[32][FT_BLK_PITCH];          // chroma samples - 128: Cb of MCU m in slot m, Cr in slot 16+m
+};
+
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t coef, uint32_t bytes, uint32_t acc) {
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(coef), "r"(bytes));
+  return acc;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t coef, uint32_t bytes, uint32_t acc) {
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(coef), "r"(bytes));
+  return acc;
+}
+__host__ __device__ constexpr uint32_t pk16(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// Numerators of the three colour planes for the 4 pixels held in 3 consecutive words (B,G,R interleaved).
+// cB, cG, cR are the integer weights of byte 0, 1, 2 of a pixel.  Accumulators start at 0x4B000000 so that
+// the integer result is already the bit pattern of the float 2^23 + n.
+template <int cB, int cG, int cR, int BASE>
+__device__ __forceinline__ void numer4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t (&n)[4]) {
+  constexpr uint32_t init = 0x4B000000u + (uint32_t)BASE;
+  n[0] = dp2a_hi(pk16(cR, 0), w0, dp2a_lo(pk16(cB, cG), w0, init));
+  n[1] = dp2a_lo(pk16(cG, cR), w1, dp2a_hi(pk16(0, cB), w0, init));
+  n[2] = dp2a_lo(pk16(cR, 0), w2, dp2a_hi(pk16(cB, cG), w1, init));
+  n[3] = dp2a_hi(pk16(cG, cR), w2, dp2a_lo(pk16(0, cB), w2, init));
+}
+
+constexpr float INV1000_UP = 0x1.0624dep-10f;     // smallest float >= 1/1000   (bits 0x3a83126f)
+constexpr float INV31250_UP = 0x1.0c6f7cp-15f;    // smallest float >= 1/31250  (bits 0x380637be)
+constexpr uint32_t TIE_M_Y = 4294968u, TIE_M_C = 137439u, TIE_LIMIT = 1u << 19;
+
+// 8 pixels of one row (6 words) -> bit patterns of 2^23 + floor(value) for Y, Cb, Cr, and the running minimum of the
+// remainder screens.
+__device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], uint32_t (&yb)[8], uint32_t (&cbb)[8], uint32_t (&crb)[8], uint32_t& screen) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t ny[4], nb[4], nr[4];
+    numer4<114, 587, 299, 0>(w[3 * h], w[3 * h + 1], w[3 * h + 2], ny);
+    numer4<15625, -10352, -5273, 4000000>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nb);
+    numer4<-2541, -13084, 15625, 4000000>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nr);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float fy = __fadd_rn(__uint_as_float(ny[k]), -8388608.0f);
+      const float fb = __fadd_rn(__uint_as_float(nb[k]), -8388608.0f);
+      const float fr = __fadd_rn(__uint_as_float(nr[k]), -8388608.0f);
+      yb[4 * h + k] = __float_as_uint(__fmaf_rz(fy, INV1000_UP, 8388608.0f));
+      cbb[4 * h + k] = __float_as_uint(__fmaf_rz(fb, INV31250_UP, 8388608.0f));
+      crb[4 * h + k] = __float_as_uint(__fmaf_rz(fr, INV31250_UP, 8388608.0f));
+      // remainder screen on n = bits - 0x4B000000:  (n * M) mod 2^32 < 2^19  for every n with n % D == 0
+      screen = min(min(screen, ny[k] * TIE_M_Y - 0x4B000000u * TIE_M_Y), min(nb[k] * TIE_M_C - 0x4B000000u * TIE_M_C, nr[k] * TIE_M_C - 0x4B000000u * TIE_M_C));
+    }
+  }
+}
+
+// In-place forward AAN butterfly on 8 floats; out[k] = X[k] / r_k (tools/analysis/gen_fast_tables.py).
+__device__ __forceinline__ void aan8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7) {
+  using namespace jbfast;
+  const float t0 = __fadd_rn(d0, d7), t7 = __fsub_rn(d0, d7), t1 = __fadd_rn(d1, d6), t6 = __fsub_rn(d1, d6);
+  const float t2 = __fadd_rn(d2, d5), t5 = __fsub_rn(d2, d5), t3 = __fadd_rn(d3, d4), t4 = __fsub_rn(d3, d4);
+  const float t10 = __fadd_rn(t0, t3), t13 = __fsub_rn(t0, t3), t11 = __fadd_rn(t1, t2), t12 = __fsub_rn(t1, t2);
+  d0 = __fadd_rn(t10, t11);
+  d4 = __fsub_rn(t10, t11);
+  const float s = __fadd_rn(t12, t13);
+  d2 = __fmaf_rn(s, C707, t13);
+  d6 = __fmaf_rn(s, -C707, t13);
+  const float a10 = __fadd_rn(t4, t5), a11 = __fadd_rn(t5, t6), a12 = __fadd_rn(t6, t7);
+  const float z5 = __fmul_rn(__fsub_rn(a10, a12), C382);
+  const float z2 = __fmaf_rn(a10, C541, z5), z4 = __fmaf_rn(a12, C1306, z5);
+  const float z11 = __fmaf_rn(a11, C707, t7), z13 = __fmaf_rn(a11, -C707, t7);
+  d5 = __fadd_rn(z13, z2);
+  d3 = __fsub_rn(z13, z2);
+  d1 = __fadd_rn(z11, z4);
+  d7 = __fsub_rn(z11, z4);
+}
+
+// Spread the low 16 bits of x to the even bit positions.
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+
+
+// Bracketed quantisation of natural index I (compile-time so that the multipliers become FFMA immediates).
+template <int COMP, int I>
+__device__ __forceinline__ void quant_one(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad) {
+  constexpr float khi = COMP == 0 ? jbfast::KHI_L[I] : jbfast::KHI_C[I], klo = COMP == 0 ? jbfast::KLO_L[I] : jbfast::KLO_C[I];
+  const uint32_t hi = __float_as_uint(__fmaf_rz(d[I], khi, 12582912.0f));
+  const uint32_t lo = __float_as_uint(__fmaf_rz(d[I], klo, 12582912.0f));
+  bad |= hi ^ lo;
+  q[I] = lo;                          // low 16 bits: floor(v) in two's complement
+}
+template <int COMP, int... I>
+__device__ __forceinline__ void quant_all(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, std::integer_sequence<int, I...>) {
+  (quant_one<COMP, I + 1>(d, q, bad), ...);
+}
+// Word J of the zig-zagged block = positions 2J, 2J+1; trunc = floor + 1 for negative values (a negative
+// integer is never "decided" by the bracket, so it never reaches this point un-flagged); DC arrives truncated.
+template <int J>
+__device__ __forceinline__ void pack_one(const uint32_t (&q)[64], uint32_t (&out)[32], uint32_t& m0, uint32_t& m1) {
+  constexpr int a = jbfast::ZZ[2 * J], b = jbfast::ZZ[2 * J + 1];
+  uint32_t w = __byte_perm(q[a], q[b], 0x5410);
+  uint32_t neg = (w >> 15) & (J == 0 ? 0x00010000u : 0x00010001u);
+  w = __vadd2(w, neg);
+  out[J] = w;
+  const uint32_t nz = __vminu2(w, 0x00010001u);
+  if (J < 16) m0 += nz << J; else m1 += nz << (J - 16);
+}
+template <int... J>
+__device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out)[32], uint32_t& m0, uint32_t& m1, std::integer_sequence<int, J...>) {
+  (pack_one<J>(q, out, m0, m1), ...);
+}
+
+// One 8x8 block per thread: 64 staged samples -> 64 quantised coefficients, zig-zagged and packed, + mask.
+// Returns true when some AC coefficient could not be decided by the bracket.
+template <int COMP>
+__device__ __forceinline__ bool block_fast(const float* __restrict__ blk, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
+  float d[64];
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    const float4 v = reinterpret_cast<const float4*>(blk)[k];
+    d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+  }
+#pragma unroll
+  for (int y = 0; y < 8; y++) aan8(d[8 * y], d[8 * y + 1], d[8 * y + 2], d[8 * y + 3], d[8 * y + 4], d[8 * y + 5], d[8 * y + 6], d[8 * y + 7]);
+#pragma unroll
+  for (int x = 0; x < 8; x++) aan8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
+  // DC through the literal chain (encoder.c:104-108): d[0] is the exact integer sum of the 64 samples
+  {
+    const double f = __dmul_rn(__dmul_rn(__dmul_rn((double)d[0], JB_INV_SQRT2), JB_INV_SQRT2), 0.25);
+    const int v = (int)(short)__double2int_rz(COMP == 0 ? __dmul_rn(f, 0.0625) : __ddiv_rn(f, 17.0));
+    *dcq = min(max(v, -2048), 2047);
+  }
+  uint32_t q[64];
+  uint32_t bad = 0;
+  quant_all<COMP>(d, q, bad, std::make_integer_sequence<int, 63>());
+  q[0] = (uint32_t)*dcq;
+  uint32_t m0 = 0, m1 = 0;            // non-zero flags of pairs 0..15 and 16..31: even positions in the low half, odd in the high half
+  pack_all(q, out, m0, m1, std::make_integer_sequence<int, 32>());
+  const uint32_t lo32 = spread16(m0) | (spread16(m0 >> 16) << 1);
+  const uint32_t hi32 = spread16(m1) | (spread16(m1 >> 16) << 1);
+  *mask = ((uint64_t)hi32 << 32) | (lo32 & ~1u);
+  return bad != 0;
+}
+
+__global__ void __launch_bounds__(FT_THREADS) k_bgr_to_coef_fast(JbWs ws) {
+  __shared__ FastSmem sm;
+  const JbJob job = ws.jobs[blockIdx.y];
+  const int mw = job.w / 16, nm = mw * (job.h / 16);
+  const int m0 = blockIdx.x * FT_MCUS;
+  if (m0 >= nm) return;
+  const int valid = min(FT_MCUS, nm - m0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // position of the tile's first MCU; later MCUs wrap to the next MCU row
+  const int my0 = m0 / mw, mx0 = m0 - my0 * mw;
+  auto mcu_origin = [&](int mcu, int& my, int& mx) {
+    my = my0; mx = mx0 + mcu;
+    while (mx >= mw) { mx -= mw; my++; }
+  };
+  // ---- phase A: stage the BGR bytes of `valid` MCUs -------------------------------------------------
+  {
+    const size_t org = (size_t)job.y * job.pitch + 3u * (uint32_t)job.x;
+    const bool aligned = ((((uintptr_t)job.src + org) | job.pitch) & 15) == 0;
+    const int row = tid >> 3;                      // 16 rows x 8 threads; a thread walks its row in 16-byte (or 1-byte) steps
+    if (aligned) {
+      for (int j = tid & 7; j < valid * 3; j += 8) {
+        const int mcu = j / 3, v = j - mcu * 3;
+        int my, mx;
+        mcu_origin(mcu, my, mx);
+        const uint4* g = reinterpret_cast<const uint4*>(job.src + org + (size_t)(my * 16 + row) * job.pitch + (size_t)mx * 48) + v;
+        *reinterpret_cast<uint4*>(&sm.raw[mcu][row][4 * v]) = __ldg(g);
+      }
+    } else {
+      uint8_t* rawb = reinterpret_cast<uint8_t*>(&sm.raw[0][0][0]);
+      for (int j = tid & 7; j < valid * 48; j += 8) {
+        const int mcu = j / 48, c = j - mcu * 48;
+        int my, mx;
+        mcu_origin(mcu, my, mx);
+        rawb[(mcu * 16 + row) * 48 + c] = __ldg(job.src + org + (size_t)(my * 16 + row) * job.pitch + (size_t)mx * 48 + c);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: colour conversion, 4:2:0 (encoder.c:129-138); one 8x2 pixel patch per step ---------------
+#pragma unroll 1
+  for (int p = tid; p < valid * 16; p += FT_THREADS) {
+    const int mcu = p >> 4, pr = (p >> 1) & 7, pc = p & 1;
+    uint32_t yb[2][8], cbb[2][8], crb[2][8];
+    uint32_t screen = 0xFFFFFFFFu;
+#pragma unroll
+    for (int dr = 0; dr < 2; dr++) {
+      uint32_t w[6];
+      const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[mcu][2 * pr + dr][6 * pc]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { const uint2 t = src[k]; w[2 * k] = t.x; w[2 * k + 1] = t.y; }
+      ycc_row8(w, yb[dr], cbb[dr], crb[dr], screen);
+    }
+    if (screen < TIE_LIMIT) {                 // a remainder-zero candidate: replay the 16 pixels exactly
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const int dr = k >> 3, c = k & 7;
+        const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[mcu][2 * pr + dr][6 * pc]) + 3 * c;
+        const uint32_t e = ycc_pixel(px[0], px[1], px[2]);
+        yb[dr][c] = 0x4B000000u | (e & 0xFF);
+        cbb[dr][c] = 0x4B000000u | ((e >> 8) & 0xFF);
+        crb[dr][c] = 0x4B000000u | (e >> 16);
+      }
+    }
+    // luma: float(Y - 128) into the staged block (row 2pr+dr of the MCU, columns 8pc..8pc+7)
+#pragma unroll
+    for (int dr = 0; dr < 2; dr++) {
+      const int r = 2 * pr + dr;
+      float* dst = &sm.yf[(r >> 3) * 32 + mcu * 2 + pc][(r & 7) * 8];
+      float4 a, b;
+      a.x = __fadd_rn(__uint_as_float(yb[dr][0]), -8388736.0f); a.y = __fadd_rn(__uint_as_float(yb[dr][1]), -8388736.0f);
+      a.z = __fadd_rn(__uint_as_float(yb[dr][2]), -8388736.0f); a.w = __fadd_rn(__uint_as_float(yb[dr][3]), -8388736.0f);
+      b.x = __fadd_rn(__uint_as_float(yb[dr][4]), -8388736.0f); b.y = __fadd_rn(__uint_as_float(yb[dr][5]), -8388736.0f);
+      b.z = __fadd_rn(__uint_as_float(yb[dr][6]), -8388736.0f); b.w = __fadd_rn(__uint_as_float(yb[dr][7]), -8388736.0f);
+      reinterpret_cast<float4*>(dst)[0] = a;
+      reinterpret_cast<float4*>(dst)[1] = b;
+    }
+    // chroma: integer mean of the four truncated samples (encoder.c:136-138), then - 128
+    float cbv[4], crv[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const uint32_t sb = cbb[0][2 * c] + cbb[0][2 * c + 1] + cbb[1][2 * c] + cbb[1][2 * c + 1];   // 4*0x4B000000 wraps to 0x2C000000
+      const uint32_t sr = crb[0][2 * c] + crb[0][2 * c + 1] + crb[1][2 * c] + crb[1][2 * c + 1];
+      cbv[c] = __fadd_rn(__uint_as_float(0x4B000000u | ((sb >> 2) & 0xFFu)), -8388736.0f);
+      crv[c] = __fadd_rn(__uint_as_float(0x4B000000u | ((sr >> 2) & 0xFFu)), -8388736.0f);
+    }
+    *reinterpret_cast<float4*>(&sm.cf[mcu][pr * 8 + 4 * pc]) = make_float4(cbv[0], cbv[1], cbv[2], cbv[3]);
+    *reinterpret_cast<float4*>(&sm.cf[16 + mcu][pr * 8 + 4 * pc]) = make_float4(crv[0], crv[1], crv[2], crv[3]);
+  }
+  __syncthreads();
+
+  // ---- phase C: one block per thread; warps 0,1 = luma block rows 0,1 of the MCUs, warp 2 = Cb | Cr ---------
+  if (warp == 3) return;
+  const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
+  uint32_t out[32];
+  uint64_t mask;
+  int dcq;
+  bool bad;
+  uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
+  bool ok;
+  if (warp < 2) {
+    const int mcu = lane >> 1;
+    int my, mx;
+    mcu_origin(mcu, my, mx);
+    ok = mcu < valid;
+    blk = (uint32_t)(my * 2 + warp) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
+    bad = block_fast<0>(sm.yf[warp * 32 + lane], out, &mask, &dcq);
+  } else {
+    const int mcu = lane & 15, m = m0 + mcu;
+    ok = mcu < valid;
+    blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)m;
+    bad = block_fast<1>(sm.cf[lane], out, &mask, &dcq);
+  }
+  if (!ok) return;
+  uint4* dst = reinterpret_cast<uint4*>(ws.coef + job.coef_off + (size_t)blk * 64);
+#pragma unroll
+  for (int k = 0; k < 8; k++) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+  ws.mask[job.blk_off + blk] = mask;
+  ws.dcraw[job.blk_off + blk] = (int16_t)dcq;
+  if (bad) {
+    const uint32_t slot = atomicAdd(ws.fix_count, 1u);
+    ws.fix_list[slot] = make_uint2(blockIdx.y, blk);
+  }
+}
+
+// Recompute the listed blocks with the literal reference arithmetic; 8 lanes per block, 4 blocks per warp.
+__global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
+  __shared__ double tr[4][4 * TR_STRIDE];
+  __shared__ int16_t zz[4][4 * 64];
+  __shared__ double rqs[2][8][10];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int comp = tid >> 6, r = (tid >> 3) & 7, u = tid & 7;
+    rqs[comp][r][u] = __dmul_rn(__drcp_rn((double)c_quant[comp][r * 8 + u]), 0x1.00000004p-2);
+  }
+  __syncthreads();
+  const uint32_t count = *ws.fix_count;
+  const int b = lane >> 3, i = lane & 7;
+  const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
+  for (uint32_t base = (blockIdx.x * 4 + warp) * 4; base < count; base += gridDim.x * 16) {
+    const bool live = base + b < count;
+    const uint2 e = ws.fix_list[live ? base + b : base];
+    const JbJob job = ws.jobs[e.x];
+    const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
+    const uint32_t blk = e.y;
+    const int comp = blk < nby ? 0 : 1;
+    uint32_t px[8];
+    if (comp == 0) {
+      const uint32_t bw = job.w / 8, by = blk / bw, bx = blk - by * bw;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const uint8_t* p = job.src + (size_t)(job.y + by * 8 + t) * job.pitch + 3u * (uint32_t)(job.x + bx * 8 + i);
+        px[t] = ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) & 0xFF;
+      }
+    } else {
+      const int ch = blk < nby + nbc ? 0 : 1;
+      const uint32_t cblk = blk - nby - (ch ? nbc : 0), bw = job.w / 16, by = cblk / bw, bx = cblk - by * bw;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        uint32_t s = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint8_t* p = job.src + (size_t)(job.y + (by * 8 + t) * 2 + (q >> 1)) * job.pitch + 3u * (uint32_t)(job.x + (bx * 8 + i) * 2 + (q & 1));
+          s += (ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) >> (ch ? 16 : 8)) & 0xFF;
+        }
+        px[t] = s >> 2;
+      }
+    }
+    uint64_t mask;
+    const uint4 out = block_dct(px, comp, rqs[comp][i], izzrow, tr[warp], zz[warp], lane, &mask);
+    if (live) {
+      *reinterpret_cast<uint4*>(ws.coef + job.coef_off + (size_t)blk * 64 + i * 8) = out;
+      if (i == 0) {
+        ws.mask[job.blk_off + blk] = mask;
+        ws.dcraw[job.blk_off + blk] = (int16_t)(out.x & 0xFFFF);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st) {
   int tiles = ((max_w + TILE_W - 1) / TILE_W) * (max_h / 16);
   k_bgr_to_coef<<<dim3(tiles, njobs), K1_THREADS, 0, st>>>(ws);
 }
+
+void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st) {
+  const int mcus = (max_w / 16) * (max_h / 16);
+  k_bgr_to_coef_fast<<<dim3((mcus + FT_MCUS - 1) / FT_MCUS, njobs), FT_THREADS, 0, st>>>(ws);
+}
+
+void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148, 128, 0, st>>>(ws); }
 
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st) {
   uint32_t threads = max_blocks * 8;

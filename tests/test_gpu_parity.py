@@ -371,3 +371,45 @@ def test_enlarge_adjust_and_subsample_vs_oracle(api, oracle):
         x0, y0 = int(rng.integers(0, W // 4)), int(rng.integers(0, H // 4))
         x1, y1 = int(rng.integers(x0, W // 4)), int(rng.integers(y0, H // 4))
         assert api.enlarge_adjust((x0, y0, x1, y1), W, H) == oracle.enlarge_adjust((x0, y0, x1, y1), W, H)
+
+
+# ------------------------------------------------------------------ fast filter transform vs literal chain on the device
+
+def test_fast_dct_equals_exact_dct_large(frames):
+    """The FP32 filter + fix-up path must produce the bytes of the all-FP64 path on every content class, at the
+    bench shape; also reports how many blocks needed the literal chain."""
+    fast, exact = pkg.Encoder(0, 8, 1), pkg.Encoder(0, 8, 1)
+    exact.set_exact_dct(True)
+    try:
+        rng = np.random.default_rng(7)
+        W, H = 1920, 1280
+        batches = {
+            "natural": np.stack([frames.natural_frame(f, W, H) for f in (0, 1, 333)]),
+            "noise": np.stack([frames.noise_frame(f, W, H) for f in (0, 5)]),
+            "ramp": np.stack([frames.ramp_frame(f, W, H) for f in (0, 77)]),
+            "binary": (rng.integers(0, 2, (2, H, W, 3), dtype=np.uint8) * 255).astype(np.uint8),
+            "flat8": np.ascontiguousarray(np.kron(rng.integers(0, 256, (2, H // 8, W // 8, 3), dtype=np.uint8), np.ones((1, 8, 8, 1), np.uint8))),
+            "edges": np.ascontiguousarray(np.kron((rng.integers(0, 2, (2, H // 4, W // 4, 1), dtype=np.uint8) * 255).astype(np.uint8), np.ones((1, 4, 4, 3), np.uint8))),
+        }
+        for name, b in batches.items():
+            slot = 3 * W * H // 2 + 65536
+            a = fast.encode_frames(b, slot)
+            nfix = fast.fix_count(0)
+            e = exact.encode_frames(b, slot)
+            nblk = b.shape[0] * W * H * 3 // 2 // 64
+            print(f"{name}: {nfix} of {nblk} blocks ({100.0 * nfix / nblk:.3f} %) went through the literal chain")
+            assert a == e, name
+    finally:
+        fast.close()
+        exact.close()
+
+
+def test_fast_dct_small_shapes_and_crops(api, oracle, frames):
+    """Ragged tiles: MCU counts that are not multiples of 16, single-MCU crops, unaligned crop origins."""
+    rng = np.random.default_rng(11)
+    for (h, w) in [(16, 16), (16, 272), (48, 80), (32, 528), (240, 320)]:
+        for kind in range(6):
+            _check_against_oracle(api, oracle, _rand_img(rng, h, w, kind), tag=f"{w}x{h} kind {kind}")
+    img = frames.sample_bgr("640")
+    for area in [(1, 1, 16, 16), (7, 3, 400, 16), (13, 600, 272, 32), (0, 0, 640, 640)]:
+        _check_against_oracle(api, oracle, img, area, tag=str(area))

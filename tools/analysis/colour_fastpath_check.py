@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Exhaustive check of the FP32/integer colour fast path of k_bgr_to_coef (fast kernel).
+
+For every reachable numerator n:
+  floor: RZ_f32(n * INV + 2^23) - 2^23 == n // D        (FMA: exact product, one rounding toward zero)
+  ties : (n * M mod 2^32) < 2^19  whenever n % D == 0    (superset test; false-positive rate reported)
+Y : n = 299R+587G+114B, D = 1000 ; Cb/Cr : n = 4e6 + ... , D = 31250 (coefficients divided by 32).
+"""
+import numpy as np
+
+def ru_f32(x):            # smallest float32 >= x
+    f = np.float32(x)
+    if float(f) < x:
+        f = np.nextafter(f, np.float32(np.inf))
+    return f
+
+def check(D, nmax, name):
+    inv = ru_f32(1.0 / D)
+    M = -(-2 ** 32 // D)
+    n = np.arange(0, nmax + 1, dtype=np.int64)
+    prod = n.astype(np.float64) * float(inv)                 # exact: 23-bit n times 24-bit inv fits in 53 bits
+    fl = np.floor(prod).astype(np.int64)                     # RZ at integer grid == floor for non-negative values (2^23 + prod < 2^24)
+    assert (prod < 2 ** 23).all()
+    bad = np.nonzero(fl != n // D)[0]
+    lo = (n * M) & 0xFFFFFFFF
+    ties = (n % D) == 0
+    miss = np.nonzero(ties & ~(lo < 2 ** 19))[0]
+    fp = np.count_nonzero(~ties & (lo < 2 ** 19)) / n.size
+    print(f"{name}: D={D} inv={float(inv)!r} (bits {inv.view(np.uint32):#x}) M={M} n<= {nmax}: floor mismatches {bad.size}, missed ties {miss.size}, false-positive rate {fp:.2e}")
+    assert bad.size == 0 and miss.size == 0
+
+check(1000, 255 * 1000, "Y ")
+check(31250, 4_000_000 + 255 * 15625, "Cb/Cr")
+# reachable numerator ranges
+R, G, B = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")
+cb = 4_000_000 - 5273 * R - 10352 * G + 15625 * B
+cr = 4_000_000 + 15625 * R - 13084 * G - 2541 * B
+print("Cb numerator range", cb.min(), cb.max(), " Cr", cr.min(), cr.max(), " (must be in [0, 2^23) =", 2 ** 23, ")")
+# cross-check the /32 reduction against the reference's 1e6-denominator form
+cb6 = 128_000_000 - 168736 * R - 331264 * G + 500000 * B
+cr6 = 128_000_000 + 500000 * R - 418688 * G - 81312 * B
+assert (cb6 == 32 * cb).all() and (cr6 == 32 * cr).all()
+print("ok")

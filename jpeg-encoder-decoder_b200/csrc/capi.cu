@@ -219,14 +219,14 @@ struct StageTimer {
 
 // Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
 int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
-              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes) {
+              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false) {
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (from == FROM_PIXELS) {
     if (c->exact_dct) { StageTimer t(c, st, ST_DCT); jb_launch_dct(ws, njobs, max_w, max_h, st); }
     else {
-      { StageTimer t(c, st, ST_DCT); jb_launch_dct_fast(ws, njobs, max_w, max_h, st); }
+      { StageTimer t(c, st, ST_DCT); jb_launch_dct_fast(ws, njobs, max_w, max_h, rows_aligned, st); }
       { StageTimer t(c, st, ST_FIX); jb_launch_fix_blocks(ws, st); }
     }
   }
@@ -412,7 +412,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, d_bgr + (size_t)first * frame_stride, frame_stride, w, h,
                                                           d_out + (size_t)first * slot, slot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first, true)) return -1;
   }
   for (int i = 0; i < nl; i++) {
     CK(cudaEventRecord(c->lanes[i].done, c->lanes[i].stream));
@@ -466,7 +466,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, (const uint8_t*)l.in.p, frame, w, h, (uint8_t*)l.out.p, dslot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true)) return -1;
     CK(cudaMemcpyAsync(l.h_sizes.p, l.sizes.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaEventRecord(l.sizes_ready, l.stream));
     l.pending_first = first;
@@ -505,7 +505,9 @@ int jpegb200_encode_regions(jpegb200_ctx* c, const uint8_t* d_frame, int frame_w
   CK(cudaStreamSynchronize(l.stream));       // the workspace may be re-allocated below
   if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc)) return -1;
   if (upload_jobs(l, jobs)) return -1;
-  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes)) return -1;
+  bool rows_aligned = true;          // every crop row starts on a 16-byte boundary -> bulk async copies
+  for (const JbJob& j : jobs) rows_aligned = rows_aligned && ((((uintptr_t)j.src + (size_t)j.y * j.pitch + 3u * (uint32_t)j.x) | j.pitch) & 15) == 0;
+  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes, rows_aligned)) return -1;
   CK(cudaEventRecord(l.done, l.stream));
   CK(cudaStreamWaitEvent(user, l.done, 0));
   return 0;
@@ -535,7 +537,8 @@ int jpegb200_stage_dct(jpegb200_ctx* c, const uint8_t* bgr, int frame_w, int fra
   j.src = (const uint8_t*)l.in.p;
   CK(cudaMemcpyAsync(l.in.p, bgr + pitch * y, rows_bytes, cudaMemcpyHostToDevice, l.stream));
   if (upload_jobs(l, jobs)) return -1;
-  if (run_chain(c, l, 1, mw, mh, mb, mc, FROM_PIXELS, true, false, nullptr)) return -1;
+  const bool rows_aligned = ((((uintptr_t)j.src + 3u * (uint32_t)x) | pitch) & 15) == 0;
+  if (run_chain(c, l, 1, mw, mh, mb, mc, FROM_PIXELS, true, false, nullptr, rows_aligned)) return -1;
   const size_t n = (size_t)w * h;
   CK(cudaMemcpyAsync(Y, l.ws.coef, n * 2, cudaMemcpyDeviceToHost, l.stream));
   CK(cudaMemcpyAsync(Cb, l.ws.coef + n, n / 2, cudaMemcpyDeviceToHost, l.stream));

@@ -98,7 +98,7 @@ __host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
 
 // ---- launchers (each enqueues on `st`; defined in the k_*.cu files) -------------------------------
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
-void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
+void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st);
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);

@@ -26,6 +26,8 @@
 #include "tables.cuh"
 #include "fast_tables.cuh"
 #include <utility>
+#include <cstdio>
+#include <cstdlib>
 
 namespace {
 
@@ -318,13 +320,40 @@ __global__ void k_plane_masks(JbWs ws) {
 // tools/analysis/colour_fastpath_check.py).  A patch with a candidate replays ycc_pixel (exact).
 constexpr int FT_MCUS = 16;            // MCUs per tile, consecutive in raster order over the crop
 constexpr int FT_THREADS = 128;
-constexpr int FT_BLK_PITCH = 68;       // floats per staged 8x8 block (64 + 4: conflict-free LDS.128 across lanes)
 
-struct __align__(16) FastSmem {
-  uint32_t raw[FT_MCUS][16][12];       // BGR bytes of each MCU: 16 rows x 48 B
-  float yf[64][FT_BLK_PITCH];          // luma samples - 128, slot = (block row of the MCU)*32 + mcu*2 + (block column)
-  float cf[32][FT_BLK_PITCH];          // chroma samples - 128: Cb of MCU m in slot m, Cr in slot 16+m
+constexpr int FT_SMP_PITCH = 20;       // words per staged 8x8 block of samples (64 B + 16 B pad: conflict-free LDS.128 across lanes)
+struct __align__(128) FastSmem {
+  uint32_t raw[2][16][FT_MCUS * 12];   // two stages of BGR bytes: 16 pixel rows x (16 MCUs x 48 B), filled by bulk async copies
+  uint32_t smp[96][FT_SMP_PITCH];      // 8-bit samples of the tile's blocks: luma slot = (block row)*32 + mcu*2 + (block column),
+                                       // Cb of MCU m in slot 64+m, Cr in slot 80+m
+  unsigned long long full[2];          // mbarriers: stage s holds the bytes of its tile
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra D_%=;\n"
+      "bra W_%=;\n"
+      "D_%=:\n"
+      "}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
 
 __device__ __forceinline__ uint32_t dp2a_lo(uint32_t coef, uint32_t bytes, uint32_t acc) {
   asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(coef), "r"(bytes));
@@ -437,29 +466,40 @@ __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out
   (pack_one<J>(q, out, m0, m1), ...);
 }
 
-// One 8x8 block per thread: 64 staged samples -> 64 quantised coefficients, zig-zagged and packed, + mask.
-// Returns true when some AC coefficient could not be decided by the bracket.
-template <int COMP>
-__device__ __forceinline__ bool block_fast(const float* __restrict__ blk, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
+// One 8x8 block per thread: 64 staged 8-bit samples -> 64 quantised coefficients, zig-zagged and packed, + mask.
+// Sample b enters as the float 2^15 + b (one PRMT drops the byte into the mantissa): all sums of the flow stay exact
+// integers below 2^24 and the offset cancels in every difference, so it only shows up in the DC sum, where it is
+// removed exactly together with the reference's -128 (encoder.c:92).  Returns true when some AC coefficient could not
+// be decided by the bracket.
+__device__ __forceinline__ bool block_fast(const uint32_t* __restrict__ blk, int comp, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
   float d[64];
 #pragma unroll
-  for (int k = 0; k < 16; k++) {
-    const float4 v = reinterpret_cast<const float4*>(blk)[k];
-    d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+  for (int k = 0; k < 4; k++) {
+    const uint4 v = reinterpret_cast<const uint4*>(blk)[k];
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      d[16 * k + 4 * j + 0] = __uint_as_float(__byte_perm(w[j], 0x47000000u, 0x7404));
+      d[16 * k + 4 * j + 1] = __uint_as_float(__byte_perm(w[j], 0x47000000u, 0x7414));
+      d[16 * k + 4 * j + 2] = __uint_as_float(__byte_perm(w[j], 0x47000000u, 0x7424));
+      d[16 * k + 4 * j + 3] = __uint_as_float(__byte_perm(w[j], 0x47000000u, 0x7434));
+    }
   }
 #pragma unroll
   for (int y = 0; y < 8; y++) aan8(d[8 * y], d[8 * y + 1], d[8 * y + 2], d[8 * y + 3], d[8 * y + 4], d[8 * y + 5], d[8 * y + 6], d[8 * y + 7]);
 #pragma unroll
   for (int x = 0; x < 8; x++) aan8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
-  // DC through the literal chain (encoder.c:104-108): d[0] is the exact integer sum of the 64 samples
+  // DC through the literal chain (encoder.c:104-108): d[0] - 64*(2^15 + 128) is the exact integer sum of (sample - 128)
   {
-    const double f = __dmul_rn(__dmul_rn(__dmul_rn((double)d[0], JB_INV_SQRT2), JB_INV_SQRT2), 0.25);
-    const int v = (int)(short)__double2int_rz(COMP == 0 ? __dmul_rn(f, 0.0625) : __ddiv_rn(f, 17.0));
+    const double S = (double)__fadd_rn(d[0], -2105344.0f);
+    const double f = __dmul_rn(__dmul_rn(__dmul_rn(S, JB_INV_SQRT2), JB_INV_SQRT2), 0.25);
+    const int v = (int)(short)__double2int_rz(comp == 0 ? __dmul_rn(f, 0.0625) : __ddiv_rn(f, 17.0));
     *dcq = min(max(v, -2048), 2047);
   }
   uint32_t q[64];
   uint32_t bad = 0;
-  quant_all<COMP>(d, q, bad, std::make_integer_sequence<int, 63>());
+  if (comp == 0) quant_all<0>(d, q, bad, std::make_integer_sequence<int, 63>());
+  else quant_all<1>(d, q, bad, std::make_integer_sequence<int, 63>());
   q[0] = (uint32_t)*dcq;
   uint32_t m0 = 0, m1 = 0;            // non-zero flags of pairs 0..15 and 16..31: even positions in the low half, odd in the high half
   pack_all(q, out, m0, m1, std::make_integer_sequence<int, 32>());
@@ -469,129 +509,188 @@ __device__ __forceinline__ bool block_fast(const float* __restrict__ blk, uint32
   return bad != 0;
 }
 
-__global__ void __launch_bounds__(FT_THREADS) k_bgr_to_coef_fast(JbWs ws) {
-  __shared__ FastSmem sm;
-  const JbJob job = ws.jobs[blockIdx.y];
-  const int mw = job.w / 16, nm = mw * (job.h / 16);
-  const int m0 = blockIdx.x * FT_MCUS;
-  if (m0 >= nm) return;
-  const int valid = min(FT_MCUS, nm - m0);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  // position of the tile's first MCU; later MCUs wrap to the next MCU row
-  const int my0 = m0 / mw, mx0 = m0 - my0 * mw;
-  auto mcu_origin = [&](int mcu, int& my, int& mx) {
-    my = my0; mx = mx0 + mcu;
-    while (mx >= mw) { mx -= mw; my++; }
-  };
-  // ---- phase A: stage the BGR bytes of `valid` MCUs -------------------------------------------------
-  {
-    const size_t org = (size_t)job.y * job.pitch + 3u * (uint32_t)job.x;
-    const bool aligned = ((((uintptr_t)job.src + org) | job.pitch) & 15) == 0;
-    const int row = tid >> 3;                      // 16 rows x 8 threads; a thread walks its row in 16-byte (or 1-byte) steps
-    if (aligned) {
-      for (int j = tid & 7; j < valid * 3; j += 8) {
-        const int mcu = j / 3, v = j - mcu * 3;
-        int my, mx;
-        mcu_origin(mcu, my, mx);
-        const uint4* g = reinterpret_cast<const uint4*>(job.src + org + (size_t)(my * 16 + row) * job.pitch + (size_t)mx * 48) + v;
-        *reinterpret_cast<uint4*>(&sm.raw[mcu][row][4 * v]) = __ldg(g);
-      }
-    } else {
-      uint8_t* rawb = reinterpret_cast<uint8_t*>(&sm.raw[0][0][0]);
-      for (int j = tid & 7; j < valid * 48; j += 8) {
-        const int mcu = j / 48, c = j - mcu * 48;
-        int my, mx;
-        mcu_origin(mcu, my, mx);
-        rawb[(mcu * 16 + row) * 48 + c] = __ldg(job.src + org + (size_t)(my * 16 + row) * job.pitch + (size_t)mx * 48 + c);
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase B: colour conversion, 4:2:0 (encoder.c:129-138); one 8x2 pixel patch per step ---------------
+// Cold path of the colour stage: some pixel of the 8x2 patch has a zero remainder (every grey pixel does), where the
+// reference's double chain decides between floor and floor-1; replay the patch with ycc_pixel and stage the bytes.
+__device__ __noinline__ void replay_patch(FastSmem& sm, int s, int mcu, int pr, int pc) {
+  uint32_t cb[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
 #pragma unroll 1
-  for (int p = tid; p < valid * 16; p += FT_THREADS) {
-    const int mcu = p >> 4, pr = (p >> 1) & 7, pc = p & 1;
-    uint32_t yb[2][8], cbb[2][8], crb[2][8];
-    uint32_t screen = 0xFFFFFFFFu;
+  for (int dr = 0; dr < 2; dr++) {
+    const int r = 2 * pr + dr;
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[s][r][mcu * 12 + 6 * pc]);
+    uint8_t* ydst = reinterpret_cast<uint8_t*>(&sm.smp[(r >> 3) * 32 + mcu * 2 + pc][(r & 7) * 2]);
 #pragma unroll
-    for (int dr = 0; dr < 2; dr++) {
-      uint32_t w[6];
-      const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[mcu][2 * pr + dr][6 * pc]);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { const uint2 t = src[k]; w[2 * k] = t.x; w[2 * k + 1] = t.y; }
-      ycc_row8(w, yb[dr], cbb[dr], crb[dr], screen);
+    for (int c = 0; c < 8; c++) {
+      const uint32_t e = ycc_pixel(px[3 * c], px[3 * c + 1], px[3 * c + 2]);
+      ydst[c] = (uint8_t)e;
+      cb[c >> 1] += (e >> 8) & 0xFF;
+      cr[c >> 1] += e >> 16;
     }
-    if (screen < TIE_LIMIT) {                 // a remainder-zero candidate: replay the 16 pixels exactly
-#pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const int dr = k >> 3, c = k & 7;
-        const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[mcu][2 * pr + dr][6 * pc]) + 3 * c;
-        const uint32_t e = ycc_pixel(px[0], px[1], px[2]);
-        yb[dr][c] = 0x4B000000u | (e & 0xFF);
-        cbb[dr][c] = 0x4B000000u | ((e >> 8) & 0xFF);
-        crb[dr][c] = 0x4B000000u | (e >> 16);
+  }
+  sm.smp[64 + mcu][pr * 2 + pc] = (cb[0] >> 2) | ((cb[1] >> 2) << 8) | ((cb[2] >> 2) << 16) | ((cb[3] >> 2) << 24);
+  sm.smp[80 + mcu][pr * 2 + pc] = (cr[0] >> 2) | ((cr[1] >> 2) << 8) | ((cr[2] >> 2) << 16) | ((cr[3] >> 2) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {   // low bytes of a,b,c,d -> one word
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// Tile = 16 consecutive MCUs (raster order over the crop) of one job.  Persistent CTAs walk the tiles of the wave;
+// with BULK the BGR rows of tile i+1 are fetched by bulk async copies (one per pixel row and MCU-row run) into the
+// other stage while tile i is converted and transformed.  BULK needs 16-byte aligned rows (every full frame);
+// crops with odd origins take the synchronous byte loader.
+struct TilePos {
+  int job, m0, valid, mw, my0, mx0;
+};
+__device__ __forceinline__ bool tile_pos(const JbWs& ws, int t, int tiles_per_job, TilePos& p, JbJob& job) {
+  p.job = t / tiles_per_job;
+  const int tile = t - p.job * tiles_per_job;
+  job = ws.jobs[p.job];
+  p.mw = job.w / 16;
+  const int nm = p.mw * (job.h / 16);
+  p.m0 = tile * FT_MCUS;
+  if (p.m0 >= nm) return false;
+  p.valid = min(FT_MCUS, nm - p.m0);
+  p.my0 = p.m0 / p.mw;
+  p.mx0 = p.m0 - p.my0 * p.mw;
+  return true;
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int ntiles, int tiles_per_job) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (BULK) {
+    if (tid == 0) {
+      mbar_init(&sm.full[0], 1);
+      mbar_init(&sm.full[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // Issue the copies of tile t into stage s (warp 0: lane r < 16 owns pixel row r).
+  auto prefetch = [&](int t, int s) {
+    TilePos p;
+    JbJob job;
+    if (t >= ntiles || !tile_pos(ws, t, tiles_per_job, p, job)) return;
+    if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)p.valid * 768u);
+    __syncwarp();
+    if (lane < 16) {
+      int mcu = 0, my = p.my0, mx = p.mx0;
+      while (mcu < p.valid) {
+        const int run = min(p.valid - mcu, p.mw - mx);
+        const uint8_t* g = job.src + (size_t)(job.y + my * 16 + lane) * job.pitch + 3u * (uint32_t)job.x + (size_t)mx * 48;
+        bulk_g2s(&sm.raw[s][lane][mcu * 12], g, (uint32_t)run * 48u, &sm.full[s]);
+        mcu += run; mx = 0; my++;
       }
     }
-    // luma: float(Y - 128) into the staged block (row 2pr+dr of the MCU, columns 8pc..8pc+7)
-#pragma unroll
-    for (int dr = 0; dr < 2; dr++) {
-      const int r = 2 * pr + dr;
-      float* dst = &sm.yf[(r >> 3) * 32 + mcu * 2 + pc][(r & 7) * 8];
-      float4 a, b;
-      a.x = __fadd_rn(__uint_as_float(yb[dr][0]), -8388736.0f); a.y = __fadd_rn(__uint_as_float(yb[dr][1]), -8388736.0f);
-      a.z = __fadd_rn(__uint_as_float(yb[dr][2]), -8388736.0f); a.w = __fadd_rn(__uint_as_float(yb[dr][3]), -8388736.0f);
-      b.x = __fadd_rn(__uint_as_float(yb[dr][4]), -8388736.0f); b.y = __fadd_rn(__uint_as_float(yb[dr][5]), -8388736.0f);
-      b.z = __fadd_rn(__uint_as_float(yb[dr][6]), -8388736.0f); b.w = __fadd_rn(__uint_as_float(yb[dr][7]), -8388736.0f);
-      reinterpret_cast<float4*>(dst)[0] = a;
-      reinterpret_cast<float4*>(dst)[1] = b;
-    }
-    // chroma: integer mean of the four truncated samples (encoder.c:136-138), then - 128
-    float cbv[4], crv[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const uint32_t sb = cbb[0][2 * c] + cbb[0][2 * c + 1] + cbb[1][2 * c] + cbb[1][2 * c + 1];   // 4*0x4B000000 wraps to 0x2C000000
-      const uint32_t sr = crb[0][2 * c] + crb[0][2 * c + 1] + crb[1][2 * c] + crb[1][2 * c + 1];
-      cbv[c] = __fadd_rn(__uint_as_float(0x4B000000u | ((sb >> 2) & 0xFFu)), -8388736.0f);
-      crv[c] = __fadd_rn(__uint_as_float(0x4B000000u | ((sr >> 2) & 0xFFu)), -8388736.0f);
-    }
-    *reinterpret_cast<float4*>(&sm.cf[mcu][pr * 8 + 4 * pc]) = make_float4(cbv[0], cbv[1], cbv[2], cbv[3]);
-    *reinterpret_cast<float4*>(&sm.cf[16 + mcu][pr * 8 + 4 * pc]) = make_float4(crv[0], crv[1], crv[2], crv[3]);
-  }
-  __syncthreads();
+  };
+  if (BULK && warp == 0) prefetch(blockIdx.x, 0);
 
-  // ---- phase C: one block per thread; warps 0,1 = luma block rows 0,1 of the MCUs, warp 2 = Cb | Cr ---------
-  if (warp == 3) return;
-  const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
-  uint32_t out[32];
-  uint64_t mask;
-  int dcq;
-  bool bad;
-  uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
-  bool ok;
-  if (warp < 2) {
-    const int mcu = lane >> 1;
-    int my, mx;
-    mcu_origin(mcu, my, mx);
-    ok = mcu < valid;
-    blk = (uint32_t)(my * 2 + warp) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
-    bad = block_fast<0>(sm.yf[warp * 32 + lane], out, &mask, &dcq);
-  } else {
-    const int mcu = lane & 15, m = m0 + mcu;
-    ok = mcu < valid;
-    blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)m;
-    bad = block_fast<1>(sm.cf[lane], out, &mask, &dcq);
-  }
-  if (!ok) return;
-  uint4* dst = reinterpret_cast<uint4*>(ws.coef + job.coef_off + (size_t)blk * 64);
+  int it = 0;
+  uint32_t phases = 0;               // parity of the next completion of each stage's mbarrier
+  int rot = 0;
+#pragma unroll 1
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+    const int s = BULK ? (it & 1) : 0;
+    TilePos p;
+    JbJob job;
+    const bool have = tile_pos(ws, t, tiles_per_job, p, job);
+    if (BULK) {
+      if (warp == 0) prefetch(t + gridDim.x, s ^ 1);      // stage s^1 was last read two barriers ago
+      if (!have) continue;
+      mbar_wait(&sm.full[s], (phases >> s) & 1u);
+      phases ^= 1u << s;
+    } else {
+      if (!have) continue;
+      // synchronous byte loader (arbitrary crop origin)
+      uint8_t* rawb = reinterpret_cast<uint8_t*>(&sm.raw[0][0][0]);
+      const int row = tid >> 3;
+      for (int j = tid & 7; j < p.valid * 48; j += 8) {
+        const int mcu = j / 48, c = j - mcu * 48;
+        int my = p.my0, mx = p.mx0 + mcu;
+        while (mx >= p.mw) { mx -= p.mw; my++; }
+        rawb[row * (FT_MCUS * 48) + j] = __ldg(job.src + (size_t)(job.y + my * 16 + row) * job.pitch + 3u * (uint32_t)(job.x + mx * 16) + c);
+      }
+      __syncthreads();
+    }
+    const int valid = p.valid;
+
+    // ---- phase B: colour conversion, 4:2:0 (encoder.c:129-138); one 8x2 pixel patch per step ---------------
+    // patch id -> (mcu, left/right half, row pair); lanes sweep the MCUs so that every LDS.64 / STS.128 is conflict-free
+#pragma unroll 1
+    for (int q = tid; q < 256; q += FT_THREADS) {
+      const int mcu = (q >> 1) & 15, pc = q & 1, pr = q >> 5;
+      if (mcu >= valid) continue;
+      uint32_t yb[2][8], cbb[2][8], crb[2][8];
+      uint32_t screen = 0xFFFFFFFFu;
 #pragma unroll
-  for (int k = 0; k < 8; k++) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-  ws.mask[job.blk_off + blk] = mask;
-  ws.dcraw[job.blk_off + blk] = (int16_t)dcq;
-  if (bad) {
-    const uint32_t slot = atomicAdd(ws.fix_count, 1u);
-    ws.fix_list[slot] = make_uint2(blockIdx.y, blk);
+      for (int dr = 0; dr < 2; dr++) {
+        uint32_t w[6];
+        const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[s][2 * pr + dr][mcu * 12 + 6 * pc]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+        ycc_row8(w, yb[dr], cbb[dr], crb[dr], screen);
+      }
+      if (screen < TIE_LIMIT) {
+        replay_patch(sm, s, mcu, pr, pc);
+        continue;
+      }
+      // luma bytes of rows 2pr, 2pr+1 (columns 8pc..8pc+7) into their block; the low byte of each pattern is the sample
+#pragma unroll
+      for (int dr = 0; dr < 2; dr++) {
+        const int r = 2 * pr + dr;
+        *reinterpret_cast<uint2*>(&sm.smp[(r >> 3) * 32 + mcu * 2 + pc][(r & 7) * 2]) =
+            make_uint2(pack4(yb[dr][0], yb[dr][1], yb[dr][2], yb[dr][3]), pack4(yb[dr][4], yb[dr][5], yb[dr][6], yb[dr][7]));
+      }
+      // chroma: integer mean of the four truncated samples (encoder.c:136-138); 4*0x4B000000 wraps to 0x2C000000
+      uint32_t cbv[4], crv[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        cbv[c] = (cbb[0][2 * c] + cbb[0][2 * c + 1] + cbb[1][2 * c] + cbb[1][2 * c + 1]) >> 2;
+        crv[c] = (crb[0][2 * c] + crb[0][2 * c + 1] + crb[1][2 * c] + crb[1][2 * c + 1]) >> 2;
+      }
+      sm.smp[64 + mcu][pr * 2 + pc] = pack4(cbv[0], cbv[1], cbv[2], cbv[3]);
+      sm.smp[80 + mcu][pr * 2 + pc] = pack4(crv[0], crv[1], crv[2], crv[3]);
+    }
+    __syncthreads();
+
+    // ---- phase C: one block per thread.  Three of the four warps take the tile's three rounds (luma block rows 0 and 1
+    // of the MCUs, then Cb|Cr); the idle role rotates so that every scheduler partition gets the same share.
+    const int role = (warp + rot) & 3;
+    rot++;
+    if (role < 3) {
+      const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
+      uint32_t out[32];
+      uint64_t mask;
+      int dcq;
+      bool ok;
+      uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
+      if (role < 2) {
+        const int mcu = lane >> 1;
+        int my = p.my0, mx = p.mx0 + mcu;
+        while (mx >= p.mw) { mx -= p.mw; my++; }
+        ok = mcu < valid;
+        blk = (uint32_t)(my * 2 + role) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
+      } else {
+        const int mcu = lane & 15;
+        ok = mcu < valid;
+        blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)(p.m0 + mcu);
+      }
+      const bool bad = block_fast(sm.smp[role * 32 + lane], role < 2 ? 0 : 1, out, &mask, &dcq);
+      if (ok) {
+        uint4* dst = reinterpret_cast<uint4*>(ws.coef + job.coef_off + (size_t)blk * 64);
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+        ws.mask[job.blk_off + blk] = mask;
+        ws.dcraw[job.blk_off + blk] = (int16_t)dcq;
+        if (bad) {
+          const uint32_t slot = atomicAdd(ws.fix_count, 1u);
+          ws.fix_list[slot] = make_uint2((uint32_t)p.job, blk);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -657,9 +756,23 @@ void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t
   k_bgr_to_coef<<<dim3(tiles, njobs), K1_THREADS, 0, st>>>(ws);
 }
 
-void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st) {
-  const int mcus = (max_w / 16) * (max_h / 16);
-  k_bgr_to_coef_fast<<<dim3((mcus + FT_MCUS - 1) / FT_MCUS, njobs), FT_THREADS, 0, st>>>(ws);
+void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st) {
+  static int ctas_per_sm[2] = {0, 0}, sms = 0;
+  const int v = rows_aligned ? 1 : 0;
+  auto kern = rows_aligned ? k_bgr_to_coef_fast<true> : k_bgr_to_coef_fast<false>;
+  if (!ctas_per_sm[v]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, FT_THREADS, sizeof(FastSmem));
+    ctas_per_sm[v] = n > 0 ? n : 1;
+    if (getenv("JPEGB200_DEBUG")) fprintf(stderr, "k_bgr_to_coef_fast<%d>: %d SMs x %d CTAs, %zu B smem (%s)\n", v, sms, n, sizeof(FastSmem), cudaGetErrorString(cudaGetLastError()));
+  }
+  const int mcus = (max_w / 16) * (max_h / 16), tiles_per_job = (mcus + FT_MCUS - 1) / FT_MCUS, ntiles = tiles_per_job * njobs;
+  const int grid = ntiles < sms * ctas_per_sm[v] ? ntiles : sms * ctas_per_sm[v];
+  kern<<<grid, FT_THREADS, sizeof(FastSmem), st>>>(ws, ntiles, tiles_per_job);
 }
 
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148, 128, 0, st>>>(ws); }

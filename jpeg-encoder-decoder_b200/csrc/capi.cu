@@ -66,7 +66,7 @@ struct WaveDims {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr, sizes_ready = nullptr;
-  DevBuf jobs, state_hist, coef, mask, dcraw, blkbits, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix;
+  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
@@ -82,7 +82,7 @@ struct Lane {
     if ((e = coef.ensure(d.coefs * sizeof(int16_t))) != cudaSuccess) return e;
     if ((e = mask.ensure(d.blocks * sizeof(uint64_t))) != cudaSuccess) return e;
     if ((e = dcraw.ensure(d.blocks * sizeof(int16_t))) != cudaSuccess) return e;
-    if ((e = blkbits.ensure(d.blocks * sizeof(uint32_t))) != cudaSuccess) return e;
+    if ((e = chunk_hist.ensure(d.chunks * JB_CHUNK_HIST * sizeof(int))) != cudaSuccess) return e;
     if ((e = chunk_bits.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = chunk_base.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = huff.ensure(d.njobs * 4 * sizeof(JbHuff))) != cudaSuccess) return e;
@@ -96,7 +96,7 @@ struct Lane {
     ws.coef = (int16_t*)coef.p;
     ws.mask = (uint64_t*)mask.p;
     ws.dcraw = (int16_t*)dcraw.p;
-    ws.blkbits = (uint32_t*)blkbits.p;
+    ws.chunk_hist = (int*)chunk_hist.p;
     ws.chunk_bits = (uint32_t*)chunk_bits.p;
     ws.chunk_base = (uint32_t*)chunk_base.p;
     ws.huff = (JbHuff*)huff.p;
@@ -108,7 +108,7 @@ struct Lane {
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &blkbits, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &in, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -231,16 +231,17 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     }
   }
   else { StageTimer t(c, st, ST_MASKS); jb_launch_plane_masks(ws, njobs, max_blocks, st); }
+  const int dc_from_raw = from == FROM_PIXELS ? 1 : 0;
+  // symbol statistics (per job and per chunk); the drop-in rgb_to_dct also wants the differenced DC in the plane (encoder.c:168-177)
+  { StageTimer t(c, st, ST_STATS); jb_launch_symbol_stats(ws, njobs, max_chunks, dc_from_raw, stop_after_dct ? 1 : 0, st); }
+  if (stop_after_dct) { CK(cudaGetLastError()); return 0; }
   if (from != FROM_PLANES_WRITE) {
-    { StageTimer t(c, st, ST_STATS); jb_launch_symbol_stats(ws, njobs, max_chunks, from == FROM_PIXELS ? 1 : 0, st); }
-    if (stop_after_dct) { CK(cudaGetLastError()); return 0; }
     { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, st); }
     if (stop_after_tables) { CK(cudaGetLastError()); return 0; }
   }
   { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
-  { StageTimer t(c, st, ST_BITS); jb_launch_block_bits(ws, njobs, max_chunks, st); }
   { StageTimer t(c, st, ST_SCAN); jb_launch_scan(ws, njobs, st); }
-  { StageTimer t(c, st, ST_PACK); jb_launch_pack(ws, njobs, max_chunks, st); }
+  { StageTimer t(c, st, ST_PACK); jb_launch_pack(ws, njobs, max_chunks, dc_from_raw, st); }
   { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
   { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
   { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, 8, st); }

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #define JB_CHUNK_BLOCKS 256        // blocks per entropy-coding CTA (one block per thread)
+#define JB_CHUNK_HIST 272          // ints per chunk histogram: 16 DC categories + 256 AC symbols
 #define JB_STUFF_TILE 4096         // bytes of un-stuffed scan data per byte-stuffing CTA
 #define JB_MAX_REGIONS 100         // brain.c:115,158
 
@@ -32,7 +33,7 @@ struct JbJob {
   uint32_t pitch;       // bytes per frame row (3 * frame width; encoder.c:132 uses the global WIDTH)
   int x, y, w, h;       // crop, w and h multiples of 16
   uint32_t coef_off;    // first int16 of this job's Y plane inside ws.coef (Cb at +w*h, Cr at +w*h*5/4)
-  uint32_t blk_off;     // first block id of this job (Y blocks, then Cb, then Cr) in ws.mask / ws.dcraw / ws.blkbits
+  uint32_t blk_off;     // first block id of this job (Y blocks, then Cb, then Cr) in ws.mask / ws.dcraw
   uint32_t chunk_off;   // first chunk id of this job (Y chunks, then Cb, then Cr)
   uint32_t tile_off;    // first byte-stuffing tile id of this job (3 segments x tiles_per_seg)
   uint32_t tiles_per_seg;
@@ -62,7 +63,7 @@ struct JbWs {
   int16_t* coef;        // zig-zagged quantised coefficients, DC differenced after k_symbol_stats
   uint64_t* mask;       // per block: bit p set <=> zig-zag position p (1..63) is non-zero
   int16_t* dcraw;       // per block: DC before differencing
-  uint32_t* blkbits;    // per block: exclusive prefix of code bits inside its chunk
+  int* chunk_hist;      // per chunk: 16 DC-category counts then 256 AC-symbol counts of its blocks (JB_CHUNK_HIST ints)
   uint32_t* chunk_bits; // per chunk: total bits
   uint32_t* chunk_base; // per chunk: bit offset inside its segment
   int* hist;            // per job: 4 x 257 symbol counts (luma DC, luma AC, chroma DC, chroma AC)
@@ -101,12 +102,11 @@ void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t
 void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st);
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
-void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
+void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st);
 void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st);
-void jb_launch_block_bits(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
 void jb_launch_scan(const JbWs& ws, int njobs, cudaStream_t st);
-void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
+void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
 void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);

@@ -775,7 +775,7 @@ void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool ro
   kern<<<grid, FT_THREADS, sizeof(FastSmem), st>>>(ws, ntiles, tiles_per_job);
 }
 
-void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148, 128, 0, st>>>(ws); }
+void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148 * 3, 128, 0, st>>>(ws); }
 
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st) {
   uint32_t threads = max_blocks * 8;

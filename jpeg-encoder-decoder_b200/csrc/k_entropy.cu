@@ -3,12 +3,12 @@
 //
 // The reference appends one symbol at a time to a global bit buffer.  Here the same bytes are
 // produced in parallel:
-//   k_block_bits   per block: number of code bits (Huffman code + magnitude bits, encoder.c:434-502);
-//                  per chunk of 256 blocks: exclusive prefix and total.
-//   k_scan         per job: exclusive prefix of the chunk totals inside each of the three scans
+//   k_scan         per job: bits of every chunk of 256 blocks from the chunk's symbol counts (k_symbol_stats) and the
+//                  code lengths; exclusive prefix of the chunk totals inside each of the three scans
 //                  (Y, Cb, Cr are independently byte-aligned scans, encoder.c:605-635); lays the
 //                  scans out in the job's scratch area and clears the words two chunks share.
-//   k_pack         per chunk: every thread appends its block's bits MSB-first at its bit offset into a
+//   k_pack         per chunk: every thread measures its block's code bits (Huffman code + magnitude bits,
+//                  encoder.c:434-502), a CTA scan gives its bit offset, then it appends the bits MSB-first into a
 //                  shared-memory image of the chunk, which is then stored as big-endian words
 //                  (the two boundary words with atomicOr).
 //   k_count_ff     per 4 KiB tile of packed scan bytes: number of 0xFF bytes (each needs a stuffed
@@ -69,41 +69,33 @@ __device__ __forceinline__ void load_tables(const JbWs& ws, int job, int s, uint
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_block_bits(JbWs ws) {
-  __shared__ uint32_t e_dc[16], e_ac[256], wsum[9];
-  const JbJob job = ws.jobs[blockIdx.y];
-  int s; uint32_t c;
-  if (!locate_chunk(job, blockIdx.x, &s, &c)) return;
-  const JbSeg seg = jb_seg(job, s);
-  load_tables(ws, blockIdx.y, s, e_dc, e_ac);
-  __syncthreads();
-  const uint32_t b = c * JB_CHUNK_BLOCKS + threadIdx.x;
-  uint32_t bits = 0;
-  if (b < seg.nblk) {
-    const int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
-    const int cat = jb_category(blk[0]);
-    bits = (e_dc[cat] & 31) + cat;
-    struct V {
-      const uint32_t* e; uint32_t n;
-      __device__ void zrl(int k) { n += k * (e[0xF0] & 31); }
-      __device__ void ac(int run, int v) { int cat = jb_category(v); n += (e[(run << 4) | cat] & 31) + cat; }
-      __device__ void eob() { n += e[0] & 31; }
-    } vis{e_ac, 0};
-    jb_walk_block(ws.mask[seg.blk0 + b], blk, vis);
-    bits += vis.n;
-  }
-  uint32_t total;
-  uint32_t ex = cta_exclusive_scan(bits, wsum, &total);
-  if (b < seg.nblk) ws.blkbits[seg.blk0 + b] = ex;
-  if (threadIdx.x == 0) ws.chunk_bits[seg.chunk0 + c] = total;
-}
-
-// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scan(JbWs ws) {
   __shared__ uint32_t wsum[9];
   __shared__ uint32_t s_word[4];
   const JbJob job = ws.jobs[blockIdx.x];
   JbJobState* st = ws.state + blockIdx.x;
+  // bits of a chunk = sum over symbols of count * (code length + magnitude bits); encoder.c:434-460
+  __shared__ uint32_t s_cost[2][JB_CHUNK_HIST];
+  {
+    const uint32_t* enc = ws.enc + (size_t)blockIdx.x * 4 * 256;
+    for (int k = threadIdx.x; k < 2 * JB_CHUNK_HIST; k += 256) {
+      const int t = k / JB_CHUNK_HIST, i = k - t * JB_CHUNK_HIST;      // t: 0 luma, 1 chroma
+      s_cost[t][i] = i < 16 ? (enc[(2 * t) * 256 + i] & 31) + i : (enc[(2 * t + 1) * 256 + (i - 16)] & 31) + ((i - 16) & 15);
+    }
+    __syncthreads();
+    const uint32_t cy = jb_chunks(jb_nby(job.w, job.h)), cc = jb_chunks(jb_nbc(job.w, job.h)), nchunks = cy + 2 * cc;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t c = warp; c < nchunks; c += 8) {
+      const int* ch = ws.chunk_hist + (size_t)(job.chunk_off + c) * JB_CHUNK_HIST;
+      const uint32_t* cost = s_cost[c < cy ? 0 : 1];
+      uint32_t sum = 0;
+      for (int i = lane; i < JB_CHUNK_HIST; i += 32) sum += (uint32_t)ch[i] * cost[i];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+      if (lane == 0) ws.chunk_bits[job.chunk_off + c] = sum;
+    }
+    __syncthreads();
+  }
   uint32_t seg_bits[3];
   for (int s = 0; s < 3; s++) {
     const JbSeg seg = jb_seg(job, s);
@@ -188,8 +180,16 @@ struct PackVisitor {
   __device__ __forceinline__ void eob() { uint32_t c = e[0]; w->put(c >> 5, c & 31); }
 };
 
-__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws) {
-  __shared__ uint32_t e_dc[16], e_ac[256];
+struct BitsVisitor {
+  const uint32_t* e;
+  uint32_t n;
+  __device__ __forceinline__ void zrl(int k) { n += k * (e[0xF0] & 31); }
+  __device__ __forceinline__ void ac(int run, int v) { const int cat = jb_category(v); n += (e[(run << 4) | cat] & 31) + cat; }
+  __device__ __forceinline__ void eob() { n += e[0] & 31; }
+};
+
+__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws, int dc_from_raw) {
+  __shared__ uint32_t e_dc[16], e_ac[256], wsum[9];
   __shared__ uint32_t stage[STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
@@ -219,16 +219,33 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws) {
   }
   __syncthreads();
 
+  // pass 1: code bits of my block (Huffman code + magnitude bits, encoder.c:434-502), then its offset inside the chunk
   const uint32_t b = c * JB_CHUNK_BLOCKS + threadIdx.x;
-  if (b < seg.nblk) {
-    const int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
-    const uint32_t start = phase + ws.blkbits[seg.blk0 + b];
+  const bool live = b < seg.nblk;
+  const int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
+  uint64_t mask = 0;
+  int dc = 0;
+  uint32_t bits = 0;
+  if (live) {
+    mask = ws.mask[seg.blk0 + b];
+    if (dc_from_raw) dc = (int)ws.dcraw[seg.blk0 + b] - (b ? (int)ws.dcraw[seg.blk0 + b - 1] : 0);   // encoder.c:168-177
+    else dc = blk[0];
+    const int cat = jb_category(dc);
+    BitsVisitor vis{e_ac, (e_dc[cat] & 31) + cat};
+    jb_walk_block(mask, blk, vis);
+    bits = vis.n;
+  }
+  uint32_t chunk_total;
+  const uint32_t ex = cta_exclusive_scan(bits, wsum, &chunk_total);
+  // pass 2: append the bits (the coefficients are now in L1)
+  if (live) {
+    const uint32_t start = phase + ex;
     BitWriter w{staged ? stage : gw, 0, start & 31, start >> 5, true, !staged};
-    const int dc = blk[0], cat = jb_category(dc);
+    const int cat = jb_category(dc);
     const uint32_t cd = e_dc[cat];
     w.put(((cd >> 5) << cat) | ((uint32_t)(dc < 0 ? dc - 1 : dc) & ((1u << cat) - 1u)), (cd & 31) + cat);   // encoder.c:434-446
     PackVisitor vis{e_ac, &w};
-    jb_walk_block(ws.mask[seg.blk0 + b], blk, vis);
+    jb_walk_block(mask, blk, vis);
     w.flush();
   }
   if (!staged) return;
@@ -403,12 +420,9 @@ __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
 
 }  // namespace
 
-void jb_launch_block_bits(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st) {
-  k_block_bits<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws);
-}
 void jb_launch_scan(const JbWs& ws, int njobs, cudaStream_t st) { k_scan<<<njobs, 256, 0, st>>>(ws); }
-void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st) {
-  k_pack<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws);
+void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st) {
+  k_pack<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
 }
 void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st) {
   k_count_ff<<<dim3(ctas_per_job, njobs), 256, 0, st>>>(ws);

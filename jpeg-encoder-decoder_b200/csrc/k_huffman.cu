@@ -14,7 +14,7 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int dc_from_raw) {
+__global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int dc_from_raw, int store_dc_diff) {
   __shared__ int h_dc[16];
   __shared__ int h_ac[256];
   const JbJob job = ws.jobs[blockIdx.y];
@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int d
     int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
     int dc;
     if (dc_from_raw) {                                   // encoder.c:168-177, plane-wide prediction
-      int cur = ws.dcraw[seg.blk0 + b];
-      int prev = b ? ws.dcraw[seg.blk0 + b - 1] : 0;
+      const int cur = ws.dcraw[seg.blk0 + b];
+      const int prev = b ? ws.dcraw[seg.blk0 + b - 1] : 0;
       dc = cur - prev;
-      blk[0] = (int16_t)dc;
+      if (store_dc_diff) blk[0] = (int16_t)dc;           // only the drop-in rgb_to_dct hands the plane back to the caller
     } else {
       dc = blk[0];
     }
@@ -51,8 +51,14 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int d
     jb_walk_block(ws.mask[seg.blk0 + b], blk, vis);
   }
   __syncthreads();
+  // per-chunk counts (k_scan turns them into the chunk's bit length once the tables exist) and the job's totals
+  int* ch = ws.chunk_hist + (size_t)(seg.chunk0 + c) * JB_CHUNK_HIST;
   int* g = ws.hist + (size_t)blockIdx.y * 4 * 257 + (s ? 2 * 257 : 0);
-  if (tid < 16 && h_dc[tid]) atomicAdd(&g[tid], h_dc[tid]);
+  if (tid < 16) {
+    ch[tid] = h_dc[tid];
+    if (h_dc[tid]) atomicAdd(&g[tid], h_dc[tid]);
+  }
+  ch[16 + tid] = h_ac[tid];
   if (h_ac[tid]) atomicAdd(&g[257 + tid], h_ac[tid]);
 }
 
@@ -200,8 +206,8 @@ __global__ void k_pack_tables(JbWs ws, int ntables) {
 
 }  // namespace
 
-void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st) {
-  k_symbol_stats<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
+void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st) {
+  k_symbol_stats<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw, store_dc_diff);
 }
 void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st) {
   int nt = njobs * 4;

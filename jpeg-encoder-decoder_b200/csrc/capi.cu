@@ -236,11 +236,11 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   { StageTimer t(c, st, ST_STATS); jb_launch_symbol_stats(ws, njobs, max_chunks, dc_from_raw, stop_after_dct ? 1 : 0, st); }
   if (stop_after_dct) { CK(cudaGetLastError()); return 0; }
   if (from != FROM_PLANES_WRITE) {
-    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, st); }
+    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }
     if (stop_after_tables) { CK(cudaGetLastError()); return 0; }
   }
   { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
-  { StageTimer t(c, st, ST_SCAN); jb_launch_scan(ws, njobs, st); }
+  { StageTimer t(c, st, ST_SCAN); jb_launch_scan(ws, njobs, max_chunks, st); c->launches++; }
   { StageTimer t(c, st, ST_PACK); jb_launch_pack(ws, njobs, max_chunks, dc_from_raw, st); }
   { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
   { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
@@ -621,7 +621,13 @@ int jpegb200_debug_build_tables(jpegb200_ctx* c, const int* freq, int ntab, void
   CK(l.ensure(wd));
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, l.stream));
   CK(cudaMemcpyAsync(l.ws.hist, freq, (size_t)ntab * 257 * sizeof(int), cudaMemcpyHostToDevice, l.stream));
-  jb_launch_build_huffman(l.ws, (int)wd.njobs, l.stream);
+  bool wide = false;                     // same rule as the encode path: 32-bit keys while every (merged) frequency stays below 2^23
+  for (int t = 0; t < ntab; t++) {
+    long long sum = 1;
+    for (int i = 0; i < 256; i++) { sum += freq[(size_t)t * 257 + i]; wide = wide || freq[(size_t)t * 257 + i] < 0; }
+    wide = wide || sum >= (1 << 23);
+  }
+  jb_launch_build_huffman(l.ws, (int)wd.njobs, wide, l.stream);
   c->launches++;
   CK(cudaMemcpyAsync(huff_out, l.ws.huff, (size_t)ntab * sizeof(JbHuff), cudaMemcpyDeviceToHost, l.stream));
   CK(cudaStreamSynchronize(l.stream));

@@ -103,9 +103,9 @@ void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool ro
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st);
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st);
-void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_build_huffman(const JbWs& ws, int njobs, bool wide_keys, cudaStream_t st);
 void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st);
-void jb_launch_scan(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_scan(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
 void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
 void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);

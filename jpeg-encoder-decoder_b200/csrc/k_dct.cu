@@ -437,17 +437,18 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
 
 
 // Bracketed quantisation of natural index I (compile-time so that the multipliers become FFMA immediates).
+// `magic` is 1.5 * 2^23 handed in through a kernel parameter: a register operand, so that the multiplier can be the FFMA immediate.
 template <int COMP, int I>
-__device__ __forceinline__ void quant_one(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad) {
+__device__ __forceinline__ void quant_one(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, float magic) {
   constexpr float khi = COMP == 0 ? jbfast::KHI_L[I] : jbfast::KHI_C[I], klo = COMP == 0 ? jbfast::KLO_L[I] : jbfast::KLO_C[I];
-  const uint32_t hi = __float_as_uint(__fmaf_rz(d[I], khi, 12582912.0f));
-  const uint32_t lo = __float_as_uint(__fmaf_rz(d[I], klo, 12582912.0f));
+  const uint32_t hi = __float_as_uint(__fmaf_rz(d[I], khi, magic));
+  const uint32_t lo = __float_as_uint(__fmaf_rz(d[I], klo, magic));
   bad |= hi ^ lo;
   q[I] = lo;                          // low 16 bits: floor(v) in two's complement
 }
 template <int COMP, int... I>
-__device__ __forceinline__ void quant_all(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, std::integer_sequence<int, I...>) {
-  (quant_one<COMP, I + 1>(d, q, bad), ...);
+__device__ __forceinline__ void quant_all(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, float magic, std::integer_sequence<int, I...>) {
+  (quant_one<COMP, I + 1>(d, q, bad, magic), ...);
 }
 // Word J of the zig-zagged block = positions 2J, 2J+1; trunc = floor + 1 for negative values (a negative
 // integer is never "decided" by the bracket, so it never reaches this point un-flagged); DC arrives truncated.
@@ -459,7 +460,7 @@ __device__ __forceinline__ void pack_one(const uint32_t (&q)[64], uint32_t (&out
   w = __vadd2(w, neg);
   out[J] = w;
   const uint32_t nz = __vminu2(w, 0x00010001u);
-  if (J < 16) m0 += nz << J; else m1 += nz << (J - 16);
+  if (J < 16) m0 = nz * (1u << J) + m0; else m1 = nz * (1u << (J - 16)) + m1;       // IMAD: keeps the ALU pipe free
 }
 template <int... J>
 __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out)[32], uint32_t& m0, uint32_t& m1, std::integer_sequence<int, J...>) {
@@ -471,7 +472,7 @@ __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out
 // integers below 2^24 and the offset cancels in every difference, so it only shows up in the DC sum, where it is
 // removed exactly together with the reference's -128 (encoder.c:92).  Returns true when some AC coefficient could not
 // be decided by the bracket.
-__device__ __forceinline__ bool block_fast(const uint32_t* __restrict__ blk, int comp, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
+__device__ __forceinline__ bool block_fast(const uint32_t* __restrict__ blk, int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
   float d[64];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -498,8 +499,8 @@ __device__ __forceinline__ bool block_fast(const uint32_t* __restrict__ blk, int
   }
   uint32_t q[64];
   uint32_t bad = 0;
-  if (comp == 0) quant_all<0>(d, q, bad, std::make_integer_sequence<int, 63>());
-  else quant_all<1>(d, q, bad, std::make_integer_sequence<int, 63>());
+  if (comp == 0) quant_all<0>(d, q, bad, magic, std::make_integer_sequence<int, 63>());
+  else quant_all<1>(d, q, bad, magic, std::make_integer_sequence<int, 63>());
   q[0] = (uint32_t)*dcq;
   uint32_t m0 = 0, m1 = 0;            // non-zero flags of pairs 0..15 and 16..31: even positions in the low half, odd in the high half
   pack_all(q, out, m0, m1, std::make_integer_sequence<int, 32>());
@@ -556,7 +557,7 @@ __device__ __forceinline__ bool tile_pos(const JbWs& ws, int t, int tiles_per_jo
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int ntiles, int tiles_per_job) {
+__global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int ntiles, int tiles_per_job, float magic) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FastSmem& sm = *reinterpret_cast<FastSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int
         ok = mcu < valid;
         blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)(p.m0 + mcu);
       }
-      const bool bad = block_fast(sm.smp[role * 32 + lane], role < 2 ? 0 : 1, out, &mask, &dcq);
+      const bool bad = block_fast(sm.smp[role * 32 + lane], role < 2 ? 0 : 1, magic, out, &mask, &dcq);
       if (ok) {
         uint4* dst = reinterpret_cast<uint4*>(ws.coef + job.coef_off + (size_t)blk * 64);
 #pragma unroll
@@ -772,7 +773,7 @@ void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool ro
   }
   const int mcus = (max_w / 16) * (max_h / 16), tiles_per_job = (mcus + FT_MCUS - 1) / FT_MCUS, ntiles = tiles_per_job * njobs;
   const int grid = ntiles < sms * ctas_per_sm[v] ? ntiles : sms * ctas_per_sm[v];
-  kern<<<grid, FT_THREADS, sizeof(FastSmem), st>>>(ws, ntiles, tiles_per_job);
+  kern<<<grid, FT_THREADS, sizeof(FastSmem), st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
 }
 
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148 * 3, 128, 0, st>>>(ws); }

@@ -69,33 +69,35 @@ __device__ __forceinline__ void load_tables(const JbWs& ws, int job, int s, uint
 }
 
 // ---------------------------------------------------------------------------------------------
+// bits of a chunk = sum over symbols of count * (code length + magnitude bits); encoder.c:434-460.  One warp per chunk.
+__global__ void __launch_bounds__(256) k_chunk_bits(JbWs ws) {
+  __shared__ uint32_t s_cost[2][JB_CHUNK_HIST];
+  const JbJob job = ws.jobs[blockIdx.y];
+  const uint32_t* enc = ws.enc + (size_t)blockIdx.y * 4 * 256;
+  for (int k = threadIdx.x; k < 2 * JB_CHUNK_HIST; k += 256) {
+    const int t = k / JB_CHUNK_HIST, i = k - t * JB_CHUNK_HIST;      // t: 0 luma, 1 chroma
+    s_cost[t][i] = i < 16 ? (enc[(2 * t) * 256 + i] & 31) + i : (enc[(2 * t + 1) * 256 + (i - 16)] & 31) + ((i - 16) & 15);
+  }
+  __syncthreads();
+  const uint32_t cy = jb_chunks(jb_nby(job.w, job.h)), cc = jb_chunks(jb_nbc(job.w, job.h)), nchunks = cy + 2 * cc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t c = blockIdx.x * 8 + warp; c < nchunks; c += gridDim.x * 8) {
+    const int* ch = ws.chunk_hist + (size_t)(job.chunk_off + c) * JB_CHUNK_HIST;
+    const uint32_t* cost = s_cost[c < cy ? 0 : 1];
+    uint32_t sum = 0;
+    for (int i = lane; i < JB_CHUNK_HIST; i += 32) sum += (uint32_t)ch[i] * cost[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+    if (lane == 0) ws.chunk_bits[job.chunk_off + c] = sum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scan(JbWs ws) {
   __shared__ uint32_t wsum[9];
   __shared__ uint32_t s_word[4];
   const JbJob job = ws.jobs[blockIdx.x];
   JbJobState* st = ws.state + blockIdx.x;
-  // bits of a chunk = sum over symbols of count * (code length + magnitude bits); encoder.c:434-460
-  __shared__ uint32_t s_cost[2][JB_CHUNK_HIST];
-  {
-    const uint32_t* enc = ws.enc + (size_t)blockIdx.x * 4 * 256;
-    for (int k = threadIdx.x; k < 2 * JB_CHUNK_HIST; k += 256) {
-      const int t = k / JB_CHUNK_HIST, i = k - t * JB_CHUNK_HIST;      // t: 0 luma, 1 chroma
-      s_cost[t][i] = i < 16 ? (enc[(2 * t) * 256 + i] & 31) + i : (enc[(2 * t + 1) * 256 + (i - 16)] & 31) + ((i - 16) & 15);
-    }
-    __syncthreads();
-    const uint32_t cy = jb_chunks(jb_nby(job.w, job.h)), cc = jb_chunks(jb_nbc(job.w, job.h)), nchunks = cy + 2 * cc;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (uint32_t c = warp; c < nchunks; c += 8) {
-      const int* ch = ws.chunk_hist + (size_t)(job.chunk_off + c) * JB_CHUNK_HIST;
-      const uint32_t* cost = s_cost[c < cy ? 0 : 1];
-      uint32_t sum = 0;
-      for (int i = lane; i < JB_CHUNK_HIST; i += 32) sum += (uint32_t)ch[i] * cost[i];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
-      if (lane == 0) ws.chunk_bits[job.chunk_off + c] = sum;
-    }
-    __syncthreads();
-  }
   uint32_t seg_bits[3];
   for (int s = 0; s < 3; s++) {
     const JbSeg seg = jb_seg(job, s);
@@ -420,7 +422,10 @@ __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
 
 }  // namespace
 
-void jb_launch_scan(const JbWs& ws, int njobs, cudaStream_t st) { k_scan<<<njobs, 256, 0, st>>>(ws); }
+void jb_launch_scan(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st) {
+  k_chunk_bits<<<dim3((max_chunks + 63) / 64, njobs), 256, 0, st>>>(ws);
+  k_scan<<<njobs, 256, 0, st>>>(ws);
+}
 void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st) {
   k_pack<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
 }

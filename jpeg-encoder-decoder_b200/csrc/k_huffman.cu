@@ -75,6 +75,19 @@ struct TabSmem {
 
 constexpr int TAB_WARPS = 4;
 
+// warp-wide minimum: one REDUX for 32-bit keys, a shuffle tree for 64-bit keys
+__device__ __forceinline__ unsigned warp_min(unsigned v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
+__device__ __forceinline__ unsigned long long warp_min(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+
+// KeyT = unsigned when every frequency is below 2^23 (crops up to 2^23 pixels), else unsigned long long.
+template <typename KeyT>
 __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int ntables) {
   __shared__ TabSmem sm_all[TAB_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -87,58 +100,59 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
   JbJobState* state = ws.state + job;
   (void)which;
 
-  for (int k = lane; k < 257 + 31; k += 32) {
+  // Symbol k = lane + 32*j lives in slot j of lane `lane`: frequency, code length and chain head stay in registers for
+  // the whole merge loop; only the chain links (next/tail, touched by one lane, never read back by the selection) are
+  // in shared memory.
+  int rf[9], rl[9], rg[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const int k = lane + 32 * j;
     int f = 0;
     if (k < 256) f = hist[k];
     else if (k == 256) f = 1;                          // reserved code point, encoder.c:367
-    sm.freq[k] = f;
-    sm.len[k] = 0;
-    sm.grp[k] = k;
+    rf[j] = f;
+    rl[j] = 0;
+    rg[j] = k;
     if (k < 257) { sm.next[k] = -1; sm.tail[k] = k; }
   }
   __syncwarp();
 
-  // -- merge loop (encoder.c:190-228).  key = (freq, 511 - index): smallest key = least frequent,
-  //    ties to the LATER index, exactly the reference's ascending scan with '<='.
+  // -- merge loop (encoder.c:190-228).  key = (frequency << 9) | (511 - index): smallest key = least frequent, ties to
+  //    the LATER index, exactly the reference's ascending scan with '<=' (encoder.c:196-207).
+  constexpr KeyT NONE = ~(KeyT)0;
   for (;;) {
-    unsigned long long best1 = ~0ull, best2 = ~0ull;
+    KeyT best1 = NONE, best2 = NONE;
 #pragma unroll
     for (int j = 0; j < 9; j++) {
-      int k = lane + 32 * j;
-      int f = sm.freq[k];
-      unsigned long long key = f ? (((unsigned long long)(unsigned)f << 32) | (unsigned)(511 - k)) : ~0ull;
+      const KeyT key = rf[j] ? (((KeyT)(unsigned)rf[j] << 9) | (KeyT)(511 - (lane + 32 * j))) : NONE;
       if (key < best1) { best2 = best1; best1 = key; }
       else if (key < best2) best2 = key;
     }
-    // warp-wide two smallest
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, best1, o);
-      unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, best2, o);
-      unsigned long long lo = best1 < o1 ? best1 : o1;
-      unsigned long long hi = best1 < o1 ? o1 : best1;          // the larger of the two minima
-      unsigned long long m2 = best2 < o2 ? best2 : o2;
-      best1 = lo;
-      best2 = hi < m2 ? hi : m2;
-    }
-    if (best2 == ~0ull) break;
-    const int v1 = 511 - (int)(unsigned)(best1 & 0xFFFFFFFFull);
-    const int v2 = 511 - (int)(unsigned)(best2 & 0xFFFFFFFFull);
-    // every member of both chains gets one bit longer and now belongs to v1
+    const KeyT g1 = warp_min(best1);
+    const KeyT g2 = warp_min(best1 == g1 ? best2 : best1);      // keys are unique: the index is part of them
+    if (g2 == NONE) break;
+    const int v1 = 511 - (int)(g1 & 511u), v2 = 511 - (int)(g2 & 511u);
+    const int fsum = (int)(g1 >> 9) + (int)(g2 >> 9);
+    // every member of both chains gets one bit longer and now belongs to v1; v1 carries the merged frequency
 #pragma unroll
     for (int j = 0; j < 9; j++) {
-      int k = lane + 32 * j;
-      int g = sm.grp[k];
-      if (g == v1 || g == v2) { sm.len[k]++; sm.grp[k] = v1; }
+      const int k = lane + 32 * j;
+      if (rg[j] == v1 || rg[j] == v2) { rl[j]++; rg[j] = v1; }
+      if (k == v1) rf[j] = fsum;
+      if (k == v2) rf[j] = 0;
     }
     if (lane == 0) {
-      sm.freq[v1] += sm.freq[v2];
-      sm.freq[v2] = 0;
       sm.next[sm.tail[v1]] = v2;
       sm.tail[v1] = sm.tail[v2];
     }
-    __syncwarp();
   }
+#pragma unroll
+  for (int j = 0; j < 9; j++) {
+    const int k = lane + 32 * j;
+    sm.freq[k] = rf[j];
+    sm.len[k] = rl[j];
+  }
+  __syncwarp();
 
   // The rest is short and strictly sequential: lane 0 replays it, the warp copies results out.
   __shared__ int s_clf[TAB_WARPS][32];
@@ -152,14 +166,32 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
   for (int k = lane; k < 256; k += 32) { sorted[k] = -1; slen[k] = 0; code[k] = -1; }
   clf[lane] = 0;
   __syncwarp();
-  if (lane == 0) {
+  // code_len_freq (encoder.c:230-236): histogram of the lengths of all 257 symbols
+  {
     bool overflow = false;
-    for (int k = 0; k < 257; k++) {
+    for (int k = lane; k < 257; k += 32) {
       int l = sm.len[k];
       if (l > 31) { overflow = true; l = 31; }         // the reference would write past code_len_freq[32]
-      if (l) clf[l]++;
+      if (l) atomicAdd(&clf[l], 1);
     }
     if (overflow) atomicOr(&state->error, (uint32_t)JB_ERR_CODELEN);
+  }
+  // sym_sorted (encoder.c:262-268): symbols 0..255 ordered by (pre-limit length, symbol); ballots give each symbol its rank
+  {
+    int n = 0;
+    for (int l = 1; l < 32; l++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int k = lane + 32 * j;
+        const bool hit = sm.len[k] == l;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) sorted[n + __popc(bal & ((1u << lane) - 1u))] = k;
+        n += __popc(bal);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
     for (int i = 31; i > 16; i--)                        // encoder.c:239-254
       while (clf[i] > 0) {
         int j = i - 2;
@@ -167,9 +199,6 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
         clf[i] -= 2; clf[i - 1]++; clf[j + 1] += 2; clf[j]--;
       }
     { int i = 16; while (i > 0 && clf[i] == 0) i--; clf[i]--; }   // encoder.c:255-258
-    int n = 0;
-    for (int l = 1; l < 32; l++)                         // encoder.c:262-268
-      for (int k = 0; k < 256; k++) if (sm.len[k] == l) sorted[n++] = k;
     int k = 0, cd = 0;
     for (int l = 1; l <= 16; l++) {                      // encoder.c:271-276 and :280-300
       for (int c = 0; c < clf[l] && k < 256 && sorted[k] >= 0; c++) { slen[sorted[k]] = l; code[sorted[k]] = cd++; k++; }
@@ -209,9 +238,10 @@ __global__ void k_pack_tables(JbWs ws, int ntables) {
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st) {
   k_symbol_stats<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw, store_dc_diff);
 }
-void jb_launch_build_huffman(const JbWs& ws, int njobs, cudaStream_t st) {
+void jb_launch_build_huffman(const JbWs& ws, int njobs, bool wide_keys, cudaStream_t st) {
   int nt = njobs * 4;
-  k_build_huffman<<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
+  if (wide_keys) k_build_huffman<unsigned long long><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
+  else k_build_huffman<unsigned><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
 }
 void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st) {
   k_pack_tables<<<njobs * 4, 256, 0, st>>>(ws, njobs * 4);

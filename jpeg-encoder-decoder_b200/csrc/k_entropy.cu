@@ -23,35 +23,6 @@
 
 namespace {
 
-constexpr int STAGE_WORDS = 4096;   // 16 KiB shared-memory image of one chunk's bits
-
-// Exclusive prefix sum over the 256 threads of a CTA; returns the exclusive prefix, *total = sum.
-__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* warp_sums /*[9]*/, uint32_t* total) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-    if (lane >= o) inc += n;
-  }
-  __syncthreads();                       // protects warp_sums against the previous use
-  if (lane == 31) warp_sums[warp] = inc;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < 8 ? warp_sums[lane] : 0;
-    uint32_t winc = w;
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, winc, o);
-      if (lane >= o) winc += n;
-    }
-    if (lane < 8) warp_sums[lane] = winc - w;
-    if (lane == 7) warp_sums[8] = winc;
-  }
-  __syncthreads();
-  *total = warp_sums[8];
-  return warp_sums[warp] + inc - v;
-}
 
 // Resolve (chunk index inside the job) -> segment and chunk inside the segment.
 __device__ __forceinline__ bool locate_chunk(const JbJob& job, uint32_t c, int* s, uint32_t* cs) {
@@ -60,12 +31,6 @@ __device__ __forceinline__ bool locate_chunk(const JbJob& job, uint32_t c, int* 
   *s = c < cy ? 0 : (c < cy + cc ? 1 : 2);
   *cs = c - (*s == 0 ? 0 : *s == 1 ? cy : cy + cc);
   return true;
-}
-
-__device__ __forceinline__ void load_tables(const JbWs& ws, int job, int s, uint32_t* e_dc, uint32_t* e_ac) {
-  const uint32_t* enc = ws.enc + ((size_t)job * 4 + (s ? 2 : 0)) * 256;
-  if (threadIdx.x < 16) e_dc[threadIdx.x] = enc[threadIdx.x];
-  e_ac[threadIdx.x] = enc[256 + threadIdx.x];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -138,60 +103,23 @@ __global__ void __launch_bounds__(256) k_scan(JbWs ws) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// MSB-first bit appender of one thread.  `dst` may be shared or global memory; the first word a thread
-// emits and its final partial word can be shared with its neighbours and are OR-ed atomically, every
-// word in between is exclusively its own.
-struct BitWriter {
-  uint32_t* dst;
-  uint64_t acc;
-  uint32_t n;       // valid low bits of acc (< 32 between calls)
-  uint32_t wi;      // next word index
-  bool first;
-  bool direct;      // fallback for chunks larger than the shared-memory image: straight to global memory,
-                    // every word OR-ed atomically and already in big-endian byte order
-  __device__ __forceinline__ void emit(uint32_t w) {
-    if (direct) atomicOr(dst + wi, __byte_perm(w, 0, 0x0123));
-    else if (first) atomicOr(dst + wi, w);
-    else dst[wi] = w;
-    first = false;
-    wi++;
-  }
-  __device__ __forceinline__ void put(uint32_t bits, uint32_t len) {   // len <= 31
-    acc = (acc << len) | bits;
-    n += len;
-    if (n >= 32) { n -= 32; emit((uint32_t)(acc >> n)); }
-  }
-  __device__ __forceinline__ void flush() {
-    if (n) {
-      const uint32_t w = (uint32_t)(acc << (32 - n));
-      atomicOr(dst + wi, direct ? __byte_perm(w, 0, 0x0123) : w);
-    }
-  }
-};
+constexpr int PACK_TOK = 8;                       // tokens per thread and round
+constexpr int PACK_ROUND = JB_CHUNK_BLOCKS * PACK_TOK;
+// a token is at most 3 ZRL codes + one code + 10 magnitude bits = 74 bits: shared-memory image of one round's bits
+constexpr int STAGE_WORDS = (31 + PACK_ROUND * 74 + 31) / 32 + 1;
 
-struct PackVisitor {
-  const uint32_t* e;
-  BitWriter* w;
-  __device__ __forceinline__ void zrl(int k) { uint32_t c = e[0xF0]; for (int i = 0; i < k; i++) w->put(c >> 5, c & 31); }
-  __device__ __forceinline__ void ac(int run, int v) {
-    const int cat = jb_category(v);
-    const uint32_t c = e[(run << 4) | cat];
-    const uint32_t mag = (uint32_t)(v < 0 ? v - 1 : v) & ((1u << cat) - 1u);      // encoder.c:455-457
-    w->put(((c >> 5) << cat) | mag, (c & 31) + cat);
-  }
-  __device__ __forceinline__ void eob() { uint32_t c = e[0]; w->put(c >> 5, c & 31); }
-};
-
-struct BitsVisitor {
-  const uint32_t* e;
-  uint32_t n;
-  __device__ __forceinline__ void zrl(int k) { n += k * (e[0xF0] & 31); }
-  __device__ __forceinline__ void ac(int run, int v) { const int cat = jb_category(v); n += (e[(run << 4) | cat] & 31) + cat; }
-  __device__ __forceinline__ void eob() { n += e[0] & 31; }
-};
+// OR `len` (<= 32) bits into the MSB-first bit image at bit position pos (rare path: threads whose tokens carry ZRLs).
+__device__ __forceinline__ void or_bits(uint32_t* img, uint32_t pos, uint32_t bits, uint32_t len) {
+  if (!len) return;
+  const uint32_t sh = pos & 31, wi = pos >> 5;
+  const uint64_t v = ((uint64_t)bits << (64 - len)) >> sh;          // left-aligned at bit `sh` of a 64-bit window
+  atomicOr(img + wi, (uint32_t)(v >> 32));
+  if ((uint32_t)v) atomicOr(img + wi + 1, (uint32_t)v);
+}
 
 __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws, int dc_from_raw) {
-  __shared__ uint32_t e_dc[16], e_ac[256], wsum[9];
+  __shared__ JbChunkTokens ct;
+  __shared__ uint32_t enc[272];      // 0..255 AC symbols, 256..271 DC categories: code << 5 | length
   __shared__ uint32_t stage[STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
@@ -199,63 +127,100 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws, int dc_from_r
   int s; uint32_t c;
   if (!locate_chunk(job, blockIdx.x, &s, &c)) return;
   const JbSeg seg = jb_seg(job, s);
-  load_tables(ws, blockIdx.y, s, e_dc, e_ac);
-
+  const int tid = threadIdx.x;
+  {
+    const uint32_t* g = ws.enc + ((size_t)blockIdx.y * 4 + (s ? 2 : 0)) * 256;
+    enc[tid] = g[256 + tid];
+    if (tid < 16) enc[256 + tid] = g[tid];
+  }
   const uint32_t base_bits = ws.chunk_base[seg.chunk0 + c], total = ws.chunk_bits[seg.chunk0 + c];
   const uint32_t phase = base_bits & 31;
-  const uint32_t nwords = (phase + total + 31) >> 5;
-  const bool staged = nwords <= STAGE_WORDS;
-  uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);
-  // a word is shared with a neighbouring chunk unless this chunk covers all 32 of its bits
+  uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the chunk's first bit
+  // the chunk's first / last word is shared with a neighbouring chunk unless the chunk covers all 32 of its bits
   const bool first_shared = phase != 0 || total < 32;
-  const bool last_shared = ((phase + total) & 31) != 0;
+  const uint32_t last_word = (phase + total - 1) >> 5;
+  const uint32_t ntok = jb_stage_chunk(ws, seg, c, dc_from_raw, 0, ct);      // its barriers also cover the tables
+  const int16_t* coef = ws.coef + seg.coef0 + (size_t)c * JB_CHUNK_BLOCKS * 64;
+  const uint32_t zrl_code = enc[0xF0] >> 5, zrl_len = enc[0xF0] & 31;
 
-  if (staged) {
-    for (uint32_t k = threadIdx.x; k < nwords; k += JB_CHUNK_BLOCKS) stage[k] = 0;
-  } else {
-    for (uint32_t k = threadIdx.x + 1; k + 1 < nwords; k += JB_CHUNK_BLOCKS) gw[k] = 0;   // interior words are ours alone
-    if (threadIdx.x == 0) {
-      if (!first_shared) gw[0] = 0;
-      if (!last_shared && nwords > 1) gw[nwords - 1] = 0;
+  // Rounds of 256 x PACK_TOK tokens.  A thread builds the code words of its PACK_TOK consecutive tokens (Huffman code and
+  // magnitude bits, encoder.c:434-460) in registers; a CTA scan of the bit counts gives its bit offset; it concatenates
+  // them in a 288-bit register accumulator and stores the words into the round's shared-memory image (first and last
+  // word OR-ed, they may be shared with the neighbours); the image is then flushed to the scan's scratch area.
+  uint32_t rbase = phase;            // chunk-relative bit position where the round starts (bit 0 = MSB of gw[0])
+  if (tid == 0) stage[0] = 0;
+  for (uint32_t r0 = 0; r0 < ntok; r0 += PACK_ROUND) {
+    const uint32_t first = min(ntok, r0 + tid * PACK_TOK), count = min((uint32_t)PACK_TOK, ntok - first);
+    uint32_t word[PACK_TOK], len[PACK_TOK], zr = 0, nbits = 0;
+    JbCursor cur = jb_cursor_init(ct, min(first, ntok - 1));
+#pragma unroll
+    for (int j = 0; j < PACK_TOK; j++) {
+      const JbToken t = jb_next_token(ct, cur, coef);                 // running past the chunk's last token is harmless (masks are 0)
+      const bool live = (uint32_t)j < count;
+      const uint32_t e = enc[t.idx];
+      const int cat = t.idx & 15;
+      const uint32_t mag = (uint32_t)(t.value < 0 ? t.value - 1 : t.value) & ((1u << cat) - 1u);      // encoder.c:441-443, :455-457
+      word[j] = ((e >> 5) << cat) | mag;
+      len[j] = live ? (e & 31) + cat : 0;
+      const uint32_t z = live ? (uint32_t)t.zrl : 0;
+      zr |= z << (2 * j);
+      nbits += len[j] + z * zrl_len;
     }
-  }
-  __syncthreads();
-
-  // pass 1: code bits of my block (Huffman code + magnitude bits, encoder.c:434-502), then its offset inside the chunk
-  const uint32_t b = c * JB_CHUNK_BLOCKS + threadIdx.x;
-  const bool live = b < seg.nblk;
-  const int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
-  uint64_t mask = 0;
-  int dc = 0;
-  uint32_t bits = 0;
-  if (live) {
-    mask = ws.mask[seg.blk0 + b];
-    if (dc_from_raw) dc = (int)ws.dcraw[seg.blk0 + b] - (b ? (int)ws.dcraw[seg.blk0 + b - 1] : 0);   // encoder.c:168-177
-    else dc = blk[0];
-    const int cat = jb_category(dc);
-    BitsVisitor vis{e_ac, (e_dc[cat] & 31) + cat};
-    jb_walk_block(mask, blk, vis);
-    bits = vis.n;
-  }
-  uint32_t chunk_total;
-  const uint32_t ex = cta_exclusive_scan(bits, wsum, &chunk_total);
-  // pass 2: append the bits (the coefficients are now in L1)
-  if (live) {
-    const uint32_t start = phase + ex;
-    BitWriter w{staged ? stage : gw, 0, start & 31, start >> 5, true, !staged};
-    const int cat = jb_category(dc);
-    const uint32_t cd = e_dc[cat];
-    w.put(((cd >> 5) << cat) | ((uint32_t)(dc < 0 ? dc - 1 : dc) & ((1u << cat) - 1u)), (cd & 31) + cat);   // encoder.c:434-446
-    PackVisitor vis{e_ac, &w};
-    jb_walk_block(mask, blk, vis);
-    w.flush();
-  }
-  if (!staged) return;
-  __syncthreads();
-  for (uint32_t k = threadIdx.x; k < nwords; k += JB_CHUNK_BLOCKS) {
-    const uint32_t w = __byte_perm(stage[k], 0, 0x0123);     // first bit of the stream = MSB of the first byte
-    if ((k == 0 && first_shared) || (k == nwords - 1 && last_shared)) atomicOr(gw + k, w);
-    else gw[k] = w;
+    uint32_t round_total;
+    const uint32_t ex = cta_exclusive_scan(nbits, ct.wsum, &round_total);
+    const uint32_t r_in = rbase & 31, endbit = r_in + round_total, nwr = (endbit + 31) >> 5;
+    for (uint32_t k = tid + 1; k < nwr + 1; k += JB_CHUNK_BLOCKS) stage[k] = 0;        // stage[0] carries the previous round's tail
+    __syncthreads();
+    const uint32_t sbit = r_in + ex;
+    if (zr == 0) {
+      uint32_t A[9];
+#pragma unroll
+      for (int r = 0; r < 9; r++) A[r] = 0;
+      uint32_t tot = sbit & 31;
+#pragma unroll
+      for (int j = 0; j < PACK_TOK; j++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) A[r] = __funnelshift_l(A[r + 1], A[r], len[j]);
+        A[8] = (A[8] << len[j]) | (len[j] ? word[j] : 0u);
+        tot += len[j];
+      }
+      const uint32_t pad = (32u - (tot & 31u)) & 31u;
+#pragma unroll
+      for (int r = 0; r < 8; r++) A[r] = __funnelshift_l(A[r + 1], A[r], pad);
+      A[8] <<= pad;
+      const int nw = nbits ? (int)((tot + pad) >> 5) : 0;
+      uint32_t* dst = stage + (sbit >> 5) - (9 - nw);
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        if (r >= 9 - nw) {
+          if (r == 9 - nw || r == 8) atomicOr(dst + r, A[r]);
+          else dst[r] = A[r];
+        }
+      }
+    } else {
+      uint32_t pos = sbit;
+#pragma unroll
+      for (int j = 0; j < PACK_TOK; j++) {
+        for (uint32_t z = (zr >> (2 * j)) & 3u; z; z--) { or_bits(stage, pos, zrl_code, zrl_len); pos += zrl_len; }
+        or_bits(stage, pos, word[j], len[j]);
+        pos += len[j];
+      }
+    }
+    __syncthreads();
+    // flush: complete words of the image; the very last word of the chunk even if partial
+    const bool last_round = r0 + PACK_ROUND >= ntok;
+    const uint32_t full = endbit >> 5, rem = endbit & 31, w0 = rbase >> 5;
+    const uint32_t nflush = full + ((last_round && rem) ? 1u : 0u);
+    for (uint32_t k = tid; k < nflush; k += JB_CHUNK_BLOCKS) {
+      const uint32_t w = __byte_perm(stage[k], 0, 0x0123);     // first bit of the stream = MSB of the first byte
+      const uint32_t g = w0 + k;
+      if ((g == 0 && first_shared) || (g == last_word && k == full)) atomicOr(gw + g, w);
+      else gw[g] = w;
+    }
+    const uint32_t tail = (!last_round && rem) ? stage[full] : 0u;
+    __syncthreads();
+    if (tid == 0) stage[0] = tail;
+    rbase += round_total;
   }
 }
 

@@ -15,8 +15,8 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int dc_from_raw, int store_dc_diff) {
-  __shared__ int h_dc[16];
-  __shared__ int h_ac[256];
+  __shared__ JbChunkTokens ct;
+  __shared__ int h[8][JB_CHUNK_HIST];                    // one histogram per warp: 16 DC categories, then 256 AC symbols
   const JbJob job = ws.jobs[blockIdx.y];
   const uint32_t cy = jb_chunks(jb_nby(job.w, job.h)), cc = jb_chunks(jb_nbc(job.w, job.h));
   uint32_t c = blockIdx.x;
@@ -24,42 +24,33 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_symbol_stats(JbWs ws, int d
   const int s = c < cy ? 0 : (c < cy + cc ? 1 : 2);
   c -= (s == 0 ? 0 : s == 1 ? cy : cy + cc);
   const JbSeg seg = jb_seg(job, s);
-  const int tid = threadIdx.x;
-  if (tid < 16) h_dc[tid] = 0;
-  h_ac[tid] = 0;
-  __syncthreads();
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int k = tid; k < 8 * JB_CHUNK_HIST; k += JB_CHUNK_BLOCKS) (&h[0][0])[k] = 0;
+  const uint32_t total = jb_stage_chunk(ws, seg, c, dc_from_raw, store_dc_diff, ct);   // its barriers also cover the zeroing
 
-  const uint32_t b = c * JB_CHUNK_BLOCKS + tid;
-  if (b < seg.nblk) {
-    int16_t* blk = ws.coef + seg.coef0 + (size_t)b * 64;
-    int dc;
-    if (dc_from_raw) {                                   // encoder.c:168-177, plane-wide prediction
-      const int cur = ws.dcraw[seg.blk0 + b];
-      const int prev = b ? ws.dcraw[seg.blk0 + b - 1] : 0;
-      dc = cur - prev;
-      if (store_dc_diff) blk[0] = (int16_t)dc;           // only the drop-in rgb_to_dct hands the plane back to the caller
-    } else {
-      dc = blk[0];
+  // every thread takes an equal run of consecutive tokens; h[w][0..15] DC categories, h[w][16..271] AC symbols
+  const uint32_t share = (total + JB_CHUNK_BLOCKS - 1) / JB_CHUNK_BLOCKS, first = min(total, tid * share), count = min(share, total - first);
+  const int16_t* coef = ws.coef + seg.coef0 + (size_t)c * JB_CHUNK_BLOCKS * 64;
+  int* hw = h[warp];
+  JbCursor cur = jb_cursor_init(ct, first);
+  for (uint32_t j = 0; j < share; j++) {
+    if (j < count) {
+      const JbToken t = jb_next_token(ct, cur, coef);
+      atomicAdd(&hw[t.idx < 256 ? 16 + t.idx : t.idx - 256], 1);
+      if (t.zrl) atomicAdd(&hw[16 + 0xF0], t.zrl);
     }
-    atomicAdd(&h_dc[jb_category(dc)], 1);
-    struct V {
-      int* h;
-      __device__ void zrl(int n) { atomicAdd(&h[0xF0], n); }
-      __device__ void ac(int run, int v) { atomicAdd(&h[(run << 4) | jb_category(v)], 1); }
-      __device__ void eob() { atomicAdd(&h[0], 1); }
-    } vis{h_ac};
-    jb_walk_block(ws.mask[seg.blk0 + b], blk, vis);
   }
   __syncthreads();
-  // per-chunk counts (k_scan turns them into the chunk's bit length once the tables exist) and the job's totals
+  // per-chunk counts (k_chunk_bits turns them into the chunk's bit length once the tables exist) and the job's totals
   int* ch = ws.chunk_hist + (size_t)(seg.chunk0 + c) * JB_CHUNK_HIST;
   int* g = ws.hist + (size_t)blockIdx.y * 4 * 257 + (s ? 2 * 257 : 0);
-  if (tid < 16) {
-    ch[tid] = h_dc[tid];
-    if (h_dc[tid]) atomicAdd(&g[tid], h_dc[tid]);
+  for (int k = tid; k < JB_CHUNK_HIST; k += JB_CHUNK_BLOCKS) {
+    int v = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) v += h[w][k];
+    ch[k] = v;
+    if (v) atomicAdd(&g[k < 16 ? k : 257 + (k - 16)], v);
   }
-  ch[16 + tid] = h_ac[tid];
-  if (h_ac[tid]) atomicAdd(&g[257 + tid], h_ac[tid]);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -34,7 +34,11 @@ int jpegb200_configure(jpegb200_ctx *ctx, int frames_per_wave, int lanes);
 /* DCT arithmetic: 0 (default) = FP32 filter transform + literal FP64 recomputation of every block the
  * filter cannot decide (same bytes); 1 = literal FP64 chain of encoder.c:87-108 for every block. */
 int jpegb200_set_exact_dct(jpegb200_ctx *ctx, int on);
-/* Diagnostics: blocks that the last wave of `lane` sent to the literal chain. */
+/* Batched entry points (encode_batch, encode_batch_host, encode_regions, compare_encode): 1 (default) = token path
+ * (pixels -> token stream + histograms in one kernel, bit packer streams tokens; no coefficient planes in memory);
+ * 0 = plane path (materialised int16 planes, the kernels the stage functions use).  Same bytes either way. */
+int jpegb200_set_token_path(jpegb200_ctx *ctx, int on);
+/* Diagnostics: blocks that the last wave of `lane` sent to the literal chain (plane path). */
 int jpegb200_debug_fix_count(jpegb200_ctx *ctx, int lane, uint32_t *count);
 
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */

@@ -60,13 +60,14 @@ struct PinBuf {
 
 // Sizes of one wave's workspace.
 struct WaveDims {
-  size_t njobs = 0, coefs = 0, blocks = 0, chunks = 0, scratch_words = 0, tiles = 0;
+  size_t njobs = 0, coefs = 0, blocks = 0, chunks = 0, scratch_words = 0, tiles = 0, toks = 0, runs = 0;
+  bool planes = true;         // the wave needs coefficient planes (plane path); the token path does not
 };
 
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr, sizes_ready = nullptr;
-  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix;
+  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
@@ -78,13 +79,19 @@ struct Lane {
     cudaError_t e;
     if ((e = jobs.ensure(d.njobs * sizeof(JbJob))) != cudaSuccess) return e;
     if ((e = state_hist.ensure(d.njobs * (sizeof(JbJobState) + 4 * 257 * sizeof(int)) + 16)) != cudaSuccess) return e;
-    if ((e = fix.ensure(d.blocks * sizeof(uint2))) != cudaSuccess) return e;
-    if ((e = coef.ensure(d.coefs * sizeof(int16_t))) != cudaSuccess) return e;
-    if ((e = mask.ensure(d.blocks * sizeof(uint64_t))) != cudaSuccess) return e;
-    if ((e = dcraw.ensure(d.blocks * sizeof(int16_t))) != cudaSuccess) return e;
-    if ((e = chunk_hist.ensure(d.chunks * JB_CHUNK_HIST * sizeof(int))) != cudaSuccess) return e;
-    if ((e = chunk_bits.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
-    if ((e = chunk_base.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
+    if (d.planes) {
+      if ((e = fix.ensure(d.blocks * sizeof(uint2))) != cudaSuccess) return e;
+      if ((e = coef.ensure(d.coefs * sizeof(int16_t))) != cudaSuccess) return e;
+      if ((e = mask.ensure(d.blocks * sizeof(uint64_t))) != cudaSuccess) return e;
+      if ((e = dcraw.ensure(d.blocks * sizeof(int16_t))) != cudaSuccess) return e;
+      if ((e = chunk_hist.ensure(d.chunks * JB_CHUNK_HIST * sizeof(int))) != cudaSuccess) return e;
+      if ((e = chunk_bits.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = chunk_base.ensure(d.chunks * sizeof(uint32_t))) != cudaSuccess) return e;
+    } else {
+      if ((e = tok.ensure(d.toks * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = runs.ensure(d.runs * sizeof(JbRun))) != cudaSuccess) return e;
+      if ((e = run_base.ensure(d.runs * sizeof(uint32_t))) != cudaSuccess) return e;
+    }
     if ((e = huff.ensure(d.njobs * 4 * sizeof(JbHuff))) != cudaSuccess) return e;
     if ((e = enc.ensure(d.njobs * 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return e;
     if ((e = scratch.ensure(d.scratch_words * sizeof(uint32_t))) != cudaSuccess) return e;
@@ -105,10 +112,13 @@ struct Lane {
     ws.tile_ff = (uint32_t*)tile_ff.p;
     ws.fix_count = (uint32_t*)((char*)state_hist.p + sh_bytes - 16);
     ws.fix_list = (uint2*)fix.p;
+    ws.tok = (uint32_t*)tok.p;
+    ws.runs = (JbRun*)runs.p;
+    ws.run_base = (uint32_t*)run_base.p;
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &in, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -120,7 +130,7 @@ struct Lane {
 
 // Per-job workspace footprint for a w x h crop whose output slot holds `slot` bytes.
 struct JobDims {
-  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg;
+  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs;
 };
 JobDims job_dims(int w, int h, size_t slot) {
   JobDims d;
@@ -133,6 +143,8 @@ JobDims job_dims(int w, int h, size_t slot) {
   words = (words + 3) & ~(size_t)3;
   d.scratch_words = (uint32_t)words;
   d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
+  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS;
+  d.runs = 4u * jb_runs_chroma(w, h);
   return d;
 }
 
@@ -154,6 +166,8 @@ __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t fram
   j.out = out0 + (size_t)i * slot;
   j.out_cap = slot > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)slot;
   j.src_bytes = 3u * (uint32_t)w * (uint32_t)h;
+  j.tok_off = (uint32_t)i * d.toks;
+  j.run_off = (uint32_t)i * d.runs;
   jobs[i] = j;
 }
 
@@ -163,6 +177,7 @@ struct jpegb200_ctx {
   int device = 0;
   int frames_per_wave = 8;
   int exact_dct = 0;          // 1 = literal FP64 chain for every block (the on-device checker of the fast path)
+  int token_path = 1;         // batched entry points: 1 = k_pixels_to_tokens + k_pack_runs, 0 = coefficient planes (k_dct.cu + chunk kernels)
   std::vector<Lane> lanes;
   cudaEvent_t fork = nullptr;
   uint64_t launches = 0;
@@ -194,7 +209,7 @@ int make_lanes(jpegb200_ctx* c, int n) {
 }
 
 // Stage ids for the optional per-kernel CUDA-event timing (jpegb200_get_stage_timing).
-enum Stage { ST_DCT = 0, ST_MASKS, ST_STATS, ST_HUFF, ST_TABLES, ST_BITS, ST_SCAN, ST_PACK, ST_COUNTFF, ST_LAYOUT, ST_STUFF, ST_FIX, ST_COUNT };
+enum Stage { ST_DCT = 0, ST_MASKS, ST_STATS, ST_HUFF, ST_TABLES, ST_BITS, ST_SCAN, ST_PACK, ST_COUNTFF, ST_LAYOUT, ST_STUFF, ST_FIX, ST_DCFIX, ST_RUNBITS, ST_COUNT };
 
 struct StageTimer {
   jpegb200_ctx* c;
@@ -219,10 +234,24 @@ struct StageTimer {
 
 // Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
 int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
-              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false) {
+              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false, uint32_t max_runs = 0) {
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
+  if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
+    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, st); }
+    { StageTimer t(c, st, ST_DCFIX); jb_launch_dc_fix(ws, njobs, max_runs, st); }
+    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }
+    { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
+    { StageTimer t(c, st, ST_RUNBITS); jb_launch_run_bits(ws, njobs, max_runs, st); }
+    { StageTimer t(c, st, ST_SCAN); jb_launch_scan_runs(ws, njobs, st); }
+    { StageTimer t(c, st, ST_PACK); jb_launch_pack_runs(ws, njobs, max_runs, st); }
+    { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
+    { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
+    { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, 8, st); }
+    CK(cudaGetLastError());
+    return 0;
+  }
   if (from == FROM_PIXELS) {
     if (c->exact_dct) { StageTimer t(c, st, ST_DCT); jb_launch_dct(ws, njobs, max_w, max_h, st); }
     else {
@@ -267,9 +296,11 @@ int upload_jobs(Lane& l, const std::vector<JbJob>& jobs) {
 
 // Lay out `n` heterogeneous jobs in one lane workspace.
 int plan_jobs(Lane& l, std::vector<JbJob>& jobs, const std::vector<size_t>& slots, int* max_w, int* max_h, uint32_t* max_blocks,
-              uint32_t* max_chunks) {
+              uint32_t* max_chunks, bool planes = true, uint32_t* max_runs = nullptr) {
   WaveDims wd;
   wd.njobs = jobs.size();
+  wd.planes = planes;
+  if (max_runs) *max_runs = 0;
   *max_w = *max_h = 0; *max_blocks = *max_chunks = 0;
   for (size_t i = 0; i < jobs.size(); i++) {
     JobDims d = job_dims(jobs[i].w, jobs[i].h, slots[i]);
@@ -280,12 +311,16 @@ int plan_jobs(Lane& l, std::vector<JbJob>& jobs, const std::vector<size_t>& slot
     jobs[i].tiles_per_seg = d.tiles_per_seg;
     jobs[i].scratch_off = (uint32_t)wd.scratch_words;
     jobs[i].scratch_cap = d.scratch_words;
+    jobs[i].tok_off = (uint32_t)wd.toks;
+    jobs[i].run_off = (uint32_t)wd.runs;
+    wd.toks += d.toks; wd.runs += d.runs;
+    if (max_runs) *max_runs = std::max(*max_runs, d.runs);
     wd.coefs += d.coefs; wd.blocks += d.blocks; wd.chunks += d.chunks; wd.tiles += 3 * (size_t)d.tiles_per_seg;
     wd.scratch_words += d.scratch_words;
     *max_w = std::max(*max_w, jobs[i].w); *max_h = std::max(*max_h, jobs[i].h);
     *max_blocks = std::max(*max_blocks, d.blocks); *max_chunks = std::max(*max_chunks, d.chunks);
   }
-  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large for 32-bit offsets");
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large for 32-bit offsets");
   CK(l.ensure(wd));
   return 0;
 }
@@ -341,6 +376,12 @@ uint64_t jpegb200_launch_count(const jpegb200_ctx* c) { return c ? c->launches :
 int jpegb200_set_exact_dct(jpegb200_ctx* c, int on) {
   if (!c) return fail("null ctx");
   c->exact_dct = on != 0;
+  return 0;
+}
+
+int jpegb200_set_token_path(jpegb200_ctx* c, int on) {
+  if (!c) return fail("null ctx");
+  c->token_path = on != 0;
   return 0;
 }
 
@@ -401,7 +442,10 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   const size_t g = (size_t)std::min(G, n);
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
-  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
+  wd.toks = g * jd.toks; wd.runs = g * jd.runs;
+  const bool tokens = c->token_path && !c->exact_dct;
+  wd.planes = !tokens;
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
   const int nwaves = (n + G - 1) / G;
   const int nl = std::min<int>((int)c->lanes.size(), nwaves);
   for (int i = 0; i < nl; i++) CK(c->lanes[i].ensure(wd));
@@ -413,7 +457,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, d_bgr + (size_t)first * frame_stride, frame_stride, w, h,
                                                           d_out + (size_t)first * slot, slot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first, true)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first, true, tokens ? jd.runs : 0)) return -1;
   }
   for (int i = 0; i < nl; i++) {
     CK(cudaEventRecord(c->lanes[i].done, c->lanes[i].stream));
@@ -435,7 +479,10 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
   WaveDims wd;
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
-  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
+  wd.toks = g * jd.toks; wd.runs = g * jd.runs;
+  const bool tokens = c->token_path && !c->exact_dct;
+  wd.planes = !tokens;
+  if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
   const int nwaves = (n + G - 1) / G;
   const int nl = std::min<int>((int)c->lanes.size(), nwaves);
   for (int i = 0; i < nl; i++) {
@@ -467,7 +514,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, (const uint8_t*)l.in.p, frame, w, h, (uint8_t*)l.out.p, dslot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true, tokens ? jd.runs : 0)) return -1;
     CK(cudaMemcpyAsync(l.h_sizes.p, l.sizes.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaEventRecord(l.sizes_ready, l.stream));
     l.pending_first = first;
@@ -504,11 +551,13 @@ int jpegb200_encode_regions(jpegb200_ctx* c, const uint8_t* d_frame, int frame_w
   CK(cudaEventRecord(c->fork, user));
   CK(cudaStreamWaitEvent(l.stream, c->fork, 0));
   CK(cudaStreamSynchronize(l.stream));       // the workspace may be re-allocated below
-  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc)) return -1;
+  const bool tokens = c->token_path && !c->exact_dct;
+  uint32_t mr = 0;
+  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc, !tokens, &mr)) return -1;
   if (upload_jobs(l, jobs)) return -1;
   bool rows_aligned = true;          // every crop row starts on a 16-byte boundary -> bulk async copies
   for (const JbJob& j : jobs) rows_aligned = rows_aligned && ((((uintptr_t)j.src + (size_t)j.y * j.pitch + 3u * (uint32_t)j.x) | j.pitch) & 15) == 0;
-  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes, rows_aligned)) return -1;
+  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes, rows_aligned, tokens ? mr : 0)) return -1;
   CK(cudaEventRecord(l.done, l.stream));
   CK(cudaStreamWaitEvent(user, l.done, 0));
   return 0;

@@ -42,6 +42,8 @@ struct JbJob {
   uint8_t* out;         // destination slot of the finished JFIF stream
   uint32_t out_cap;     // bytes available there
   uint32_t src_bytes;   // bytes readable from src (bounds the over-fetch of the aligned loader)
+  uint32_t tok_off;     // token path: first token of this job's pool inside ws.tok (JB_ROUND_TOKENS per tile and round)
+  uint32_t run_off;     // token path: first run record of this job (Y runs, then Cb, then Cr)
 };
 
 // Per-job results of the scan / layout kernels.
@@ -55,6 +57,30 @@ struct JbJobState {
 };
 
 enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4 };
+
+// ---- token path ------------------------------------------------------------------------------------------------
+// k_pixels_to_tokens walks the crop in tiles of JB_TILE_MCUS consecutive MCUs (raster order).  The blocks of one
+// component that a tile contributes to one block row are consecutive in the component's scan order: a *run*.  A run's
+// tokens (DC, non-zero AC coefficients with their ZRL count, EOB; walk.cuh) are stored contiguously, so the bit packer
+// streams them without touching coefficients.
+//   token: bits 0..10 magnitude bits | 11..14 category | 15..23 table index (0..255 AC symbol, 256+category DC) | 24..25 ZRLs
+#define JB_TILE_MCUS 16
+#define JB_ROUND_TOKENS (32 * 65)  // capacity of one tile round (32 blocks x (DC + 63 AC + EOB))
+struct JbRun {
+  uint32_t tok;        // index of the run's first token in ws.tok (always the head block's DC token)
+  uint32_t ntok;
+  uint32_t dc;         // low half: quantised DC of the run's first block, high half: of its last block (before prediction)
+  uint32_t bits;       // entropy-coded bits of the run (k_run_bits)
+};
+// runs of one chroma plane that lie in MCU rows < my (mw = MCUs per row); luma has twice as many (two block rows per MCU row)
+__host__ __device__ inline uint32_t jb_runs_before(uint32_t mw, uint32_t my) {
+  uint32_t g = mw & (0u - mw);                   // largest power of two dividing mw
+  if (g > JB_TILE_MCUS) g = JB_TILE_MCUS;
+  const uint32_t period = JB_TILE_MCUS / g;      // every `period` MCU rows a row starts on a tile boundary
+  return (my * mw) / JB_TILE_MCUS + my - my / period;
+}
+__host__ __device__ inline uint32_t jb_runs_chroma(int w, int h) { return jb_runs_before((uint32_t)w / 16u, (uint32_t)h / 16u); }
+__host__ __device__ inline uint32_t jb_tiles(int w, int h) { return ((uint32_t)(w / 16) * (uint32_t)(h / 16) + JB_TILE_MCUS - 1) / JB_TILE_MCUS; }
 
 // Workspace of one wave (all device pointers).
 struct JbWs {
@@ -73,6 +99,9 @@ struct JbWs {
   uint32_t* tile_ff;    // per tile: 0xFF count, then (after k_layout) exclusive prefix inside the segment
   uint32_t* fix_count;  // per wave: number of entries in fix_list (zeroed with the state block)
   uint2* fix_list;      // per wave: (job, block id inside the job) of blocks the fast DCT could not decide
+  uint32_t* tok;        // token path: token pool
+  JbRun* runs;          // token path: run records
+  uint32_t* run_base;   // token path: per run, bit offset inside its scan
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -110,6 +139,13 @@ void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_
 void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
+
+// token path (k_tokens.cu, k_pack_runs.cu)
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
+void jb_launch_dc_fix(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
+void jb_launch_run_bits(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
+void jb_launch_scan_runs(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_pack_runs(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
 
 // comparator (brain.c)
 void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, cudaStream_t st);

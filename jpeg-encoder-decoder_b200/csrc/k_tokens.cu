@@ -1,0 +1,445 @@
+// k_tokens.cu — pass 1 of the batched encoder on sm_100a, one kernel:
+//   BGR888 crop -> Y/Cb/Cr 4:2:0 -> 8x8 forward DCT -> quantise -> zig-zag            (encoder.c:81-150, as k_dct.cu)
+//   -> DC prediction, run/size symbols, the four symbol histograms                      (encoder.c:168-177, :303-375)
+//   -> a compact token stream per run of consecutive blocks (jpegb200_internal.cuh)
+// so that neither the coefficient planes nor a second walk over them are needed: the bit packer (k_pack_runs.cu) streams
+// tokens.  Results are bit-identical with the plane path (k_dct.cu + k_symbol_stats); the parity suite compares both.
+//
+// Work decomposition: every warp is an independent worker — no CTA barrier anywhere.  A worker owns a contiguous range of
+// tiles (16 consecutive MCUs).  Per tile:
+//   rows 0-7  of the tile arrive by bulk async copies (mbarrier) -> colour conversion -> samples of luma block row 0 and
+//             chroma rows 0-3; the copies of rows 8-15 are issued, and overlap
+//   round 0   (32 luma blocks, one per lane): FP32 AAN filter + bracketed quantisation, exact FP64 replay of undecided
+//             blocks by the whole warp (8 lanes per block), token walk
+//   rows 8-15 -> colour -> luma block row 1, chroma rows 4-7; the copies of the next tile's rows 0-7 are issued
+//   round 1   (luma block row 1), round 2 (16 Cb + 16 Cr blocks)
+// The token walk of a lane visits only the non-zero coefficients of its block (its zig-zagged block sits in a lane-private
+// shared-memory row); tokens are staged in the shared memory of the round's dead samples and flushed with coalesced stores.
+#include <cstdio>
+#include <cstdlib>
+
+#include "dct_core.cuh"
+#include "walk.cuh"
+
+namespace {
+
+constexpr int TK_WARPS = 4;             // workers per CTA
+constexpr int TK_WINDOW = 512;          // tokens staged per flush (2 KB = the 32 sample slots of the round)
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+struct __align__(128) TkSmem {
+  uint32_t raw[8][JB_TILE_MCUS * 12];   // 8 pixel rows x (16 MCUs x 48 B) of B,G,R bytes
+  uint32_t smp[96 * 16];                // 8-bit samples, 64 B per block: luma slot = (block row)*32 + mcu*2 + (block column),
+                                        // Cb of MCU m in slot 64+m, Cr in slot 80+m.  The 16-byte chunk c (sample rows 2c, 2c+1)
+                                        // of slot s lives at chunk (c ^ (s >> 1)) & 3  -> conflict-free LDS.128 / STS.128
+  uint32_t cbuf[32 * 33];               // lane-private rows of 32 words: the zig-zagged block (pitch 33: conflict-free);
+                                        // also the transpose / zig-zag scratch of the exact replay
+  uint32_t hist[544];                   // 0..15 luma DC categories, 16..271 luma AC symbols, 272..287 / 288..543 chroma
+  unsigned long long full;              // mbarrier: the 8 rows in flight have landed
+  uint32_t pad[2];
+};
+static_assert(sizeof(double) * 4 * TR_STRIDE + 4 * 64 * sizeof(int16_t) <= sizeof(uint32_t) * 32 * 33, "exact-replay scratch must fit in cbuf");
+
+struct TkTile {
+  int job, tile, m0, valid, mw, my0, mx0;
+};
+__device__ __forceinline__ bool tk_tile(const JbWs& ws, int t, int tiles_per_job, TkTile& p, JbJob& job) {
+  p.job = t / tiles_per_job;
+  p.tile = t - p.job * tiles_per_job;
+  job = ws.jobs[p.job];
+  p.mw = job.w / 16;
+  const int nm = p.mw * (job.h / 16);
+  p.m0 = p.tile * JB_TILE_MCUS;
+  if (p.m0 >= nm) return false;
+  p.valid = min(JB_TILE_MCUS, nm - p.m0);
+  p.my0 = p.m0 / p.mw;
+  p.mx0 = p.m0 - p.my0 * p.mw;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t tk_token(int v, int cat, int idx, int zrl) {
+  const uint32_t mag = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);           // encoder.c:441-443, :455-457
+  return mag | ((uint32_t)cat << 11) | ((uint32_t)idx << 15) | ((uint32_t)zrl << 24);
+}
+
+// Cold path of the colour stage (see replay_patch in k_dct.cu): exact replay of one 8x2 patch.
+__device__ __noinline__ void tk_replay_patch(TkSmem& sm, int half, int mcu, int pr, int pc) {
+  uint32_t cb[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
+  const int slot = half * 32 + mcu * 2 + pc;
+#pragma unroll 1
+  for (int dr = 0; dr < 2; dr++) {
+    const int r = 2 * pr + dr;                   // row inside the half = sample row of the luma block
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[r][mcu * 12 + 6 * pc]);
+    uint8_t* ydst = reinterpret_cast<uint8_t*>(&sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4 + dr * 2]);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint32_t e = ycc_pixel(px[3 * c], px[3 * c + 1], px[3 * c + 2]);
+      ydst[c] = (uint8_t)e;
+      cb[c >> 1] += (e >> 8) & 0xFF;
+      cr[c >> 1] += e >> 16;
+    }
+  }
+  const int crow = half * 4 + pr, cw = (((crow >> 1) ^ (mcu >> 1)) & 3) * 4 + (crow & 1) * 2 + pc;
+  sm.smp[(64 + mcu) * 16 + cw] = (cb[0] >> 2) | ((cb[1] >> 2) << 8) | ((cb[2] >> 2) << 16) | ((cb[3] >> 2) << 24);
+  sm.smp[(80 + mcu) * 16 + cw] = (cr[0] >> 2) | ((cr[1] >> 2) << 8) | ((cr[2] >> 2) << 16) | ((cr[3] >> 2) << 24);
+}
+
+// Colour conversion + 4:2:0 of the 8 staged rows (encoder.c:129-138): one 8x2 patch per lane and step.
+__device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, int lane) {
+  const int mcu = lane >> 1, pc = lane & 1;
+  if (mcu >= valid) return;
+  const int slot = half * 32 + lane;
+#pragma unroll 1
+  for (int pr = 0; pr < 4; pr++) {
+    uint32_t yb[2][8], cbb[2][8], crb[2][8];
+    uint32_t screen = 0xFFFFFFFFu;
+#pragma unroll
+    for (int dr = 0; dr < 2; dr++) {
+      uint32_t w[6];
+      const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+      ycc_row8(w, yb[dr], cbb[dr], crb[dr], screen);
+    }
+    if (screen < TIE_LIMIT) {
+      tk_replay_patch(sm, half, mcu, pr, pc);
+      continue;
+    }
+    *reinterpret_cast<uint4*>(&sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4]) =
+        make_uint4(pack4(yb[0][0], yb[0][1], yb[0][2], yb[0][3]), pack4(yb[0][4], yb[0][5], yb[0][6], yb[0][7]),
+                   pack4(yb[1][0], yb[1][1], yb[1][2], yb[1][3]), pack4(yb[1][4], yb[1][5], yb[1][6], yb[1][7]));
+    uint32_t cbv[4], crv[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      cbv[c] = (cbb[0][2 * c] + cbb[0][2 * c + 1] + cbb[1][2 * c] + cbb[1][2 * c + 1]) >> 2;
+      crv[c] = (crb[0][2 * c] + crb[0][2 * c + 1] + crb[1][2 * c] + crb[1][2 * c + 1]) >> 2;
+    }
+    const int crow = half * 4 + pr, cw = (((crow >> 1) ^ (mcu >> 1)) & 3) * 4 + (crow & 1) * 2 + pc;
+    sm.smp[(64 + mcu) * 16 + cw] = pack4(cbv[0], cbv[1], cbv[2], cbv[3]);
+    sm.smp[(80 + mcu) * 16 + cw] = pack4(crv[0], crv[1], crv[2], crv[3]);
+  }
+}
+
+// Walk the non-zero coefficients whose (bit-reversed) flags are in r: zig-zag positions BASE + 0..31.
+template <int BASE>
+__device__ __forceinline__ void tk_walk(uint32_t& r, bool gate, uint32_t& pos, uint32_t wbase, int& prev1, const int16_t* cbh, uint32_t* stage,
+                                        uint32_t* hist_ac) {
+  const uint32_t wend = wbase + TK_WINDOW;
+  while (true) {
+    const bool act = gate && r != 0 && pos < wend;
+    if (!__any_sync(FULL, act)) break;
+    if (act) {
+      const int pz = __clz(r);
+      r &= ~(0x80000000u >> pz);
+      const int p = BASE + pz;
+      const int v = cbh[p];
+      const int run = p - prev1;
+      prev1 = p + 1;
+      const int cat = 32 - __clz(abs(v));
+      const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
+      atomicAdd(&hist_ac[sym], 1u);
+      if (zrl) atomicAdd(&hist_ac[0xF0], (uint32_t)zrl);
+      stage[pos - wbase] = tk_token(v, cat, sym, zrl);
+      pos++;
+    }
+  }
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TkSmem& sm = reinterpret_cast<TkSmem*>(smem_raw)[warp];
+  for (int k = lane; k < 544; k += 32) sm.hist[k] = 0;
+  if (BULK) {
+    if (lane == 0) {
+      mbar_init(&sm.full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+  }
+  __syncwarp();
+  const int worker = blockIdx.x * TK_WARPS + warp, nworkers = gridDim.x * TK_WARPS;
+  const int t_begin = (int)((long long)ntiles * worker / nworkers), t_end = (int)((long long)ntiles * (worker + 1) / nworkers);
+
+  // Fetch the 8 pixel rows `half` of tile t.  BULK: asynchronous (lane r < 8 owns row r); otherwise synchronous byte loads.
+  auto fetch = [&](const TkTile& p, const JbJob& job, int half) {
+    if (BULK) {
+      if (lane == 0) mbar_expect_tx(&sm.full, (uint32_t)p.valid * 384u);
+      __syncwarp();
+      if (lane < 8) {
+        int mcu = 0, my = p.my0, mx = p.mx0;
+        while (mcu < p.valid) {
+          const int run = min(p.valid - mcu, p.mw - mx);
+          const uint8_t* g = job.src + (size_t)(job.y + my * 16 + half * 8 + lane) * job.pitch + 3u * (uint32_t)job.x + (size_t)mx * 48;
+          bulk_g2s(&sm.raw[lane][mcu * 12], g, (uint32_t)run * 48u, &sm.full);
+          mcu += run; mx = 0; my++;
+        }
+      }
+    } else {
+      uint8_t* rawb = reinterpret_cast<uint8_t*>(&sm.raw[0][0]);
+      for (int row = 0; row < 8; row++)
+        for (int j = lane; j < p.valid * 48; j += 32) {
+          const int mcu = j / 48, c = j - mcu * 48;
+          int my = p.my0, mx = p.mx0 + mcu;
+          while (mx >= p.mw) { mx -= p.mw; my++; }
+          rawb[row * (JB_TILE_MCUS * 48) + j] = __ldg(job.src + (size_t)(job.y + my * 16 + half * 8 + row) * job.pitch + 3u * (uint32_t)(job.x + mx * 16) + c);
+        }
+      __syncwarp();
+    }
+  };
+  auto next_valid = [&](int t, TkTile& p, JbJob& job) {
+    while (t < t_end && !tk_tile(ws, t, tiles_per_job, p, job)) t++;
+    return t;
+  };
+  auto flush_hist = [&](int jobid) {
+    int* G = ws.hist + (size_t)jobid * 4 * 257;
+    __syncwarp();
+    for (int k = lane; k < 544; k += 32) {
+      const uint32_t v = sm.hist[k];
+      if (v) {
+        const int comp = k >= 272, kk = k - comp * 272;
+        atomicAdd(&G[comp * 2 * 257 + (kk < 16 ? kk : 257 + (kk - 16))], (int)v);
+        sm.hist[k] = 0;
+      }
+    }
+    __syncwarp();
+  };
+
+  uint32_t parity = 0;
+  int cur_job = -1;
+  TkTile p, pn;
+  JbJob job, jobn;
+  int t = next_valid(t_begin, p, job);
+  if (t < t_end) fetch(p, job, 0);
+#pragma unroll 1
+  while (t < t_end) {
+    if (p.job != cur_job) {
+      if (cur_job >= 0) flush_hist(cur_job);
+      cur_job = p.job;
+    }
+    const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
+    const uint32_t nrc = jb_runs_chroma(job.w, job.h);
+    int tn = t_end;
+#pragma unroll 1
+    for (int step = 0; step < 3; step++) {          // step 0: rows 0-7 + round 0 ; step 1: rows 8-15 + round 1 ; step 2: round 2
+      if (step < 2) {
+        if (BULK) { mbar_wait(&sm.full, parity); parity ^= 1u; }
+        tk_colour_half(sm, step, p.valid, lane);
+        __syncwarp();
+        if (step == 0) fetch(p, job, 1);
+        else {
+          tn = next_valid(t + 1, pn, jobn);
+          if (tn < t_end) fetch(pn, jobn, 0);
+        }
+      }
+      const int role = step;
+      // ---- the lane's block -------------------------------------------------------------------------------------
+      const int comp = role < 2 ? 0 : 1;
+      const int mcu = role < 2 ? lane >> 1 : lane & 15;
+      const bool ok = mcu < p.valid;
+      int my = p.my0, mx = p.mx0 + mcu;
+      while (mx >= p.mw) { mx -= p.mw; my++; }
+      uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
+      if (role < 2) blk = (uint32_t)(my * 2 + role) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
+      else blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)(p.m0 + mcu);
+      const int slot = role * 32 + lane;
+      uint32_t out[32];
+      uint64_t mask;
+      int dcq;
+      bool bad;
+      {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const uint4*>(&sm.smp[slot * 16 + ((k ^ (slot >> 1)) & 3) * 4]);
+        bad = block_fast_regs(v, comp, magic, out, &mask, &dcq);
+      }
+      // ---- exact replay of undecided blocks: 8 lanes per block, up to 4 blocks per pass --------------------------------
+      uint32_t badm = __ballot_sync(FULL, bad && ok);
+      while (badm) {
+        double* tr = reinterpret_cast<double*>(sm.cbuf);
+        int16_t* zz = reinterpret_cast<int16_t*>(sm.cbuf) + (4 * TR_STRIDE * sizeof(double)) / sizeof(int16_t);
+        int src[4];
+        {
+          uint32_t mm = badm;
+#pragma unroll
+          for (int g = 0; g < 4; g++) { src[g] = mm ? __ffs(mm) - 1 : -1; mm &= mm - 1; }
+          badm = mm;
+        }
+        const int g = lane >> 3, i = lane & 7;
+        const int mine = g == 0 ? src[0] : g == 1 ? src[1] : g == 2 ? src[2] : src[3];
+        const int s = role * 32 + (mine >= 0 ? mine : src[0]);
+        uint32_t px[8];
+#pragma unroll
+        for (int tt = 0; tt < 8; tt++) {
+          const uint32_t wv = sm.smp[s * 16 + (((tt >> 1) ^ (s >> 1)) & 3) * 4 + (tt & 1) * 2 + (i >> 2)];
+          px[tt] = (wv >> (8 * (i & 3))) & 0xFF;
+        }
+        __align__(16) double rql[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) rql[u] = __dmul_rn(__drcp_rn((double)c_quant[comp][i * 8 + u]), 0x1.00000004p-2);
+        const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
+        uint64_t emask;
+        block_dct(px, comp, rql, izzrow, tr, zz, lane, &emask);
+        const uint32_t* zzw = reinterpret_cast<const uint32_t*>(zz);
+#pragma unroll
+        for (int gg = 0; gg < 4; gg++) {
+          const uint32_t mlo = __shfl_sync(FULL, (uint32_t)emask, gg * 8), mhi = __shfl_sync(FULL, (uint32_t)(emask >> 32), gg * 8);
+          if (lane == src[gg]) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) out[j] = zzw[gg * 32 + j];
+            mask = ((uint64_t)mhi << 32) | mlo;
+            dcq = (int)(short)(out[0] & 0xFFFFu);
+          }
+        }
+        __syncwarp();
+      }
+
+      // ---- runs, token offsets --------------------------------------------------------------------------------------
+      if (!ok) mask = 0;             // lanes past the end of the crop transformed stale samples
+      const uint32_t cnt = ok ? 2u + (uint32_t)__popcll(mask) - (uint32_t)(mask >> 63) : 0u;
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += n;
+      }
+      const uint32_t excl = inc - cnt, total = __shfl_sync(FULL, inc, 31);
+      const uint32_t prev_blk = __shfl_up_sync(FULL, blk, 1);
+      const int prev_dc = __shfl_up_sync(FULL, dcq, 1);
+      const uint32_t okb = __ballot_sync(FULL, ok);
+      const bool prev_ok = lane > 0 && ((okb >> (lane - 1)) & 1u);
+      const int prev_my = __shfl_up_sync(FULL, my, 1);
+      // a run ends with its MCU row (chroma blocks are consecutive across rows, the run records are not) and with its plane
+      const bool head = ok && (!prev_ok || blk != prev_blk + 1 || my != prev_my || (role == 2 && lane == 16));
+      const uint32_t hb = __ballot_sync(FULL, head);
+      const uint32_t round_tok = job.tok_off + (uint32_t)(p.tile * 3 + role) * JB_ROUND_TOKENS;
+      {
+        const uint32_t above = lane == 31 ? 0u : hb & ~((2u << lane) - 1u);
+        const int next = above ? __ffs(above) - 1 : 32;
+        const uint32_t excl_next = __shfl_sync(FULL, excl, next & 31);
+        const uint32_t run_end = next < 32 ? excl_next : total;
+        const uint32_t inrun = okb & (next < 32 ? (1u << next) - 1u : FULL) & ~((1u << lane) - 1u);
+        const int lastl = inrun ? 31 - __clz(inrun) : lane;
+        const int dc_last = __shfl_sync(FULL, dcq, lastl);
+        if (head) {
+          const uint32_t R0 = jb_runs_before((uint32_t)p.mw, (uint32_t)my), tfirst = (uint32_t)(my * p.mw) / JB_TILE_MCUS;
+          uint32_t rid;
+          if (role < 2) {
+            const uint32_t R1 = jb_runs_before((uint32_t)p.mw, (uint32_t)my + 1u);
+            rid = 2u * R0 + (uint32_t)role * (R1 - R0) + ((uint32_t)p.tile - tfirst);
+          } else {
+            rid = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
+          }
+          JbRun rr;
+          rr.tok = round_tok + excl;
+          rr.ntok = run_end - excl;
+          rr.dc = ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16);
+          rr.bits = 0;
+          *reinterpret_cast<uint4*>(&ws.runs[job.run_off + rid]) = make_uint4(rr.tok, rr.ntok, rr.dc, rr.bits);
+        }
+      }
+
+      // ---- token walk ---------------------------------------------------------------------------------------------------
+      uint32_t* cb = sm.cbuf + lane * 33;
+#pragma unroll
+      for (int j = 0; j < 32; j++) cb[j] = out[j];
+      const int16_t* cbh = reinterpret_cast<const int16_t*>(cb);
+      uint32_t* stage = sm.smp + role * 512;
+      uint32_t* hist_dc = sm.hist + comp * 272;
+      uint32_t* hist_ac = hist_dc + 16;
+      uint32_t pos = excl;
+      uint32_t rlo = __brev((uint32_t)mask), rhi = __brev((uint32_t)(mask >> 32));
+      int prev1 = 1;
+      bool dc_pend = ok, eob_pend = ok && !(mask >> 63);
+      const int diff = dcq - prev_dc;
+      __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
+#pragma unroll 1
+      for (uint32_t wbase = 0; wbase < total; wbase += TK_WINDOW) {
+        const uint32_t wend = wbase + TK_WINDOW;
+        if (dc_pend && pos < wend) {
+          uint32_t tok = 0;                        // a run's first DC is predicted across runs: k_dc_fix fills it in
+          if (!head) {
+            const int cat = 32 - __clz(abs(diff));
+            tok = tk_token(diff, cat, 256 + cat, 0);
+            atomicAdd(&hist_dc[cat], 1u);
+          }
+          stage[pos - wbase] = tok;
+          pos++;
+          dc_pend = false;
+        }
+        tk_walk<0>(rlo, !dc_pend, pos, wbase, prev1, cbh, stage, hist_ac);
+        tk_walk<32>(rhi, !dc_pend && rlo == 0, pos, wbase, prev1, cbh, stage, hist_ac);
+        const bool eob = eob_pend && !dc_pend && rlo == 0 && rhi == 0 && pos < wend;
+        if (eob) {
+          stage[pos - wbase] = 0;                  // EOB: table index 0, no magnitude bits
+          pos++;
+          eob_pend = false;
+        }
+        const uint32_t eb = __ballot_sync(FULL, eob);
+        if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
+        __syncwarp();
+        const uint32_t n = min(total, wend) - wbase;
+        uint32_t* dst = ws.tok + round_tok + wbase;
+        for (uint32_t k = lane; k < n; k += 32) dst[k] = stage[k];
+        __syncwarp();
+      }
+    }
+    t = tn;
+    p = pn;
+    job = jobn;
+  }
+  if (cur_job >= 0) flush_hist(cur_job);
+}
+
+// ---- the first DC token of every run (encoder.c:168-177 predicts across the whole plane) -------------------------------
+__global__ void __launch_bounds__(256) k_dc_fix(JbWs ws) {
+  __shared__ uint32_t h[32];
+  const JbJob job = ws.jobs[blockIdx.y];
+  const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
+  if (threadIdx.x < 32) h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
+  if (r < nr) {
+    const int plane = r < 2u * nrc ? 0 : (r < 3u * nrc ? 1 : 2);
+    const bool first = r == 0 || r == 2u * nrc || r == 3u * nrc;
+    const JbRun* runs = ws.runs + job.run_off;
+    const int dc = (int)(short)(runs[r].dc & 0xFFFFu);
+    const int prev = first ? 0 : (int)(short)(runs[r - 1].dc >> 16);
+    const int diff = dc - prev;
+    const int cat = 32 - __clz(abs(diff));
+    ws.tok[runs[r].tok] = tk_token(diff, cat, 256 + cat, 0);
+    atomicAdd(&h[(plane ? 16 : 0) + cat], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && h[threadIdx.x]) {
+    int* G = ws.hist + (size_t)blockIdx.y * 4 * 257;
+    atomicAdd(&G[(threadIdx.x >= 16 ? 2 * 257 : 0) + (threadIdx.x & 15)], (int)h[threadIdx.x]);
+  }
+}
+
+}  // namespace
+
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st) {
+  static int ctas_per_sm[2] = {0, 0}, sms = 0;
+  const int v = rows_aligned ? 1 : 0;
+  auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
+  const int smem = (int)sizeof(TkSmem) * TK_WARPS;
+  if (!ctas_per_sm[v]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TK_WARPS * 32, smem);
+    ctas_per_sm[v] = n > 0 ? n : 1;
+    if (getenv("JPEGB200_DEBUG")) fprintf(stderr, "k_pixels_to_tokens<%d>: %d SMs x %d CTAs, %d B smem (%s)\n", v, sms, n, smem, cudaGetErrorString(cudaGetLastError()));
+  }
+  const int mcus = (max_w / 16) * (max_h / 16), tiles_per_job = (mcus + JB_TILE_MCUS - 1) / JB_TILE_MCUS, ntiles = tiles_per_job * njobs;
+  const int want = (ntiles + TK_WARPS - 1) / TK_WARPS;
+  const int grid = want < sms * ctas_per_sm[v] ? want : sms * ctas_per_sm[v];
+  kern<<<grid, TK_WARPS * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
+}
+
+void jb_launch_dc_fix(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
+  k_dc_fix<<<dim3((max_runs + 255) / 256, njobs), 256, 0, st>>>(ws);
+}

@@ -376,9 +376,11 @@ def test_enlarge_adjust_and_subsample_vs_oracle(api, oracle):
 # ------------------------------------------------------------------ fast filter transform vs literal chain on the device
 
 def test_fast_dct_equals_exact_dct_large(frames):
-    """The FP32 filter + fix-up path must produce the bytes of the all-FP64 path on every content class, at the
-    bench shape; also reports how many blocks needed the literal chain."""
-    fast, exact = pkg.Encoder(0, 8, 1), pkg.Encoder(0, 8, 1)
+    """The FP32 filter + literal-chain replay must produce the bytes of the all-FP64 path on every content class, at the
+    bench shape, on both batched paths (token path: replay inside k_pixels_to_tokens; plane path: k_fix_blocks, which
+    also reports how many blocks needed the literal chain)."""
+    tok, fast, exact = pkg.Encoder(0, 8, 1), pkg.Encoder(0, 8, 1), pkg.Encoder(0, 8, 1)
+    fast.set_token_path(False)
     exact.set_exact_dct(True)
     try:
         rng = np.random.default_rng(7)
@@ -396,12 +398,40 @@ def test_fast_dct_equals_exact_dct_large(frames):
             a = fast.encode_frames(b, slot)
             nfix = fast.fix_count(0)
             e = exact.encode_frames(b, slot)
+            t = tok.encode_frames(b, slot)
             nblk = b.shape[0] * W * H * 3 // 2 // 64
             print(f"{name}: {nfix} of {nblk} blocks ({100.0 * nfix / nblk:.3f} %) went through the literal chain")
             assert a == e, name
+            assert t == e, name + " (token path)"
     finally:
+        tok.close()
         fast.close()
         exact.close()
+
+
+def test_token_path_small_shapes_and_crops(enc, oracle, frames):
+    """Token path (the default of the batched entry points) on ragged tiles, rows narrower than a tile, tiles that
+    straddle several MCU rows, crops with unaligned origins (synchronous loader) and heterogeneous region batches."""
+    import torch
+    rng = np.random.default_rng(13)
+    for (h, w) in [(16, 16), (16, 272), (48, 80), (32, 528), (240, 320), (112, 48), (64, 64), (16, 4112), (400, 16), (96, 112)]:
+        for kind in range(6):
+            batch = np.stack([_rand_img(rng, h, w, kind) for _ in range(3)])
+            jp = enc.encode_frames(batch)
+            for k in range(3):
+                assert jp[k] == oracle.encode(batch[k])["jpg"].tobytes(), (w, h, kind, k)
+    img = frames.sample_bgr("640_diffs")
+    areas = [(2, 36, 112, 432), (358, 66, 256, 336), (406, 476, 192, 160), (146, 412, 176, 144), (0, 0, 16, 16), (624, 624, 16, 16),
+             (3, 5, 48, 32), (101, 7, 528, 16), (16, 32, 144, 48), (5, 0, 272, 640), (0, 0, 640, 640), (16, 16, 608, 16)]
+    d_frame = _torch_batch(img)
+    slot = 640 * 640 * 3 // 2 + 65536
+    d_out = torch.zeros((len(areas), slot), dtype=torch.uint8, device="cuda")
+    d_sizes = torch.zeros(len(areas), dtype=torch.int32, device="cuda")
+    enc.encode_regions_ptr(d_frame.data_ptr(), 640, 640, areas, d_out.data_ptr(), slot, d_sizes.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    sizes, out = d_sizes.cpu().numpy(), d_out.cpu().numpy()
+    for i, a in enumerate(areas):
+        assert out[i, : sizes[i]].tobytes() == oracle.encode(img, a)["jpg"].tobytes(), a
 
 
 def test_fast_dct_small_shapes_and_crops(api, oracle, frames):

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 
-STAGES = ["dct", "plane_masks", "symbol_stats", "build_huffman", "pack_tables", "block_bits", "scan", "pack", "count_ff", "layout", "stuff", "fix_blocks"]
+STAGES = ["dct", "plane_masks", "symbol_stats", "build_huffman", "pack_tables", "block_bits", "scan", "pack", "count_ff", "layout", "stuff", "fix_blocks", "dc_fix", "run_bits"]
 
 def main():
     ap = argparse.ArgumentParser()

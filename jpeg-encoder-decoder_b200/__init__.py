@@ -20,7 +20,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjpegb200.so")
+LIB_PATH = os.environ.get("JPEGB200_LIB") or os.path.join(_HERE, "libjpegb200.so")   # the override is a development aid (kernel variants)
 ROOT = os.path.dirname(_HERE)
 
 C_ABI_SYMBOLS = [

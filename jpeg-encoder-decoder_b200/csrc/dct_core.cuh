@@ -131,6 +131,33 @@ __device__ __forceinline__ uint4 block_dct(const uint32_t (&px)[8], int comp, co
   return out;
 }
 
+// Literal chain of encoder.c:87-108 for the 8 coefficients of natural row v (vertical frequency v) of one block, by 8
+// lanes: lane i owns sample column i in the first pass (col8: byte t = sample of row t) and horizontal frequency u = i in
+// the second.  x*1.0 and 0.0+x are exact, so the unspecialised loops reproduce the reference bit for bit.  Returns the
+// quantised coefficient of natural index 8v+i.  All 32 lanes must call (shuffles inside groups of 8).
+__device__ __noinline__ int exact_row_coef(uint2 col8, int comp, int v, int lane) {
+  const int i = lane & 7;
+  double inner = 0.0;
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    const double p = sample_to_double(((t < 4 ? col8.x : col8.y) >> (8 * (t & 3))) & 0xFFu);
+    const double pr = __dmul_rn(p, c_cos[t * 8 + v]);
+    inner = t == 0 ? pr : __dadd_rn(inner, pr);
+  }
+  double f = 0.0;
+#pragma unroll
+  for (int x = 0; x < 8; x++) {
+    const double in_x = __shfl_sync(0xFFFFFFFFu, inner, x, 8);
+    const double pr = __dmul_rn(in_x, g_cos[x * 8 + i]);
+    f = x == 0 ? pr : __dadd_rn(f, pr);
+  }
+  if (i == 0) f = __dmul_rn(f, JB_INV_SQRT2);           // encoder.c:104 (x_f == 0)
+  if (v == 0) f = __dmul_rn(f, JB_INV_SQRT2);           // encoder.c:105 (y_f == 0)
+  const double q = (double)g_quant[comp][v * 8 + i];
+  const int n = (int)(short)__double2int_rz(__ddiv_rn(__dmul_rn(f, 0.25), q));       // encoder.c:106-108
+  return min(max(n, -2048), 2047);                                                    // encoder.c:109
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
@@ -206,6 +233,31 @@ __device__ __forceinline__ void ycc_row8(const uint32_t (&w)[6], uint32_t (&yb)[
   }
 }
 
+// Same conversion with exact remainder screens: r' = n - q*D computed on the bit patterns lies in [K_D, K_D + D) with
+// K_D = 0x4B000000 * (1 - D) mod 2^32 (0x53000000 for D = 1000, 0x05000000 for D = 31250; no wrap-around), and equals K_D
+// exactly when D divides n.  scr_y / scr_c keep the running minimum over the luma / chroma values: no false positives.
+constexpr uint32_t TIE_K_Y = 0x53000000u, TIE_K_C = 0x05000000u;
+__device__ __forceinline__ void ycc_row8x(const uint32_t (&w)[6], uint32_t (&yb)[8], uint32_t (&cbb)[8], uint32_t (&crb)[8], uint32_t& scr_y, uint32_t& scr_c) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t ny[4], nb[4], nr[4];
+    numer4<114, 587, 299, 0>(w[3 * h], w[3 * h + 1], w[3 * h + 2], ny);
+    numer4<15625, -10352, -5273, 4000000>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nb);
+    numer4<-2541, -13084, 15625, 4000000>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nr);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float fy = __fadd_rn(__uint_as_float(ny[k]), -8388608.0f);
+      const float fb = __fadd_rn(__uint_as_float(nb[k]), -8388608.0f);
+      const float fr = __fadd_rn(__uint_as_float(nr[k]), -8388608.0f);
+      yb[4 * h + k] = __float_as_uint(__fmaf_rz(fy, INV1000_UP, 8388608.0f));
+      cbb[4 * h + k] = __float_as_uint(__fmaf_rz(fb, INV31250_UP, 8388608.0f));
+      crb[4 * h + k] = __float_as_uint(__fmaf_rz(fr, INV31250_UP, 8388608.0f));
+      scr_y = min(scr_y, ny[k] - yb[4 * h + k] * 1000u);
+      scr_c = min(scr_c, min(nb[k] - cbb[4 * h + k] * 31250u, nr[k] - crb[4 * h + k] * 31250u));
+    }
+  }
+}
+
 // In-place forward AAN butterfly on 8 floats; out[k] = X[k] / r_k (tools/analysis/gen_fast_tables.py).
 __device__ __forceinline__ void aan8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7) {
   using namespace jbfast;
@@ -240,16 +292,17 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
 
 // Bracketed quantisation of natural index I (compile-time so that the multipliers become FFMA immediates).
 // `magic` is 1.5 * 2^23 handed in through a kernel parameter: a register operand, so that the multiplier can be the FFMA immediate.
+// bad[v] collects the undecided coefficients of natural row v (vertical frequency v).
 template <int COMP, int I>
-__device__ __forceinline__ void quant_one(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, float magic) {
+__device__ __forceinline__ void quant_one(const float (&d)[64], uint32_t (&q)[64], uint32_t (&bad)[8], float magic) {
   constexpr float khi = COMP == 0 ? jbfast::KHI_L[I] : jbfast::KHI_C[I], klo = COMP == 0 ? jbfast::KLO_L[I] : jbfast::KLO_C[I];
   const uint32_t hi = __float_as_uint(__fmaf_rz(d[I], khi, magic));
   const uint32_t lo = __float_as_uint(__fmaf_rz(d[I], klo, magic));
-  bad |= hi ^ lo;
+  bad[I >> 3] |= hi ^ lo;
   q[I] = lo;                          // low 16 bits: floor(v) in two's complement
 }
 template <int COMP, int... I>
-__device__ __forceinline__ void quant_all(const float (&d)[64], uint32_t (&q)[64], uint32_t& bad, float magic, std::integer_sequence<int, I...>) {
+__device__ __forceinline__ void quant_all(const float (&d)[64], uint32_t (&q)[64], uint32_t (&bad)[8], float magic, std::integer_sequence<int, I...>) {
   (quant_one<COMP, I + 1>(d, q, bad, magic), ...);
 }
 // Word J of the zig-zagged block = positions 2J, 2J+1; trunc = floor + 1 for negative values (a negative
@@ -262,7 +315,7 @@ __device__ __forceinline__ void pack_one(const uint32_t (&q)[64], uint32_t (&out
   w = __vadd2(w, neg);
   out[J] = w;
   const uint32_t nz = __vminu2(w, 0x00010001u);
-  if (J < 16) m0 = nz * (1u << J) + m0; else m1 = nz * (1u << (J - 16)) + m1;       // IMAD: keeps the ALU pipe free
+  if constexpr (J < 16) m0 = nz * (1u << J) + m0; else m1 = nz * (1u << (J - 16)) + m1;       // IMAD: keeps the ALU pipe free
 }
 template <int... J>
 __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out)[32], uint32_t& m0, uint32_t& m1, std::integer_sequence<int, J...>) {
@@ -273,8 +326,8 @@ __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out
 // Sample b enters as the float 2^15 + b (one PRMT drops the byte into the mantissa): all sums of the flow stay exact
 // integers below 2^24 and the offset cancels in every difference, so it only shows up in the DC sum, where it is
 // removed exactly together with the reference's -128 (encoder.c:92).  Returns true when some AC coefficient could not
-// be decided by the bracket.
-__device__ __forceinline__ bool block_fast_regs(const uint4 (&smp)[4], int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
+// be decided by the bracket: bit v of the result is set when natural row v (coefficients 8v..8v+7) holds one.
+__device__ __forceinline__ uint32_t block_fast_regs(const uint4 (&smp)[4], int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
   float d[64];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
@@ -300,7 +353,7 @@ __device__ __forceinline__ bool block_fast_regs(const uint4 (&smp)[4], int comp,
     *dcq = min(max(v, -2048), 2047);
   }
   uint32_t q[64];
-  uint32_t bad = 0;
+  uint32_t bad[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (comp == 0) quant_all<0>(d, q, bad, magic, std::make_integer_sequence<int, 63>());
   else quant_all<1>(d, q, bad, magic, std::make_integer_sequence<int, 63>());
   q[0] = (uint32_t)*dcq;
@@ -309,9 +362,12 @@ __device__ __forceinline__ bool block_fast_regs(const uint4 (&smp)[4], int comp,
   const uint32_t lo32 = spread16(m0) | (spread16(m0 >> 16) << 1);
   const uint32_t hi32 = spread16(m1) | (spread16(m1 >> 16) << 1);
   *mask = ((uint64_t)hi32 << 32) | (lo32 & ~1u);
-  return bad != 0;
+  uint32_t rows = 0;
+#pragma unroll
+  for (int v = 0; v < 8; v++) rows |= (bad[v] ? 1u : 0u) << v;
+  return rows;
 }
-__device__ __forceinline__ bool block_fast(const uint32_t* __restrict__ blk, int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
+__device__ __forceinline__ uint32_t block_fast(const uint32_t* __restrict__ blk, int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
   uint4 v[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) v[k] = reinterpret_cast<const uint4*>(blk)[k];

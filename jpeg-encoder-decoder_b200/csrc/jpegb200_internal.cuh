@@ -74,10 +74,10 @@ struct JbRun {
 };
 // runs of one chroma plane that lie in MCU rows < my (mw = MCUs per row); luma has twice as many (two block rows per MCU row)
 __host__ __device__ inline uint32_t jb_runs_before(uint32_t mw, uint32_t my) {
-  uint32_t g = mw & (0u - mw);                   // largest power of two dividing mw
-  if (g > JB_TILE_MCUS) g = JB_TILE_MCUS;
-  const uint32_t period = JB_TILE_MCUS / g;      // every `period` MCU rows a row starts on a tile boundary
-  return (my * mw) / JB_TILE_MCUS + my - my / period;
+  // every `period` = 16 / gcd(mw, 16) MCU rows a row starts on a tile boundary; period = 1 << sh
+  uint32_t sh = 4;
+  if (!(mw & 15u)) sh = 0; else if (!(mw & 7u)) sh = 1; else if (!(mw & 3u)) sh = 2; else if (!(mw & 1u)) sh = 3;
+  return (my * mw) / JB_TILE_MCUS + my - (my >> sh);
 }
 __host__ __device__ inline uint32_t jb_runs_chroma(int w, int h) { return jb_runs_before((uint32_t)w / 16u, (uint32_t)h / 16u); }
 __host__ __device__ inline uint32_t jb_tiles(int w, int h) { return ((uint32_t)(w / 16) * (uint32_t)(h / 16) + JB_TILE_MCUS - 1) / JB_TILE_MCUS; }

@@ -23,7 +23,19 @@
 
 namespace {
 
-constexpr int TK_WARPS = 4;             // workers per CTA
+#ifndef TK_WARPS_PER_CTA
+#define TK_WARPS_PER_CTA 4
+#endif
+#ifndef TK_SYNC
+#define TK_SYNC 3
+#endif
+#ifndef TK_ABLATE
+#define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
+#endif
+#ifndef TK_CTAS_PER_SM
+#define TK_CTAS_PER_SM 3
+#endif
+constexpr int TK_WARPS = TK_WARPS_PER_CTA;   // workers per CTA
 constexpr int TK_WINDOW = 512;          // tokens staged per flush (2 KB = the 32 sample slots of the round)
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
@@ -37,8 +49,9 @@ struct __align__(128) TkSmem {
   uint32_t hist[544];                   // 0..15 luma DC categories, 16..271 luma AC symbols, 272..287 / 288..543 chroma
   unsigned long long full;              // mbarrier: the 8 rows in flight have landed
   uint32_t pad[2];
+  uint8_t ties[128];                    // patches (row pair * 32 + lane) of the 8 staged rows with a pixel on an integer boundary
 };
-static_assert(sizeof(double) * 4 * TR_STRIDE + 4 * 64 * sizeof(int16_t) <= sizeof(uint32_t) * 32 * 33, "exact-replay scratch must fit in cbuf");
+constexpr int TK_TIE_COOP_MAX = 48;     // longer tie lists (grey images) are replayed one patch per lane instead of 16 lanes per patch
 
 struct TkTile {
   int job, tile, m0, valid, mw, my0, mx0;
@@ -84,45 +97,79 @@ __device__ __noinline__ void tk_replay_patch(TkSmem& sm, int half, int mcu, int 
   sm.smp[(80 + mcu) * 16 + cw] = (cr[0] >> 2) | ((cr[1] >> 2) << 8) | ((cr[2] >> 2) << 16) | ((cr[3] >> 2) << 24);
 }
 
-// Colour conversion + 4:2:0 of the 8 staged rows (encoder.c:129-138): one 8x2 patch per lane and step.
+// Colour conversion + 4:2:0 of the 8 staged rows (encoder.c:129-138): one 8x2 patch per lane and step, one pixel row at a
+// time (the row loop is kept rolled: half the code).  Patches with a pixel whose Y, Cb or Cr is an exact integer (the
+// reference's double chain decides between n and n-1 there) are listed and replayed afterwards, 16 lanes per patch:
+// about one patch in 150 on photographic content, every patch on grey content.
 __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, int lane) {
   const int mcu = lane >> 1, pc = lane & 1;
-  if (mcu >= valid) return;
+  const bool live = mcu < valid;
   const int slot = half * 32 + lane;
+  uint32_t ntie = 0;
 #pragma unroll 1
   for (int pr = 0; pr < 4; pr++) {
-    uint32_t yb[2][8], cbb[2][8], crb[2][8];
-    uint32_t screen = 0xFFFFFFFFu;
+    uint32_t cbs[4] = {0, 0, 0, 0}, crs[4] = {0, 0, 0, 0};
+    uint32_t scr_y = 0xFFFFFFFFu, scr_c = 0xFFFFFFFFu;
+    if (live) {
+      uint32_t* ydst = &sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4];
+#pragma unroll 1
+      for (int dr = 0; dr < 2; dr++) {
+        uint32_t w[6], yb[8], cbb[8], crb[8];
+        const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
 #pragma unroll
-    for (int dr = 0; dr < 2; dr++) {
-      uint32_t w[6];
-      const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
+        for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+        ycc_row8x(w, yb, cbb, crb, scr_y, scr_c);
+        *reinterpret_cast<uint2*>(ydst + 2 * dr) = make_uint2(pack4(yb[0], yb[1], yb[2], yb[3]), pack4(yb[4], yb[5], yb[6], yb[7]));
 #pragma unroll
-      for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
-      ycc_row8(w, yb[dr], cbb[dr], crb[dr], screen);
+        for (int c = 0; c < 4; c++) {
+          cbs[c] += cbb[2 * c] + cbb[2 * c + 1];
+          crs[c] += crb[2 * c] + crb[2 * c + 1];
+        }
+      }
+      // chroma: integer mean of the four truncated samples (encoder.c:136-138); 4*0x4B000000 wraps to 0x2C000000
+      const int crow = half * 4 + pr, cw = (((crow >> 1) ^ (mcu >> 1)) & 3) * 4 + (crow & 1) * 2 + pc;
+      sm.smp[(64 + mcu) * 16 + cw] = pack4(cbs[0] >> 2, cbs[1] >> 2, cbs[2] >> 2, cbs[3] >> 2);
+      sm.smp[(80 + mcu) * 16 + cw] = pack4(crs[0] >> 2, crs[1] >> 2, crs[2] >> 2, crs[3] >> 2);
     }
-    if (screen < TIE_LIMIT) {
-      tk_replay_patch(sm, half, mcu, pr, pc);
-      continue;
+    const bool tie = !(TK_ABLATE & 2) && live && (scr_y == TIE_K_Y || scr_c == TIE_K_C);
+    const uint32_t tb = __ballot_sync(FULL, tie);
+    if (tie) sm.ties[ntie + __popc(tb & ((1u << lane) - 1u))] = (uint8_t)(pr * 32 + lane);
+    ntie += __popc(tb);
+  }
+  if (ntie == 0) return;
+  __syncwarp();
+  if (ntie > TK_TIE_COOP_MAX) {
+    for (uint32_t k = lane; k < ntie; k += 32) {
+      const int id = sm.ties[k];
+      tk_replay_patch(sm, half, (id & 31) >> 1, id >> 5, id & 1);
     }
-    *reinterpret_cast<uint4*>(&sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4]) =
-        make_uint4(pack4(yb[0][0], yb[0][1], yb[0][2], yb[0][3]), pack4(yb[0][4], yb[0][5], yb[0][6], yb[0][7]),
-                   pack4(yb[1][0], yb[1][1], yb[1][2], yb[1][3]), pack4(yb[1][4], yb[1][5], yb[1][6], yb[1][7]));
-    uint32_t cbv[4], crv[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      cbv[c] = (cbb[0][2 * c] + cbb[0][2 * c + 1] + cbb[1][2 * c] + cbb[1][2 * c + 1]) >> 2;
-      crv[c] = (crb[0][2 * c] + crb[0][2 * c + 1] + crb[1][2 * c] + crb[1][2 * c + 1]) >> 2;
+    return;
+  }
+  // two listed patches per pass: lane -> (patch, pixel row dr, pixel column c)
+  const int px = lane & 15, dr = px >> 3, c = px & 7;
+#pragma unroll 1
+  for (uint32_t k = 0; k < ntie; k += 2) {
+    const uint32_t e = k + (lane >> 4);
+    const int id = sm.ties[e < ntie ? e : k];
+    const int tl = id & 31, tpr = id >> 5, tmcu = tl >> 1, tpc = tl & 1, tslot = half * 32 + tl;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(&sm.raw[2 * tpr + dr][tmcu * 12 + 6 * tpc]) + 3 * c;
+    const uint32_t v = ycc_pixel(src[0], src[1], src[2]);
+    uint32_t cb = (v >> 8) & 0xFFu, cr = v >> 16;
+    cb += __shfl_xor_sync(FULL, cb, 1); cr += __shfl_xor_sync(FULL, cr, 1);
+    cb += __shfl_xor_sync(FULL, cb, 8); cr += __shfl_xor_sync(FULL, cr, 8);
+    if (e < ntie) {
+      reinterpret_cast<uint8_t*>(&sm.smp[tslot * 16 + ((tpr ^ (tslot >> 1)) & 3) * 4 + dr * 2])[c] = (uint8_t)v;
+      if ((px & 9) == 0) {               // even column of the upper row: owns the 2x2 mean
+        const int crow = half * 4 + tpr, cw = (((crow >> 1) ^ (tmcu >> 1)) & 3) * 4 + (crow & 1) * 2 + tpc;
+        reinterpret_cast<uint8_t*>(&sm.smp[(64 + tmcu) * 16 + cw])[c >> 1] = (uint8_t)(cb >> 2);
+        reinterpret_cast<uint8_t*>(&sm.smp[(80 + tmcu) * 16 + cw])[c >> 1] = (uint8_t)(cr >> 2);
+      }
     }
-    const int crow = half * 4 + pr, cw = (((crow >> 1) ^ (mcu >> 1)) & 3) * 4 + (crow & 1) * 2 + pc;
-    sm.smp[(64 + mcu) * 16 + cw] = pack4(cbv[0], cbv[1], cbv[2], cbv[3]);
-    sm.smp[(80 + mcu) * 16 + cw] = pack4(crv[0], crv[1], crv[2], crv[3]);
   }
 }
 
-// Walk the non-zero coefficients whose (bit-reversed) flags are in r: zig-zag positions BASE + 0..31.
-template <int BASE>
-__device__ __forceinline__ void tk_walk(uint32_t& r, bool gate, uint32_t& pos, uint32_t wbase, int& prev1, const int16_t* cbh, uint32_t* stage,
+// Walk the non-zero coefficients whose (bit-reversed) flags are in r: zig-zag positions base + 0..31.
+__device__ __forceinline__ void tk_walk(int base, uint32_t& r, bool gate, uint32_t& pos, uint32_t wbase, int& prev1, const int16_t* cbh, uint32_t* stage,
                                         uint32_t* hist_ac) {
   const uint32_t wend = wbase + TK_WINDOW;
   while (true) {
@@ -131,7 +178,7 @@ __device__ __forceinline__ void tk_walk(uint32_t& r, bool gate, uint32_t& pos, u
     if (act) {
       const int pz = __clz(r);
       r &= ~(0x80000000u >> pz);
-      const int p = BASE + pz;
+      const int p = base + pz;
       const int v = cbh[p];
       const int run = p - prev1;
       prev1 = p + 1;
@@ -146,7 +193,7 @@ __device__ __forceinline__ void tk_walk(uint32_t& r, bool gate, uint32_t& pos, u
 }
 
 template <bool BULK>
-__global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
+__global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TkSmem& sm = reinterpret_cast<TkSmem*>(smem_raw)[warp];
@@ -158,8 +205,11 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, 
     }
   }
   __syncwarp();
-  const int worker = blockIdx.x * TK_WARPS + warp, nworkers = gridDim.x * TK_WARPS;
-  const int t_begin = (int)((long long)ntiles * worker / nworkers), t_end = (int)((long long)ntiles * (worker + 1) / nworkers);
+  // The CTA owns a contiguous range of tiles; its warps take them round-robin and stay in step (phase_sync): the warps of
+  // a CTA then fetch the same instructions at the same time — with every warp on its own schedule the 80 KB of code
+  // thrash the instruction caches (measured: 56 % of the stall samples were no_inst).
+  const int cta_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), cta_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+  const int t_begin = cta_begin + warp, t_end = cta_end;
 
   // Fetch the 8 pixel rows `half` of tile t.  BULK: asynchronous (lane r < 8 owns row r); otherwise synchronous byte loads.
   auto fetch = [&](const TkTile& p, const JbJob& job, int half) {
@@ -187,10 +237,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, 
       __syncwarp();
     }
   };
-  auto next_valid = [&](int t, TkTile& p, JbJob& job) {
-    while (t < t_end && !tk_tile(ws, t, tiles_per_job, p, job)) t++;
+  auto next_valid = [&](int t, TkTile& p, JbJob& job) {      // tiles of this warp: t_begin, t_begin + TK_WARPS, ...
+    while (t < t_end && !tk_tile(ws, t, tiles_per_job, p, job)) t += TK_WARPS;
     return t;
   };
+  // TK_SYNC: 1 = the CTA's warps re-align once per tile, 2 = once per step, 3 = before every phase
+  auto phase_sync = [&](int level) { if (TK_WARPS > 1 && TK_SYNC >= level) __syncthreads(); };
   auto flush_hist = [&](int jobid) {
     int* G = ws.hist + (size_t)jobid * 4 * 257;
     __syncwarp();
@@ -211,9 +263,11 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, 
   JbJob job, jobn;
   int t = next_valid(t_begin, p, job);
   if (t < t_end) fetch(p, job, 0);
+  const int niter = (cta_end - cta_begin + TK_WARPS - 1) / TK_WARPS;
 #pragma unroll 1
-  while (t < t_end) {
-    if (p.job != cur_job) {
+  for (int it = 0; it < niter; it++) {
+    const bool active = t < t_end;                  // warp-uniform; idle warps only keep the CTA's barriers company
+    if (active && p.job != cur_job) {
       if (cur_job >= 0) flush_hist(cur_job);
       cur_job = p.job;
     }
@@ -222,171 +276,174 @@ __global__ void __launch_bounds__(TK_WARPS * 32, 3) k_pixels_to_tokens(JbWs ws, 
     int tn = t_end;
 #pragma unroll 1
     for (int step = 0; step < 3; step++) {          // step 0: rows 0-7 + round 0 ; step 1: rows 8-15 + round 1 ; step 2: round 2
+      phase_sync(step == 0 ? 1 : 2);
       if (step < 2) {
-        if (BULK) { mbar_wait(&sm.full, parity); parity ^= 1u; }
-        tk_colour_half(sm, step, p.valid, lane);
-        __syncwarp();
-        if (step == 0) fetch(p, job, 1);
-        else {
-          tn = next_valid(t + 1, pn, jobn);
-          if (tn < t_end) fetch(pn, jobn, 0);
+        if (active) {
+          if (BULK) { mbar_wait(&sm.full, parity); parity ^= 1u; }
+          tk_colour_half(sm, step, p.valid, lane);
+          __syncwarp();
+          if (step == 0) fetch(p, job, 1);
+          else {
+            tn = next_valid(t + TK_WARPS, pn, jobn);
+            if (tn < t_end) fetch(pn, jobn, 0);
+          }
         }
       }
       const int role = step;
       // ---- the lane's block -------------------------------------------------------------------------------------
       const int comp = role < 2 ? 0 : 1;
       const int mcu = role < 2 ? lane >> 1 : lane & 15;
-      const bool ok = mcu < p.valid;
+      const bool ok = active && mcu < p.valid;
       int my = p.my0, mx = p.mx0 + mcu;
-      while (mx >= p.mw) { mx -= p.mw; my++; }
+      if (active) while (mx >= p.mw) { mx -= p.mw; my++; }
       uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
       if (role < 2) blk = (uint32_t)(my * 2 + role) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
       else blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)(p.m0 + mcu);
       const int slot = role * 32 + lane;
       uint32_t out[32];
-      uint64_t mask;
-      int dcq;
-      bool bad;
-      {
-        uint4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const uint4*>(&sm.smp[slot * 16 + ((k ^ (slot >> 1)) & 3) * 4]);
-        bad = block_fast_regs(v, comp, magic, out, &mask, &dcq);
-      }
-      // ---- exact replay of undecided blocks: 8 lanes per block, up to 4 blocks per pass --------------------------------
-      uint32_t badm = __ballot_sync(FULL, bad && ok);
-      while (badm) {
-        double* tr = reinterpret_cast<double*>(sm.cbuf);
-        int16_t* zz = reinterpret_cast<int16_t*>(sm.cbuf) + (4 * TR_STRIDE * sizeof(double)) / sizeof(int16_t);
-        int src[4];
+      uint64_t mask = 0;
+      uint32_t badrows = 0;
+      int dcq = 0;
+      if (step < 2) phase_sync(3);
+      if (active) {
         {
-          uint32_t mm = badm;
+          uint4 v[4];
 #pragma unroll
-          for (int g = 0; g < 4; g++) { src[g] = mm ? __ffs(mm) - 1 : -1; mm &= mm - 1; }
-          badm = mm;
+          for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const uint4*>(&sm.smp[slot * 16 + ((k ^ (slot >> 1)) & 3) * 4]);
+          badrows = block_fast_regs(v, comp, magic, out, &mask, &dcq);
         }
-        const int g = lane >> 3, i = lane & 7;
-        const int mine = g == 0 ? src[0] : g == 1 ? src[1] : g == 2 ? src[2] : src[3];
-        const int s = role * 32 + (mine >= 0 ? mine : src[0]);
-        uint32_t px[8];
+        if (!ok) { badrows = 0; mask = 0; }          // lanes past the end of the crop transformed stale samples
+        // the zig-zagged block goes to the lane's private row: the token walk indexes it, the exact replay patches it
+        uint32_t* cb = sm.cbuf + lane * 33;
 #pragma unroll
-        for (int tt = 0; tt < 8; tt++) {
-          const uint32_t wv = sm.smp[s * 16 + (((tt >> 1) ^ (s >> 1)) & 3) * 4 + (tt & 1) * 2 + (i >> 2)];
-          px[tt] = (wv >> (8 * (i & 3))) & 0xFF;
-        }
-        __align__(16) double rql[8];
+        for (int j = 0; j < 32; j++) cb[j] = out[j];
+        // ---- exact replay of the natural rows that hold an undecided coefficient (8 lanes per row, 4 copies in step) -----
+        uint32_t badm = (TK_ABLATE & 4) ? 0u : __ballot_sync(FULL, badrows != 0);
+        if (badm) __syncwarp();
+        while (badm) {
+          const int L = __ffs(badm) - 1;
+          badm &= badm - 1;
+          uint32_t rows = __shfl_sync(FULL, badrows, L);
+          const int s = role * 32 + L, i = lane & 7;
+          uint32_t colb[8];
+          const uint8_t* sb = reinterpret_cast<const uint8_t*>(sm.smp);
 #pragma unroll
-        for (int u = 0; u < 8; u++) rql[u] = __dmul_rn(__drcp_rn((double)c_quant[comp][i * 8 + u]), 0x1.00000004p-2);
-        const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
-        uint64_t emask;
-        block_dct(px, comp, rql, izzrow, tr, zz, lane, &emask);
-        const uint32_t* zzw = reinterpret_cast<const uint32_t*>(zz);
+          for (int tt = 0; tt < 8; tt++) colb[tt] = sb[(s * 16 + (((tt >> 1) ^ (s >> 1)) & 3) * 4 + (tt & 1) * 2) * 4 + i];
+          const uint2 col8 = make_uint2(colb[0] | (colb[1] << 8) | (colb[2] << 16) | (colb[3] << 24), colb[4] | (colb[5] << 8) | (colb[6] << 16) | (colb[7] << 24));
+          while (rows) {
+            const int v = __ffs(rows) - 1;
+            rows &= rows - 1;
+            const int n = exact_row_coef(col8, comp, v, lane);
+            const int pos = g_izz[v * 8 + i];
+            // position 0 (DC) already went through the literal chain inside block_fast
+            if (lane < 8 && pos) reinterpret_cast<int16_t*>(sm.cbuf + L * 33)[pos] = (int16_t)n;
+            const uint64_t bit = pos ? 1ull << pos : 0ull, set = n ? bit : 0ull;
+            uint32_t b0 = (uint32_t)bit, b1 = (uint32_t)(bit >> 32), s0 = (uint32_t)set, s1 = (uint32_t)(set >> 32);
 #pragma unroll
-        for (int gg = 0; gg < 4; gg++) {
-          const uint32_t mlo = __shfl_sync(FULL, (uint32_t)emask, gg * 8), mhi = __shfl_sync(FULL, (uint32_t)(emask >> 32), gg * 8);
-          if (lane == src[gg]) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) out[j] = zzw[gg * 32 + j];
-            mask = ((uint64_t)mhi << 32) | mlo;
-            dcq = (int)(short)(out[0] & 0xFFFFu);
+            for (int o = 1; o < 8; o <<= 1) {
+              b0 |= __shfl_xor_sync(FULL, b0, o); b1 |= __shfl_xor_sync(FULL, b1, o);
+              s0 |= __shfl_xor_sync(FULL, s0, o); s1 |= __shfl_xor_sync(FULL, s1, o);
+            }
+            if (lane == L) mask = (mask & ~(((uint64_t)b1 << 32) | b0)) | (((uint64_t)s1 << 32) | s0);
           }
-        }
-        __syncwarp();
-      }
-
-      // ---- runs, token offsets --------------------------------------------------------------------------------------
-      if (!ok) mask = 0;             // lanes past the end of the crop transformed stale samples
-      const uint32_t cnt = ok ? 2u + (uint32_t)__popcll(mask) - (uint32_t)(mask >> 63) : 0u;
-      uint32_t inc = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(FULL, inc, o);
-        if (lane >= o) inc += n;
-      }
-      const uint32_t excl = inc - cnt, total = __shfl_sync(FULL, inc, 31);
-      const uint32_t prev_blk = __shfl_up_sync(FULL, blk, 1);
-      const int prev_dc = __shfl_up_sync(FULL, dcq, 1);
-      const uint32_t okb = __ballot_sync(FULL, ok);
-      const bool prev_ok = lane > 0 && ((okb >> (lane - 1)) & 1u);
-      const int prev_my = __shfl_up_sync(FULL, my, 1);
-      // a run ends with its MCU row (chroma blocks are consecutive across rows, the run records are not) and with its plane
-      const bool head = ok && (!prev_ok || blk != prev_blk + 1 || my != prev_my || (role == 2 && lane == 16));
-      const uint32_t hb = __ballot_sync(FULL, head);
-      const uint32_t round_tok = job.tok_off + (uint32_t)(p.tile * 3 + role) * JB_ROUND_TOKENS;
-      {
-        const uint32_t above = lane == 31 ? 0u : hb & ~((2u << lane) - 1u);
-        const int next = above ? __ffs(above) - 1 : 32;
-        const uint32_t excl_next = __shfl_sync(FULL, excl, next & 31);
-        const uint32_t run_end = next < 32 ? excl_next : total;
-        const uint32_t inrun = okb & (next < 32 ? (1u << next) - 1u : FULL) & ~((1u << lane) - 1u);
-        const int lastl = inrun ? 31 - __clz(inrun) : lane;
-        const int dc_last = __shfl_sync(FULL, dcq, lastl);
-        if (head) {
-          const uint32_t R0 = jb_runs_before((uint32_t)p.mw, (uint32_t)my), tfirst = (uint32_t)(my * p.mw) / JB_TILE_MCUS;
-          uint32_t rid;
-          if (role < 2) {
-            const uint32_t R1 = jb_runs_before((uint32_t)p.mw, (uint32_t)my + 1u);
-            rid = 2u * R0 + (uint32_t)role * (R1 - R0) + ((uint32_t)p.tile - tfirst);
-          } else {
-            rid = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
-          }
-          JbRun rr;
-          rr.tok = round_tok + excl;
-          rr.ntok = run_end - excl;
-          rr.dc = ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16);
-          rr.bits = 0;
-          *reinterpret_cast<uint4*>(&ws.runs[job.run_off + rid]) = make_uint4(rr.tok, rr.ntok, rr.dc, rr.bits);
+          __syncwarp();
         }
       }
 
-      // ---- token walk ---------------------------------------------------------------------------------------------------
-      uint32_t* cb = sm.cbuf + lane * 33;
+      phase_sync(3);
+      if (active && !(TK_ABLATE & 1)) {
+        // ---- runs, token offsets --------------------------------------------------------------------------------------
+        const uint32_t cnt = ok ? 2u + (uint32_t)__popcll(mask) - (uint32_t)(mask >> 63) : 0u;
+        uint32_t inc = cnt;
 #pragma unroll
-      for (int j = 0; j < 32; j++) cb[j] = out[j];
-      const int16_t* cbh = reinterpret_cast<const int16_t*>(cb);
-      uint32_t* stage = sm.smp + role * 512;
-      uint32_t* hist_dc = sm.hist + comp * 272;
-      uint32_t* hist_ac = hist_dc + 16;
-      uint32_t pos = excl;
-      uint32_t rlo = __brev((uint32_t)mask), rhi = __brev((uint32_t)(mask >> 32));
-      int prev1 = 1;
-      bool dc_pend = ok, eob_pend = ok && !(mask >> 63);
-      const int diff = dcq - prev_dc;
-      __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t n = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += n;
+        }
+        const uint32_t excl = inc - cnt, total = __shfl_sync(FULL, inc, 31);
+        const uint32_t prev_blk = __shfl_up_sync(FULL, blk, 1);
+        const int prev_dc = __shfl_up_sync(FULL, dcq, 1);
+        const uint32_t okb = __ballot_sync(FULL, ok);
+        const bool prev_ok = lane > 0 && ((okb >> (lane - 1)) & 1u);
+        const int prev_my = __shfl_up_sync(FULL, my, 1);
+        // a run ends with its MCU row (chroma blocks are consecutive across rows, the run records are not) and with its plane
+        const bool head = ok && (!prev_ok || blk != prev_blk + 1 || my != prev_my || (role == 2 && lane == 16));
+        const uint32_t hb = __ballot_sync(FULL, head);
+        const uint32_t round_tok = job.tok_off + (uint32_t)(p.tile * 3 + role) * JB_ROUND_TOKENS;
+        {
+          const uint32_t above = lane == 31 ? 0u : hb & ~((2u << lane) - 1u);
+          const int next = above ? __ffs(above) - 1 : 32;
+          const uint32_t excl_next = __shfl_sync(FULL, excl, next & 31);
+          const uint32_t run_end = next < 32 ? excl_next : total;
+          const uint32_t inrun = okb & (next < 32 ? (1u << next) - 1u : FULL) & ~((1u << lane) - 1u);
+          const int lastl = inrun ? 31 - __clz(inrun) : lane;
+          const int dc_last = __shfl_sync(FULL, dcq, lastl);
+          if (head) {
+            const uint32_t R0 = jb_runs_before((uint32_t)p.mw, (uint32_t)my), tfirst = (uint32_t)(my * p.mw) / JB_TILE_MCUS;
+            uint32_t rid;
+            if (role < 2) {
+              const uint32_t R1 = jb_runs_before((uint32_t)p.mw, (uint32_t)my + 1u);
+              rid = 2u * R0 + (uint32_t)role * (R1 - R0) + ((uint32_t)p.tile - tfirst);
+            } else {
+              rid = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
+            }
+            *reinterpret_cast<uint4*>(&ws.runs[job.run_off + rid]) =
+                make_uint4(round_tok + excl, run_end - excl, ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16), 0u);
+          }
+        }
+
+        // ---- token walk ---------------------------------------------------------------------------------------------------
+        const int16_t* cbh = reinterpret_cast<const int16_t*>(sm.cbuf + lane * 33);
+        uint32_t* stage = sm.smp + role * 512;
+        uint32_t* hist_dc = sm.hist + comp * 272;
+        uint32_t* hist_ac = hist_dc + 16;
+        uint32_t pos = excl;
+        uint32_t rlo = __brev((uint32_t)mask), rhi = __brev((uint32_t)(mask >> 32));
+        int prev1 = 1;
+        bool dc_pend = ok, eob_pend = ok && !(mask >> 63);
+        const int diff = dcq - prev_dc;
+        __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
 #pragma unroll 1
-      for (uint32_t wbase = 0; wbase < total; wbase += TK_WINDOW) {
-        const uint32_t wend = wbase + TK_WINDOW;
-        if (dc_pend && pos < wend) {
-          uint32_t tok = 0;                        // a run's first DC is predicted across runs: k_dc_fix fills it in
-          if (!head) {
-            const int cat = 32 - __clz(abs(diff));
-            tok = tk_token(diff, cat, 256 + cat, 0);
-            atomicAdd(&hist_dc[cat], 1u);
+        for (uint32_t wbase = 0; wbase < total; wbase += TK_WINDOW) {
+          const uint32_t wend = wbase + TK_WINDOW;
+          if (dc_pend && pos < wend) {
+            uint32_t tok = 0;                        // a run's first DC is predicted across runs: k_dc_fix fills it in
+            if (!head) {
+              const int cat = 32 - __clz(abs(diff));
+              tok = tk_token(diff, cat, 256 + cat, 0);
+              atomicAdd(&hist_dc[cat], 1u);
+            }
+            stage[pos - wbase] = tok;
+            pos++;
+            dc_pend = false;
           }
-          stage[pos - wbase] = tok;
-          pos++;
-          dc_pend = false;
+#pragma unroll 1
+          for (int hh = 0; hh < 2; hh++) {           // zig-zag positions 0..31, then 32..63 (one copy of the loop)
+            uint32_t r = hh ? rhi : rlo;
+            tk_walk(32 * hh, r, !dc_pend && (hh == 0 || rlo == 0), pos, wbase, prev1, cbh, stage, hist_ac);
+            if (hh) rhi = r; else rlo = r;
+          }
+          const bool eob = eob_pend && !dc_pend && rlo == 0 && rhi == 0 && pos < wend;
+          if (eob) {
+            stage[pos - wbase] = 0;                  // EOB: table index 0, no magnitude bits
+            pos++;
+            eob_pend = false;
+          }
+          const uint32_t eb = __ballot_sync(FULL, eob);
+          if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
+          __syncwarp();
+          const uint32_t n = min(total, wend) - wbase;
+          uint32_t* dst = ws.tok + round_tok + wbase;
+          for (uint32_t k = lane; k < n; k += 32) dst[k] = stage[k];
+          __syncwarp();
         }
-        tk_walk<0>(rlo, !dc_pend, pos, wbase, prev1, cbh, stage, hist_ac);
-        tk_walk<32>(rhi, !dc_pend && rlo == 0, pos, wbase, prev1, cbh, stage, hist_ac);
-        const bool eob = eob_pend && !dc_pend && rlo == 0 && rhi == 0 && pos < wend;
-        if (eob) {
-          stage[pos - wbase] = 0;                  // EOB: table index 0, no magnitude bits
-          pos++;
-          eob_pend = false;
-        }
-        const uint32_t eb = __ballot_sync(FULL, eob);
-        if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
-        __syncwarp();
-        const uint32_t n = min(total, wend) - wbase;
-        uint32_t* dst = ws.tok + round_tok + wbase;
-        for (uint32_t k = lane; k < n; k += 32) dst[k] = stage[k];
-        __syncwarp();
       }
     }
-    t = tn;
-    p = pn;
-    job = jobn;
+    if (active) {
+      t = tn;
+      p = pn;
+      job = jobn;
+    }
   }
   if (cur_job >= 0) flush_hist(cur_job);
 }

@@ -10,7 +10,7 @@ encodes its own 1024 frames, no data-path collective — frames are independent,
 
   value : whole-job Mpix/s, inputs already resident in HBM, CUDA-event timed on the launching stream
   e2e   : same metric through the C-ABI call with HOST (pinned) buffers, H2D and D2H inside the timed region
-  roofline : dominant kernel (k_bgr_to_coef) against the measured HBM copy peak (MEASURED_PEAKS.json)
+  roofline : dominant kernel (k_pixels_to_tokens) against the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline : the reference's own C (oracle/_ref/libref.so, built from /root/reference by oracle/Makefile)
                  timed on this box's host cores, one process per core, on a bounded sample of the workload
 
@@ -120,8 +120,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kind", default=KIND, choices=["natural", "noise", "ramp"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--frames-per-wave", type=int, default=8)
-    ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--frames-per-wave", type=int, default=64)
+    ap.add_argument("--lanes", type=int, default=2)
+    ap.add_argument("--e2e-frames-per-wave", type=int, default=16, help="smaller waves keep the PCIe pipeline of the host path full")
+    ap.add_argument("--e2e-lanes", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-frames-per-proc", type=int, default=12)
@@ -240,6 +242,8 @@ def main():
         h_out = torch.empty((n, slot), dtype=torch.uint8, pin_memory=True)
         h_sizes = torch.zeros(n, dtype=torch.int32, pin_memory=True)
 
+        enc.configure(a.e2e_frames_per_wave, a.e2e_lanes)
+
         def estep():
             enc.encode_batch_host_ptr(h_in.data_ptr(), n, W, H, h_out.data_ptr(), slot, h_sizes.data_ptr())
 
@@ -258,7 +262,7 @@ def main():
         dt = float(tt.item())
         e2e = {"value": world * n * FRAME_MPIX / (dt / a.steps), "unit": "Mpix/s", "h2d_bytes_per_step": world * n * W * H * 3,
                "d2h_bytes_per_step": world * (jpeg_bytes + 4 * n), "ms_per_step": 1000 * dt / a.steps,
-               "api": "jpegb200_encode_batch_host (pinned host buffers)"}
+               "api": "jpegb200_encode_batch_host (pinned host buffers)", "frames_per_wave": a.e2e_frames_per_wave, "lanes": a.e2e_lanes}
 
     if rank == 0:
         peaks = {}
@@ -273,12 +277,12 @@ def main():
             k1_avg_ms = k1_ms / k1_n
             frames_per_launch = n * a.steps / k1_n
             ach = alg_per_frame * frames_per_launch / (k1_avg_ms / 1e3) / 1e9
-            traffic = None
+            traffic = None                     # dram__bytes_read + dram__bytes_write of the kernel from the committed ncu --set full capture
             try:
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_launch"]
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_frame"] * frames_per_launch
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "k_bgr_to_coef", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            roof = {"bound": "hbm", "kernel": "k_pixels_to_tokens", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
                     "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n, "frames_per_launch": frames_per_launch,
                     "algorithmic_bytes_per_frame": alg_per_frame,

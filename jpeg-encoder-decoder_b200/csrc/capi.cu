@@ -246,9 +246,10 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     { StageTimer t(c, st, ST_RUNBITS); jb_launch_run_bits(ws, njobs, max_runs, st); }
     { StageTimer t(c, st, ST_SCAN); jb_launch_scan_runs(ws, njobs, st); }
     { StageTimer t(c, st, ST_PACK); jb_launch_pack_runs(ws, njobs, max_runs, st); }
-    { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
+    const uint32_t tail_ctas = njobs >= 16 ? 24 : 64;       // CTAs per job of the byte-stuffing kernels
+    { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, st); }
     { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
-    { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, 8, st); }
+    { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, tail_ctas, st); }
     CK(cudaGetLastError());
     return 0;
   }

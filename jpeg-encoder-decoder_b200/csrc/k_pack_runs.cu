@@ -51,20 +51,20 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_run_bits(JbWs ws) {
   load_enc(ws, blockIdx.y, enc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t r = blockIdx.x * PR_WARPS + warp;
-  if (r >= nr) return;
-  JbRun* run = ws.runs + job.run_off + r;
-  const uint32_t* e = enc[run_scan(r, nrc) ? 1 : 0];
-  const uint32_t zrl_len = e[0xF0] & 31u;
-  const uint32_t* tok = ws.tok + run->tok;
-  const uint32_t n = run->ntok;
-  uint32_t sum = 0;
-  for (uint32_t k = lane; k < n; k += 32) {
-    const uint32_t t = tok[k];
-    sum += (e[(t >> 15) & 0x1FF] & 31u) + ((t >> 11) & 15u) + (t >> 24) * zrl_len;
+  for (uint32_t r = blockIdx.x * PR_WARPS + warp; r < nr; r += gridDim.x * PR_WARPS) {
+    JbRun* run = ws.runs + job.run_off + r;
+    const uint32_t* e = enc[run_scan(r, nrc) ? 1 : 0];
+    const uint32_t zrl_len = e[0xF0] & 31u;
+    const uint32_t* tok = ws.tok + run->tok;
+    const uint32_t n = run->ntok;
+    uint32_t sum = 0;
+    for (uint32_t k = lane; k < n; k += 32) {
+      const uint32_t t = __ldg(tok + k);
+      sum += (e[(t >> 15) & 0x1FF] & 31u) + ((t >> 11) & 15u) + (t >> 24) * zrl_len;
+    }
+    sum = __reduce_add_sync(FULL, sum);
+    if (lane == 0) run->bits = sum;
   }
-  sum = __reduce_add_sync(FULL, sum);
-  if (lane == 0) run->bits = sum;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -133,8 +133,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
   load_enc(ws, blockIdx.y, enc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t r = blockIdx.x * PR_WARPS + warp;
-  if (r >= nr) return;
+  for (uint32_t r = blockIdx.x * PR_WARPS + warp; r < nr; r += gridDim.x * PR_WARPS) {
   const JbRun run = ws.runs[job.run_off + r];
   const int s = run_scan(r, nrc);
   const uint32_t* e = enc[s ? 1 : 0];
@@ -155,7 +154,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
 #pragma unroll
     for (int j = 0; j < PR_TOK; j++) {
       const bool live = first + j < ntok;
-      const uint32_t t = live ? tok[first + j] : 0u;
+      const uint32_t t = live ? __ldg(tok + first + j) : 0u;
       const uint32_t ent = e[(t >> 15) & 0x1FF];
       const uint32_t cat = (t >> 11) & 15u;
       word[j] = ((ent >> 5) << cat) | (t & 0x7FFu);
@@ -220,14 +219,21 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
     if (lane == 0) stage[0] = tail;
     rbase += step_total;
   }
+  __syncwarp();
+  }
 }
 
 }  // namespace
 
+// CTAs per job: enough to fill the GPU a few times over, few enough that the table load of a CTA is amortised over many runs
+static uint32_t run_ctas(int njobs, uint32_t max_runs) {
+  const uint32_t want = (max_runs + PR_WARPS - 1) / PR_WARPS, cap = (uint32_t)((148 * 8 * 2 + njobs - 1) / njobs);
+  return want < cap ? want : (cap ? cap : 1);
+}
 void jb_launch_run_bits(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_run_bits<<<dim3((max_runs + PR_WARPS - 1) / PR_WARPS, njobs), PR_WARPS * 32, 0, st>>>(ws);
+  k_run_bits<<<dim3(run_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
 }
 void jb_launch_scan_runs(const JbWs& ws, int njobs, cudaStream_t st) { k_scan_runs<<<njobs, 256, 0, st>>>(ws); }
 void jb_launch_pack_runs(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_pack_runs<<<dim3((max_runs + PR_WARPS - 1) / PR_WARPS, njobs), PR_WARPS * 32, 0, st>>>(ws);
+  k_pack_runs<<<dim3(run_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
 }

@@ -60,20 +60,21 @@ struct PinBuf {
 
 // Sizes of one wave's workspace.
 struct WaveDims {
-  size_t njobs = 0, coefs = 0, blocks = 0, chunks = 0, scratch_words = 0, tiles = 0, toks = 0, runs = 0;
+  size_t njobs = 0, coefs = 0, blocks = 0, chunks = 0, scratch_words = 0, tiles = 0, toks = 0, runs = 0, tchunks = 0;
   bool planes = true;         // the wave needs coefficient planes (plane path); the token path does not
 };
 
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr, sizes_ready = nullptr;
-  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base;
+  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
   // host path bookkeeping of the wave in flight
   int pending_first = -1, pending_n = 0;
   size_t sh_bytes = 0;        // bytes of the state+histogram block laid out by the last ensure()
+  size_t tchunk_bytes = 0;    // bytes of the token-chunk bit totals (zeroed per wave)
 
   cudaError_t ensure(const WaveDims& d) {
     cudaError_t e;
@@ -91,6 +92,10 @@ struct Lane {
       if ((e = tok.ensure(d.toks * sizeof(uint32_t))) != cudaSuccess) return e;
       if ((e = runs.ensure(d.runs * sizeof(JbRun))) != cudaSuccess) return e;
       if ((e = run_base.ensure(d.runs * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = tok2.ensure(d.toks * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = tchunk_bits.ensure(d.tchunks * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = tchunk_base.ensure(d.tchunks * sizeof(uint32_t))) != cudaSuccess) return e;
+      tchunk_bytes = d.tchunks * sizeof(uint32_t);
     }
     if ((e = huff.ensure(d.njobs * 4 * sizeof(JbHuff))) != cudaSuccess) return e;
     if ((e = enc.ensure(d.njobs * 4 * 256 * sizeof(uint32_t))) != cudaSuccess) return e;
@@ -115,10 +120,13 @@ struct Lane {
     ws.tok = (uint32_t*)tok.p;
     ws.runs = (JbRun*)runs.p;
     ws.run_base = (uint32_t*)run_base.p;
+    ws.tok2 = (uint32_t*)tok2.p;
+    ws.tchunk_bits = (uint32_t*)tchunk_bits.p;
+    ws.tchunk_base = (uint32_t*)tchunk_base.p;
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &tok2, &tchunk_bits, &tchunk_base, &in, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -130,7 +138,7 @@ struct Lane {
 
 // Per-job workspace footprint for a w x h crop whose output slot holds `slot` bytes.
 struct JobDims {
-  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs;
+  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs, tchunks;
 };
 JobDims job_dims(int w, int h, size_t slot) {
   JobDims d;
@@ -143,8 +151,9 @@ JobDims job_dims(int w, int h, size_t slot) {
   words = (words + 3) & ~(size_t)3;
   d.scratch_words = (uint32_t)words;
   d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
-  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS;
+  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS + 3u * JB_TCHUNK;     // + the alignment of the three scans in scan order
   d.runs = 4u * jb_runs_chroma(w, h);
+  d.tchunks = d.toks / JB_TCHUNK + 1u;
   return d;
 }
 
@@ -168,6 +177,7 @@ __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t fram
   j.src_bytes = 3u * (uint32_t)w * (uint32_t)h;
   j.tok_off = (uint32_t)i * d.toks;
   j.run_off = (uint32_t)i * d.runs;
+  j.tchunk_off = (uint32_t)i * d.tchunks;
   jobs[i] = j;
 }
 
@@ -234,18 +244,19 @@ struct StageTimer {
 
 // Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
 int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
-              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false, uint32_t max_runs = 0) {
+              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false, uint32_t max_runs = 0, uint32_t max_tchunks = 0) {
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
     { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, st); }
-    { StageTimer t(c, st, ST_DCFIX); jb_launch_dc_fix(ws, njobs, max_runs, st); }
+    CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
+    { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }
     { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }
     { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
-    { StageTimer t(c, st, ST_RUNBITS); jb_launch_run_bits(ws, njobs, max_runs, st); }
-    { StageTimer t(c, st, ST_SCAN); jb_launch_scan_runs(ws, njobs, st); }
-    { StageTimer t(c, st, ST_PACK); jb_launch_pack_runs(ws, njobs, max_runs, st); }
+    { StageTimer t(c, st, ST_RUNBITS); jb_launch_compact_tokens(ws, njobs, max_runs, st); }
+    { StageTimer t(c, st, ST_SCAN); jb_launch_scan_tchunks(ws, njobs, st); }
+    { StageTimer t(c, st, ST_PACK); jb_launch_pack_tchunks(ws, njobs, max_tchunks, st); }
     const uint32_t tail_ctas = njobs >= 16 ? 24 : 64;       // CTAs per job of the byte-stuffing kernels
     { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, st); }
     { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
@@ -297,11 +308,12 @@ int upload_jobs(Lane& l, const std::vector<JbJob>& jobs) {
 
 // Lay out `n` heterogeneous jobs in one lane workspace.
 int plan_jobs(Lane& l, std::vector<JbJob>& jobs, const std::vector<size_t>& slots, int* max_w, int* max_h, uint32_t* max_blocks,
-              uint32_t* max_chunks, bool planes = true, uint32_t* max_runs = nullptr) {
+              uint32_t* max_chunks, bool planes = true, uint32_t* max_runs = nullptr, uint32_t* max_tchunks = nullptr) {
   WaveDims wd;
   wd.njobs = jobs.size();
   wd.planes = planes;
   if (max_runs) *max_runs = 0;
+  if (max_tchunks) *max_tchunks = 0;
   *max_w = *max_h = 0; *max_blocks = *max_chunks = 0;
   for (size_t i = 0; i < jobs.size(); i++) {
     JobDims d = job_dims(jobs[i].w, jobs[i].h, slots[i]);
@@ -314,8 +326,10 @@ int plan_jobs(Lane& l, std::vector<JbJob>& jobs, const std::vector<size_t>& slot
     jobs[i].scratch_cap = d.scratch_words;
     jobs[i].tok_off = (uint32_t)wd.toks;
     jobs[i].run_off = (uint32_t)wd.runs;
-    wd.toks += d.toks; wd.runs += d.runs;
+    jobs[i].tchunk_off = (uint32_t)wd.tchunks;
+    wd.toks += d.toks; wd.runs += d.runs; wd.tchunks += d.tchunks;
     if (max_runs) *max_runs = std::max(*max_runs, d.runs);
+    if (max_tchunks) *max_tchunks = std::max(*max_tchunks, d.tchunks);
     wd.coefs += d.coefs; wd.blocks += d.blocks; wd.chunks += d.chunks; wd.tiles += 3 * (size_t)d.tiles_per_seg;
     wd.scratch_words += d.scratch_words;
     *max_w = std::max(*max_w, jobs[i].w); *max_h = std::max(*max_h, jobs[i].h);
@@ -443,7 +457,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   const size_t g = (size_t)std::min(G, n);
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
-  wd.toks = g * jd.toks; wd.runs = g * jd.runs;
+  wd.toks = g * jd.toks; wd.runs = g * jd.runs; wd.tchunks = g * jd.tchunks;
   const bool tokens = c->token_path && !c->exact_dct;
   wd.planes = !tokens;
   if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
@@ -458,7 +472,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, d_bgr + (size_t)first * frame_stride, frame_stride, w, h,
                                                           d_out + (size_t)first * slot, slot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first, true, tokens ? jd.runs : 0)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, d_sizes + first, true, tokens ? jd.runs : 0, jd.tchunks)) return -1;
   }
   for (int i = 0; i < nl; i++) {
     CK(cudaEventRecord(c->lanes[i].done, c->lanes[i].stream));
@@ -480,7 +494,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
   WaveDims wd;
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
-  wd.toks = g * jd.toks; wd.runs = g * jd.runs;
+  wd.toks = g * jd.toks; wd.runs = g * jd.runs; wd.tchunks = g * jd.tchunks;
   const bool tokens = c->token_path && !c->exact_dct;
   wd.planes = !tokens;
   if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
@@ -515,7 +529,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, (const uint8_t*)l.in.p, frame, w, h, (uint8_t*)l.out.p, dslot, jd);
     c->launches++;
-    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true, tokens ? jd.runs : 0)) return -1;
+    if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true, tokens ? jd.runs : 0, jd.tchunks)) return -1;
     CK(cudaMemcpyAsync(l.h_sizes.p, l.sizes.p, (size_t)cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, l.stream));
     CK(cudaEventRecord(l.sizes_ready, l.stream));
     l.pending_first = first;
@@ -553,12 +567,12 @@ int jpegb200_encode_regions(jpegb200_ctx* c, const uint8_t* d_frame, int frame_w
   CK(cudaStreamWaitEvent(l.stream, c->fork, 0));
   CK(cudaStreamSynchronize(l.stream));       // the workspace may be re-allocated below
   const bool tokens = c->token_path && !c->exact_dct;
-  uint32_t mr = 0;
-  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc, !tokens, &mr)) return -1;
+  uint32_t mr = 0, mt = 0;
+  if (plan_jobs(l, jobs, slots, &mw, &mh, &mb, &mc, !tokens, &mr, &mt)) return -1;
   if (upload_jobs(l, jobs)) return -1;
   bool rows_aligned = true;          // every crop row starts on a 16-byte boundary -> bulk async copies
   for (const JbJob& j : jobs) rows_aligned = rows_aligned && ((((uintptr_t)j.src + (size_t)j.y * j.pitch + 3u * (uint32_t)j.x) | j.pitch) & 15) == 0;
-  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes, rows_aligned, tokens ? mr : 0)) return -1;
+  if (run_chain(c, l, nareas, mw, mh, mb, mc, FROM_PIXELS, false, false, d_sizes, rows_aligned, tokens ? mr : 0, mt)) return -1;
   CK(cudaEventRecord(l.done, l.stream));
   CK(cudaStreamWaitEvent(user, l.done, 0));
   return 0;

@@ -42,8 +42,9 @@ struct JbJob {
   uint8_t* out;         // destination slot of the finished JFIF stream
   uint32_t out_cap;     // bytes available there
   uint32_t src_bytes;   // bytes readable from src (bounds the over-fetch of the aligned loader)
-  uint32_t tok_off;     // token path: first token of this job's pool inside ws.tok (JB_ROUND_TOKENS per tile and round)
+  uint32_t tok_off;     // token path: first token of this job's pool inside ws.tok and ws.tok2 (capacity: JB_ROUND_TOKENS per tile and round)
   uint32_t run_off;     // token path: first run record of this job (Y runs, then Cb, then Cr)
+  uint32_t tchunk_off;  // token path: first token chunk of this job in ws.tchunk_bits / ws.tchunk_base
 };
 
 // Per-job results of the scan / layout kernels.
@@ -54,6 +55,9 @@ struct JbJobState {
   uint32_t seg_ff[3];        // number of 0xFF data bytes (= stuffed zero bytes) per scan
   uint32_t size;             // total bytes of the JFIF stream (0 on error)
   uint32_t error;            // JB_ERR_* bits
+  uint32_t tok_total[3];     // token path: tokens per scan
+  uint32_t tok_start[3];     // token path: first token of each scan inside the job's part of ws.tok2 (multiple of JB_TCHUNK)
+  uint32_t tok_cursor;       // token path: tokens handed out so far in the job's part of ws.tok (rounds claim their space atomically)
 };
 
 enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4 };
@@ -70,8 +74,17 @@ struct JbRun {
   uint32_t tok;        // index of the run's first token in ws.tok (always the head block's DC token)
   uint32_t ntok;
   uint32_t dc;         // low half: quantised DC of the run's first block, high half: of its last block (before prediction)
-  uint32_t bits;       // entropy-coded bits of the run (k_run_bits)
+  uint32_t pad;
 };
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t jb_token(int v, int cat, int idx, int zrl) {
+  const uint32_t mag = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);           // encoder.c:441-443, :455-457
+  return mag | ((uint32_t)cat << 11) | ((uint32_t)idx << 15) | ((uint32_t)zrl << 24);
+}
+#endif
+// The bit packer works on *token chunks*: JB_TCHUNK consecutive tokens of one scan, after k_compact_tokens has copied the
+// runs' tokens into scan order (ws.tok2).  Each scan's region of tok2 starts on a chunk boundary.
+#define JB_TCHUNK 256
 // runs of one chroma plane that lie in MCU rows < my (mw = MCUs per row); luma has twice as many (two block rows per MCU row)
 __host__ __device__ inline uint32_t jb_runs_before(uint32_t mw, uint32_t my) {
   // every `period` = 16 / gcd(mw, 16) MCU rows a row starts on a tile boundary; period = 1 << sh
@@ -101,7 +114,10 @@ struct JbWs {
   uint2* fix_list;      // per wave: (job, block id inside the job) of blocks the fast DCT could not decide
   uint32_t* tok;        // token path: token pool
   JbRun* runs;          // token path: run records
-  uint32_t* run_base;   // token path: per run, bit offset inside its scan
+  uint32_t* run_base;   // token path: per run, index of its first token inside the job's part of ws.tok2
+  uint32_t* tok2;       // token path: tokens in scan order
+  uint32_t* tchunk_bits;  // token path: per token chunk, entropy-coded bits (zeroed per wave, accumulated by k_compact_tokens)
+  uint32_t* tchunk_base;  // token path: per token chunk, bit offset inside its scan
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -142,10 +158,10 @@ void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStrea
 
 // token path (k_tokens.cu, k_pack_runs.cu)
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
-void jb_launch_dc_fix(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
-void jb_launch_run_bits(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
-void jb_launch_scan_runs(const JbWs& ws, int njobs, cudaStream_t st);
-void jb_launch_pack_runs(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
+void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
+void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st);
+void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st);
 
 // comparator (brain.c)
 void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, cudaStream_t st);

@@ -1,12 +1,15 @@
-// k_pack_runs.cu — pass 2 of the batched encoder on sm_100a: from the token stream of k_pixels_to_tokens to the un-stuffed
-// scan bits (reference main/encoder.c:434-502).  The unit of work is a run (consecutive blocks of one scan whose tokens
-// are contiguous, jpegb200_internal.cuh); one warp streams one run, no CTA barrier is involved.
-//   k_run_bits    bits of every run = sum over its tokens of (code length + magnitude bits [+ ZRL codes])
-//   k_scan_runs   per job: exclusive prefix of the run bits inside each of the three scans, scan placement in the
-//                 job's scratch area, clearing of the words that two runs share          (as k_scan for chunks)
-//   k_pack_runs   per run: 8 consecutive tokens per lane and step are concatenated in registers, a warp scan gives the
-//                 bit offsets, the step's bits are assembled in shared memory and flushed as big-endian words
-//                 (the first and the last word of a run are OR-ed into place)
+// k_pack_runs.cu — pass 2 of the batched encoder on sm_100a: from the token runs of k_pixels_to_tokens to the un-stuffed
+// scan bits (reference main/encoder.c:434-502).
+//   k_runs_prepare    per job: the first DC token of every run (encoder.c:168-177 predicts across the whole plane, a run only
+//                     knows its own blocks) with its histogram entry; exclusive prefix of the runs' token counts inside each
+//                     scan = where each run goes in scan order
+//   k_compact_tokens  per run (one warp): copies the run's tokens into scan order (ws.tok2) and adds their code bits
+//                     (code length + magnitude bits [+ ZRL codes]) to the totals of the token chunks they land in
+//   k_scan_tchunks    per job: exclusive prefix of the chunk bits inside each of the three scans, scan placement in the
+//                     job's scratch area, clearing of the words that two chunks share
+//   k_pack_tchunks    per chunk of 256 tokens (one warp): 8 consecutive tokens per lane are concatenated in registers, a warp
+//                     scan gives the bit offsets, the chunk's bits are assembled in shared memory and flushed as big-endian
+//                     words (the first and the last word of a chunk are OR-ed into place)
 // Byte stuffing, headers and layout stay with k_count_ff / k_layout / k_stuff (k_entropy.cu).
 #include "jpegb200_internal.cuh"
 #include "walk.cuh"
@@ -14,11 +17,11 @@
 namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
-constexpr int PR_WARPS = 8;                 // runs per CTA
-constexpr int PR_TOK = 8;                   // tokens per lane and step
-constexpr int PR_STEP = 32 * PR_TOK;
+constexpr int PR_WARPS = 8;                 // warps per CTA
+constexpr int PR_TOK = JB_TCHUNK / 32;      // tokens per lane
+static_assert(PR_TOK == 8, "the register concatenation below is written for 8 tokens per lane");
 // a token is at most 3 ZRL codes + one code + 11 magnitude bits = 75 bits
-constexpr int PR_STAGE_WORDS = (31 + PR_STEP * 75 + 31) / 32 + 2;
+constexpr int PR_STAGE_WORDS = (31 + JB_TCHUNK * 75 + 31) / 32 + 2;
 
 __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t* total) {
   const int lane = threadIdx.x & 31;
@@ -32,10 +35,10 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t* total) 
   return inc - v;
 }
 
-// run r of the job -> table set (0 luma, 1 chroma) and scan (0 Y, 1 Cb, 2 Cr)
+// run r of the job -> scan (0 Y, 1 Cb, 2 Cr); scans 1 and 2 share the chroma tables
 __device__ __forceinline__ int run_scan(uint32_t r, uint32_t nrc) { return r < 2u * nrc ? 0 : (r < 3u * nrc ? 1 : 2); }
 
-// cost[t][i]: code length of table index i (0..255 AC symbols, 256..271 DC categories) of table set t
+// enc[t][i]: code << 5 | length of table index i (0..255 AC symbols, 256..271 DC categories) of table set t (0 luma, 1 chroma)
 __device__ __forceinline__ void load_enc(const JbWs& ws, uint32_t job, uint32_t (*enc)[272]) {
   const uint32_t* g = ws.enc + (size_t)job * 4 * 256;
   for (int k = threadIdx.x; k < 2 * 272; k += blockDim.x) {
@@ -44,47 +47,112 @@ __device__ __forceinline__ void load_enc(const JbWs& ws, uint32_t job, uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32) k_run_bits(JbWs ws) {
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_runs_prepare(JbWs ws) {
+  __shared__ uint32_t h[32];
+  __shared__ uint32_t wsum[9];
+  const JbJob job = ws.jobs[blockIdx.x];
+  JbJobState* st = ws.state + blockIdx.x;
+  const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
+  const JbRun* runs = ws.runs + job.run_off;
+  if (threadIdx.x < 32) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint32_t r = threadIdx.x; r < nr; r += 256) {
+    const int plane = run_scan(r, nrc);
+    const bool first = r == 0 || r == 2u * nrc || r == 3u * nrc;
+    const JbRun run = runs[r];
+    const int dc = (int)(short)(run.dc & 0xFFFFu);
+    const int prev = first ? 0 : (int)(short)(runs[r - 1].dc >> 16);
+    const int diff = dc - prev;
+    const int cat = 32 - __clz(abs(diff));
+    ws.tok[run.tok] = jb_token(diff, cat, 256 + cat, 0);
+    atomicAdd(&h[(plane ? 16 : 0) + cat], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32 && h[threadIdx.x]) {
+    int* G = ws.hist + (size_t)blockIdx.x * 4 * 257;
+    atomicAdd(&G[(threadIdx.x >= 16 ? 2 * 257 : 0) + (threadIdx.x & 15)], (int)h[threadIdx.x]);
+  }
+  // where each run goes in scan order
+  uint32_t start = 0;
+  for (int s = 0; s < 3; s++) {
+    const uint32_t r0 = s == 0 ? 0u : (s == 1 ? 2u * nrc : 3u * nrc), n = s == 0 ? 2u * nrc : nrc;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < n; b += 256) {
+      const uint32_t k = b + threadIdx.x;
+      uint32_t v = k < n ? runs[r0 + k].ntok : 0, total;
+      const uint32_t ex = cta_exclusive_scan(v, wsum, &total);
+      if (k < n) ws.run_base[job.run_off + r0 + k] = start + carry + ex;
+      carry += total;
+    }
+    if (threadIdx.x == 0) { st->tok_total[s] = carry; st->tok_start[s] = start; }
+    start = (start + carry + JB_TCHUNK - 1) & ~(uint32_t)(JB_TCHUNK - 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
   __shared__ uint32_t enc[2][272];
   const JbJob job = ws.jobs[blockIdx.y];
   const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
   load_enc(ws, blockIdx.y, enc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* tok2 = ws.tok2 + job.tok_off;
+  uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
   for (uint32_t r = blockIdx.x * PR_WARPS + warp; r < nr; r += gridDim.x * PR_WARPS) {
-    JbRun* run = ws.runs + job.run_off + r;
+    const JbRun run = ws.runs[job.run_off + r];
     const uint32_t* e = enc[run_scan(r, nrc) ? 1 : 0];
     const uint32_t zrl_len = e[0xF0] & 31u;
-    const uint32_t* tok = ws.tok + run->tok;
-    const uint32_t n = run->ntok;
-    uint32_t sum = 0;
-    for (uint32_t k = lane; k < n; k += 32) {
-      const uint32_t t = __ldg(tok + k);
-      sum += (e[(t >> 15) & 0x1FF] & 31u) + ((t >> 11) & 15u) + (t >> 24) * zrl_len;
+    const uint32_t* tok = ws.tok + run.tok;
+    const uint32_t d0 = ws.run_base[job.run_off + r];
+    for (uint32_t k0 = 0; k0 < run.ntok; k0 += 256) {       // 8 independent loads per lane in flight
+      uint32_t t8[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t k = k0 + 32 * j + lane;
+        t8[j] = k < run.ntok ? __ldg(tok + k) : 0u;
+      }
+      // the 256 tokens of this step land in at most two chunks
+      const uint32_t ca = (d0 + k0) / JB_TCHUNK;
+      uint32_t la = 0, lb = 0;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t k = k0 + 32 * j + lane;
+        if (k < run.ntok) {
+          const uint32_t t = t8[j];
+          tok2[d0 + k] = t;
+          const uint32_t len = (e[(t >> 15) & 0x1FF] & 31u) + ((t >> 11) & 15u) + (t >> 24) * zrl_len;
+          if ((d0 + k) / JB_TCHUNK == ca) la += len; else lb += len;
+        }
+      }
+      la = __reduce_add_sync(FULL, la);
+      lb = __reduce_add_sync(FULL, lb);
+      if (lane == 0) {
+        if (la) atomicAdd(&cbits[ca], la);
+        if (lb) atomicAdd(&cbits[ca + 1], lb);
+      }
     }
-    sum = __reduce_add_sync(FULL, sum);
-    if (lane == 0) run->bits = sum;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scan_runs(JbWs ws) {
+__global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
   __shared__ uint32_t wsum[9];
   __shared__ uint32_t s_word[4];
   const JbJob job = ws.jobs[blockIdx.x];
   JbJobState* st = ws.state + blockIdx.x;
-  const uint32_t nrc = jb_runs_chroma(job.w, job.h);
-  const JbRun* runs = ws.runs + job.run_off;
-  uint32_t* base = ws.run_base + job.run_off;
+  const uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
+  uint32_t* cbase = ws.tchunk_base + job.tchunk_off;
   uint32_t seg_bits[3];
   for (int s = 0; s < 3; s++) {
-    const uint32_t r0 = s == 0 ? 0u : (s == 1 ? 2u * nrc : 3u * nrc), n = s == 0 ? 2u * nrc : nrc;
+    const uint32_t c0 = st->tok_start[s] / JB_TCHUNK, n = (st->tok_total[s] + JB_TCHUNK - 1) / JB_TCHUNK;
     uint32_t carry = 0;
     for (uint32_t b = 0; b < n; b += 256) {
       const uint32_t k = b + threadIdx.x;
-      uint32_t v = k < n ? runs[r0 + k].bits : 0, total;
+      uint32_t v = k < n ? cbits[c0 + k] : 0, total;
       const uint32_t ex = cta_exclusive_scan(v, wsum, &total);
-      if (k < n) base[r0 + k] = carry + ex;
+      if (k < n) cbase[c0 + k] = carry + ex;
       carry += total;
     }
     seg_bits[s] = carry;
@@ -102,12 +170,12 @@ __global__ void __launch_bounds__(256) k_scan_runs(JbWs ws) {
   }
   __syncthreads();
   if (s_word[3] > job.scratch_cap) return;
-  // clear every word that two runs (or a run and the scan end) may share
+  // clear every word that two chunks (or a chunk and the scan end) may share
   for (int s = 0; s < 3; s++) {
-    const uint32_t r0 = s == 0 ? 0u : (s == 1 ? 2u * nrc : 3u * nrc), n = s == 0 ? 2u * nrc : nrc;
+    const uint32_t c0 = st->tok_start[s] / JB_TCHUNK, n = (st->tok_total[s] + JB_TCHUNK - 1) / JB_TCHUNK;
     uint32_t* scr = ws.scratch + job.scratch_off + s_word[s];
     for (uint32_t k = threadIdx.x; k <= n; k += 256) {
-      const uint32_t bit = k < n ? base[r0 + k] : seg_bits[s];
+      const uint32_t bit = k < n ? cbase[c0 + k] : seg_bits[s];
       scr[bit >> 5] = 0;
     }
   }
@@ -123,38 +191,44 @@ __device__ __forceinline__ void or_bits_s(uint32_t* img, uint32_t pos, uint32_t 
   if ((uint32_t)v) atomicOr(img + wi + 1, (uint32_t)v);
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
+__global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
   __shared__ uint32_t enc[2][272];
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
   if (st->error) return;
-  const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
+  uint32_t nchunk[3], total_chunks = 0;
+  for (int s = 0; s < 3; s++) { nchunk[s] = (st->tok_total[s] + JB_TCHUNK - 1) / JB_TCHUNK; total_chunks += nchunk[s]; }
+  if (blockIdx.x * PR_WARPS >= total_chunks) return;           // the grid is sized for the worst case
   load_enc(ws, blockIdx.y, enc);
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (uint32_t r = blockIdx.x * PR_WARPS + warp; r < nr; r += gridDim.x * PR_WARPS) {
-  const JbRun run = ws.runs[job.run_off + r];
-  const int s = run_scan(r, nrc);
-  const uint32_t* e = enc[s ? 1 : 0];
   uint32_t* stage = stage_all[warp];
-  const uint32_t zrl_code = e[0xF0] >> 5, zrl_len = e[0xF0] & 31u;
-  const uint32_t base_bits = ws.run_base[job.run_off + r], total = run.bits, ntok = run.ntok;
-  const uint32_t phase = base_bits & 31;
-  uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the run's first bit
-  const bool first_shared = phase != 0 || total < 32;
-  const uint32_t last_word = (phase + total - 1) >> 5;
-  const uint32_t* tok = ws.tok + run.tok;
-
-  uint32_t rbase = phase;            // run-relative bit position where the step starts (bit 0 = MSB of gw[0])
-  if (lane == 0) stage[0] = 0;
-  for (uint32_t r0 = 0; r0 < ntok; r0 += PR_STEP) {
-    const uint32_t first = r0 + lane * PR_TOK;
+  for (uint32_t f = blockIdx.x * PR_WARPS + warp; f < total_chunks; f += gridDim.x * PR_WARPS) {
+    const int s = f < nchunk[0] ? 0 : (f < nchunk[0] + nchunk[1] ? 1 : 2);
+    const uint32_t c = f - (s == 0 ? 0u : s == 1 ? nchunk[0] : nchunk[0] + nchunk[1]);
+    const uint32_t cg = st->tok_start[s] / JB_TCHUNK + c;                      // chunk id inside the job
+    const uint32_t ntok = min((uint32_t)JB_TCHUNK, st->tok_total[s] - c * JB_TCHUNK);
+    const uint32_t* e = enc[s ? 1 : 0];
+    const uint32_t zrl_code = e[0xF0] >> 5, zrl_len = e[0xF0] & 31u;
+    const uint32_t base_bits = ws.tchunk_base[job.tchunk_off + cg], total = ws.tchunk_bits[job.tchunk_off + cg];
+    const uint32_t phase = base_bits & 31;
+    uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the chunk's first bit
+    const bool first_shared = phase != 0 || total < 32;
+    const uint32_t last_word = (phase + total - 1) >> 5;
+    const uint4* tp = reinterpret_cast<const uint4*>(ws.tok2 + job.tok_off + (size_t)cg * JB_TCHUNK) + 2 * lane;
+    uint32_t t8[PR_TOK];
+    {
+      uint4 a = make_uint4(0, 0, 0, 0), b = a;
+      if (lane * PR_TOK < ntok) a = __ldg(tp);
+      if (lane * PR_TOK + 4 < ntok) b = __ldg(tp + 1);
+      t8[0] = a.x; t8[1] = a.y; t8[2] = a.z; t8[3] = a.w; t8[4] = b.x; t8[5] = b.y; t8[6] = b.z; t8[7] = b.w;
+    }
     uint32_t word[PR_TOK], len[PR_TOK], zr = 0, nbits = 0;
 #pragma unroll
     for (int j = 0; j < PR_TOK; j++) {
-      const bool live = first + j < ntok;
-      const uint32_t t = live ? __ldg(tok + first + j) : 0u;
+      const bool live = lane * PR_TOK + j < ntok;             // a partly filled vector carries stale tokens past the end
+      const uint32_t t = live ? t8[j] : 0u;
       const uint32_t ent = e[(t >> 15) & 0x1FF];
       const uint32_t cat = (t >> 11) & 15u;
       word[j] = ((ent >> 5) << cat) | (t & 0x7FFu);
@@ -163,12 +237,12 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
       zr |= z << (2 * j);
       nbits += len[j] + z * zrl_len;
     }
-    uint32_t step_total;
-    const uint32_t ex = warp_excl_scan(nbits, &step_total);
-    const uint32_t r_in = rbase & 31, endbit = r_in + step_total, nwr = (endbit + 31) >> 5;
-    for (uint32_t k = lane + 1; k < nwr + 1; k += 32) stage[k] = 0;        // stage[0] carries the previous step's tail
+    uint32_t chunk_total;
+    const uint32_t ex = warp_excl_scan(nbits, &chunk_total);
+    const uint32_t endbit = phase + chunk_total, nwr = (endbit + 31) >> 5;
+    for (uint32_t k = lane; k < nwr + 1; k += 32) stage[k] = 0;
     __syncwarp();
-    const uint32_t sbit = r_in + ex;
+    const uint32_t sbit = phase + ex;
     if (zr == 0) {
       uint32_t A[9];
 #pragma unroll
@@ -204,36 +278,28 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_runs(JbWs ws) {
       }
     }
     __syncwarp();
-    // flush: complete words of the image; the very last word of the run even if partial
-    const bool last_step = r0 + PR_STEP >= ntok;
-    const uint32_t full = endbit >> 5, rem = endbit & 31, w0 = rbase >> 5;
-    const uint32_t nflush = full + ((last_step && rem) ? 1u : 0u);
-    for (uint32_t k = lane; k < nflush; k += 32) {
+    // flush: every word of the image that holds bits of the chunk
+    for (uint32_t k = lane; k < nwr; k += 32) {
       const uint32_t w = __byte_perm(stage[k], 0, 0x0123);     // first bit of the stream = MSB of the first byte
-      const uint32_t g = w0 + k;
-      if ((g == 0 && first_shared) || (g == last_word && k == full)) atomicOr(gw + g, w);
-      else gw[g] = w;
+      if ((k == 0 && first_shared) || (k == last_word && (endbit & 31))) atomicOr(gw + k, w);
+      else gw[k] = w;
     }
-    const uint32_t tail = (!last_step && rem) ? stage[full] : 0u;
     __syncwarp();
-    if (lane == 0) stage[0] = tail;
-    rbase += step_total;
-  }
-  __syncwarp();
   }
 }
 
 }  // namespace
 
-// CTAs per job: enough to fill the GPU a few times over, few enough that the table load of a CTA is amortised over many runs
-static uint32_t run_ctas(int njobs, uint32_t max_runs) {
-  const uint32_t want = (max_runs + PR_WARPS - 1) / PR_WARPS, cap = (uint32_t)((148 * 8 * 2 + njobs - 1) / njobs);
-  return want < cap ? want : (cap ? cap : 1);
+// CTAs per job: enough to fill the GPU a few times over, few enough that the table load of a CTA is amortised over many items
+static uint32_t item_ctas(int njobs, uint32_t max_items) {
+  const uint32_t want = (max_items + PR_WARPS - 1) / PR_WARPS, cap = (uint32_t)((148 * 8 * 2 + njobs - 1) / njobs);
+  return want < cap ? (want ? want : 1) : (cap ? cap : 1);
 }
-void jb_launch_run_bits(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_run_bits<<<dim3(run_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
+void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st) { k_runs_prepare<<<njobs, 256, 0, st>>>(ws); }
+void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
+  k_compact_tokens<<<dim3(item_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
 }
-void jb_launch_scan_runs(const JbWs& ws, int njobs, cudaStream_t st) { k_scan_runs<<<njobs, 256, 0, st>>>(ws); }
-void jb_launch_pack_runs(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_pack_runs<<<dim3(run_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
+void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st) { k_scan_tchunks<<<njobs, 256, 0, st>>>(ws); }
+void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st) {
+  k_pack_tchunks<<<dim3(item_ctas(njobs, max_tchunks), njobs), PR_WARPS * 32, 0, st>>>(ws);
 }

@@ -27,7 +27,7 @@ namespace {
 #define TK_WARPS_PER_CTA 4
 #endif
 #ifndef TK_SYNC
-#define TK_SYNC 3
+#define TK_SYNC 2
 #endif
 #ifndef TK_ABLATE
 #define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
@@ -36,7 +36,9 @@ namespace {
 #define TK_CTAS_PER_SM 3
 #endif
 constexpr int TK_WARPS = TK_WARPS_PER_CTA;   // workers per CTA
-constexpr int TK_WINDOW = 512;          // tokens staged per flush (2 KB = the 32 sample slots of the round)
+constexpr int TK_WINDOW = 384;          // a round with at most this many tokens is staged in shared memory (the round's dead sample
+                                        // slots: 1.5 KB of tokens + 0.5 KB of per-block walk state) and flushed with coalesced stores;
+                                        // busier rounds store their tokens straight to global memory
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 struct __align__(128) TkSmem {
@@ -68,11 +70,6 @@ __device__ __forceinline__ bool tk_tile(const JbWs& ws, int t, int tiles_per_job
   p.my0 = p.m0 / p.mw;
   p.mx0 = p.m0 - p.my0 * p.mw;
   return true;
-}
-
-__device__ __forceinline__ uint32_t tk_token(int v, int cat, int idx, int zrl) {
-  const uint32_t mag = (uint32_t)(v + (v >> 31)) & ((1u << cat) - 1u);           // encoder.c:441-443, :455-457
-  return mag | ((uint32_t)cat << 11) | ((uint32_t)idx << 15) | ((uint32_t)zrl << 24);
 }
 
 // Cold path of the colour stage (see replay_patch in k_dct.cu): exact replay of one 8x2 patch.
@@ -164,30 +161,6 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
         reinterpret_cast<uint8_t*>(&sm.smp[(64 + tmcu) * 16 + cw])[c >> 1] = (uint8_t)(cb >> 2);
         reinterpret_cast<uint8_t*>(&sm.smp[(80 + tmcu) * 16 + cw])[c >> 1] = (uint8_t)(cr >> 2);
       }
-    }
-  }
-}
-
-// Walk the non-zero coefficients whose (bit-reversed) flags are in r: zig-zag positions base + 0..31.
-__device__ __forceinline__ void tk_walk(int base, uint32_t& r, bool gate, uint32_t& pos, uint32_t wbase, int& prev1, const int16_t* cbh, uint32_t* stage,
-                                        uint32_t* hist_ac) {
-  const uint32_t wend = wbase + TK_WINDOW;
-  while (true) {
-    const bool act = gate && r != 0 && pos < wend;
-    if (!__any_sync(FULL, act)) break;
-    if (act) {
-      const int pz = __clz(r);
-      r &= ~(0x80000000u >> pz);
-      const int p = base + pz;
-      const int v = cbh[p];
-      const int run = p - prev1;
-      prev1 = p + 1;
-      const int cat = 32 - __clz(abs(v));
-      const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
-      atomicAdd(&hist_ac[sym], 1u);
-      if (zrl) atomicAdd(&hist_ac[0xF0], (uint32_t)zrl);
-      stage[pos - wbase] = tk_token(v, cat, sym, zrl);
-      pos++;
     }
   }
 }
@@ -369,7 +342,11 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
         // a run ends with its MCU row (chroma blocks are consecutive across rows, the run records are not) and with its plane
         const bool head = ok && (!prev_ok || blk != prev_blk + 1 || my != prev_my || (role == 2 && lane == 16));
         const uint32_t hb = __ballot_sync(FULL, head);
-        const uint32_t round_tok = job.tok_off + (uint32_t)(p.tile * 3 + role) * JB_ROUND_TOKENS;
+        // the round claims its tokens' place in the job's pool (dense pool: the readers stream it); the answer is needed
+        // only when the tokens leave shared memory
+        uint32_t claim = 0;
+        if (lane == 0) claim = atomicAdd(&ws.state[p.job].tok_cursor, total);
+        uint32_t run_rid = 0xFFFFFFFFu, run_ntok = 0, run_dc = 0;
         {
           const uint32_t above = lane == 31 ? 0u : hb & ~((2u << lane) - 1u);
           const int next = above ? __ffs(above) - 1 : 32;
@@ -387,56 +364,107 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
             } else {
               rid = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
             }
-            *reinterpret_cast<uint4*>(&ws.runs[job.run_off + rid]) =
-                make_uint4(round_tok + excl, run_end - excl, ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16), 0u);
+            run_rid = rid;
+            run_ntok = run_end - excl;
+            run_dc = ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16);
           }
         }
 
         // ---- token walk ---------------------------------------------------------------------------------------------------
-        const int16_t* cbh = reinterpret_cast<const int16_t*>(sm.cbuf + lane * 33);
+        // DC and EOB tokens: every lane for its own block.  AC tokens: the round's non-zero coefficients are numbered in
+        // stream order and dealt out evenly, T consecutive ones per lane, whatever block they belong to (a lane-per-block
+        // walk runs at the pace of the busiest of 32 blocks: 36 % lane utilisation on photographic content).
         uint32_t* stage = sm.smp + role * 512;
+        uint2* s_mask = reinterpret_cast<uint2*>(stage + TK_WINDOW);           // bit-reversed non-zero flags of each block
+        uint32_t* s_meta = stage + TK_WINDOW + 64;                             // AC tokens before the block | tokens before it << 16
         uint32_t* hist_dc = sm.hist + comp * 272;
         uint32_t* hist_ac = hist_dc + 16;
-        uint32_t pos = excl;
-        uint32_t rlo = __brev((uint32_t)mask), rhi = __brev((uint32_t)(mask >> 32));
-        int prev1 = 1;
-        bool dc_pend = ok, eob_pend = ok && !(mask >> 63);
+        const uint32_t ac = (uint32_t)__popcll(mask);
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t b63 = __ballot_sync(FULL, (mask >> 63) != 0);
+        const uint32_t acex = excl - 2u * (uint32_t)__popc(okb & lt) + (uint32_t)__popc(b63 & lt);
+        const uint32_t total_ac = total - 2u * (uint32_t)__popc(okb) + (uint32_t)__popc(b63);
+        const uint32_t ne = __ballot_sync(FULL, ac != 0);
         const int diff = dcq - prev_dc;
         __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
-#pragma unroll 1
-        for (uint32_t wbase = 0; wbase < total; wbase += TK_WINDOW) {
-          const uint32_t wend = wbase + TK_WINDOW;
-          if (dc_pend && pos < wend) {
-            uint32_t tok = 0;                        // a run's first DC is predicted across runs: k_dc_fix fills it in
-            if (!head) {
-              const int cat = 32 - __clz(abs(diff));
-              tok = tk_token(diff, cat, 256 + cat, 0);
-              atomicAdd(&hist_dc[cat], 1u);
-            }
-            stage[pos - wbase] = tok;
-            pos++;
-            dc_pend = false;
+        s_mask[lane] = make_uint2(__brev((uint32_t)mask), __brev((uint32_t)(mask >> 32)));
+        s_meta[lane] = acex | (excl << 16);
+        uint32_t round_tok = 0;
+        if (total > TK_WINDOW) round_tok = job.tok_off + __shfl_sync(FULL, claim, 0);
+        uint32_t* dst = total <= TK_WINDOW ? stage : ws.tok + round_tok;        // generic pointer: shared or global
+        if (ok) {
+          uint32_t tok = 0;                          // a run's first DC is predicted across runs: k_dc_fix fills it in
+          if (!head) {
+            const int cat = 32 - __clz(abs(diff));
+            tok = jb_token(diff, cat, 256 + cat, 0);
+            atomicAdd(&hist_dc[cat], 1u);
           }
-#pragma unroll 1
-          for (int hh = 0; hh < 2; hh++) {           // zig-zag positions 0..31, then 32..63 (one copy of the loop)
-            uint32_t r = hh ? rhi : rlo;
-            tk_walk(32 * hh, r, !dc_pend && (hh == 0 || rlo == 0), pos, wbase, prev1, cbh, stage, hist_ac);
-            if (hh) rhi = r; else rlo = r;
-          }
-          const bool eob = eob_pend && !dc_pend && rlo == 0 && rhi == 0 && pos < wend;
-          if (eob) {
-            stage[pos - wbase] = 0;                  // EOB: table index 0, no magnitude bits
-            pos++;
-            eob_pend = false;
-          }
-          const uint32_t eb = __ballot_sync(FULL, eob);
-          if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
-          __syncwarp();
-          const uint32_t n = min(total, wend) - wbase;
-          uint32_t* dst = ws.tok + round_tok + wbase;
-          for (uint32_t k = lane; k < n; k += 32) dst[k] = stage[k];
-          __syncwarp();
+          dst[excl] = tok;
+          if (!(mask >> 63)) dst[excl + 1 + ac] = 0;                           // EOB: table index 0, no magnitude bits
         }
+        {
+          const uint32_t eb = okb & ~b63;
+          if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
+        }
+        __syncwarp();
+        const uint32_t T = (total_ac + 31) >> 5;
+        uint32_t g = min(lane * T, total_ac);
+        const uint32_t gend = min(g + T, total_ac);
+        int b = 0;
+        uint32_t rlo = 0, rhi = 0, pos = 0;
+        int prev1 = 1;
+        if (g < gend) {
+          int lo = 0, hi = 32;                       // block that holds AC token g: the last one with acex <= g
+#pragma unroll
+          for (int it = 0; it < 5; it++) {
+            const int mid = (lo + hi) >> 1;
+            const bool ge = (s_meta[mid] & 0xFFFFu) <= g;
+            lo = ge ? mid : lo;
+            hi = ge ? hi : mid;
+          }
+          b = lo;
+          const uint2 mm = s_mask[b];
+          const uint32_t meta = s_meta[b];
+          rlo = mm.x; rhi = mm.y;
+          uint32_t skip = g - (meta & 0xFFFFu);
+          pos = (meta >> 16) + 1u + skip;
+          for (; skip; skip--) {                     // tokens of this block that belong to the previous lane
+            if (rlo) { const int pz = __clz(rlo); rlo &= ~(0x80000000u >> pz); prev1 = pz + 1; }
+            else { const int pz = __clz(rhi); rhi &= ~(0x80000000u >> pz); prev1 = pz + 33; }
+          }
+        }
+#pragma unroll 1
+        for (uint32_t it = 0; it < T; it++) {
+          if (g < gend) {
+            if ((rlo | rhi) == 0) {                  // next block that has AC tokens
+              b = __ffs(ne & ~((2u << b) - 1u)) - 1;
+              const uint2 mm = s_mask[b];
+              rlo = mm.x; rhi = mm.y;
+              pos = (s_meta[b] >> 16) + 1u;
+              prev1 = 1;
+            }
+            int p;
+            if (rlo) { const int pz = __clz(rlo); rlo &= ~(0x80000000u >> pz); p = pz; }
+            else { const int pz = __clz(rhi); rhi &= ~(0x80000000u >> pz); p = pz + 32; }
+            const int v = reinterpret_cast<const int16_t*>(sm.cbuf + b * 33)[p];
+            const int run = p - prev1;
+            prev1 = p + 1;
+            const int cat = 32 - __clz(abs(v));
+            const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
+            atomicAdd(&hist_ac[sym], 1u);
+            if (zrl) atomicAdd(&hist_ac[0xF0], (uint32_t)zrl);
+            dst[pos] = jb_token(v, cat, sym, zrl);
+            pos++;
+            g++;
+          }
+        }
+        if (total <= TK_WINDOW) {
+          round_tok = job.tok_off + __shfl_sync(FULL, claim, 0);
+          uint32_t* gdst = ws.tok + round_tok;
+          for (uint32_t k = lane; k < total; k += 32) gdst[k] = stage[k];
+        }
+        if (run_rid != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(&ws.runs[job.run_off + run_rid]) = make_uint4(round_tok + excl, run_ntok, run_dc, 0u);
+        __syncwarp();
       }
     }
     if (active) {
@@ -446,32 +474,6 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
     }
   }
   if (cur_job >= 0) flush_hist(cur_job);
-}
-
-// ---- the first DC token of every run (encoder.c:168-177 predicts across the whole plane) -------------------------------
-__global__ void __launch_bounds__(256) k_dc_fix(JbWs ws) {
-  __shared__ uint32_t h[32];
-  const JbJob job = ws.jobs[blockIdx.y];
-  const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
-  if (threadIdx.x < 32) h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t r = blockIdx.x * 256u + threadIdx.x;
-  if (r < nr) {
-    const int plane = r < 2u * nrc ? 0 : (r < 3u * nrc ? 1 : 2);
-    const bool first = r == 0 || r == 2u * nrc || r == 3u * nrc;
-    const JbRun* runs = ws.runs + job.run_off;
-    const int dc = (int)(short)(runs[r].dc & 0xFFFFu);
-    const int prev = first ? 0 : (int)(short)(runs[r - 1].dc >> 16);
-    const int diff = dc - prev;
-    const int cat = 32 - __clz(abs(diff));
-    ws.tok[runs[r].tok] = tk_token(diff, cat, 256 + cat, 0);
-    atomicAdd(&h[(plane ? 16 : 0) + cat], 1u);
-  }
-  __syncthreads();
-  if (threadIdx.x < 32 && h[threadIdx.x]) {
-    int* G = ws.hist + (size_t)blockIdx.y * 4 * 257;
-    atomicAdd(&G[(threadIdx.x >= 16 ? 2 * 257 : 0) + (threadIdx.x & 15)], (int)h[threadIdx.x]);
-  }
 }
 
 }  // namespace
@@ -495,8 +497,4 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   const int want = (ntiles + TK_WARPS - 1) / TK_WARPS;
   const int grid = want < sms * ctas_per_sm[v] ? want : sms * ctas_per_sm[v];
   kern<<<grid, TK_WARPS * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
-}
-
-void jb_launch_dc_fix(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_dc_fix<<<dim3((max_runs + 255) / 256, njobs), 256, 0, st>>>(ws);
 }

@@ -352,11 +352,16 @@ __global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*p
 }
 
 // ---------------------------------------------------------------------------------------------
+// One 4 KiB tile of scan bytes per CTA step: the stuffed bytes are assembled in shared memory (byte stores are cheap there)
+// and leave as aligned 32-bit words; only the partial words at the two ends of the tile's output range are written
+// byte by byte, because the neighbouring tiles own the other bytes of those words.
 __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
   __shared__ uint32_t wsum[9];
+  __shared__ uint32_t so[(2 * JB_STUFF_TILE + 16) / 4];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
   if (st->error) return;
+  uint8_t* sob = reinterpret_cast<uint8_t*>(so);
   for (int s = 0; s < 3; s++) {
     const uint32_t nfull = st->seg_bits[s] >> 3;
     const uint32_t ntiles = (nfull + JB_STUFF_TILE - 1) / JB_STUFF_TILE;
@@ -370,8 +375,12 @@ __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
       if (off < nfull) { v = *reinterpret_cast<const uint4*>(src + off); valid = min(16u, nfull - off); }
       const uint32_t cnt = count_ff16(v, valid);
       uint32_t total;
-      const uint32_t ex = cta_exclusive_scan(cnt, wsum, &total);
-      uint8_t* o = dst + off + tf[t] + ex;
+      const uint32_t ex = cta_exclusive_scan(cnt, wsum, &total);       // its barriers also protect `so` against the previous tile
+      uint8_t* g = dst + (size_t)t * JB_STUFF_TILE + tf[t];             // first output byte of the tile
+      const uint32_t mis = (uint32_t)(uintptr_t)g & 3u;
+      const uint32_t nbytes = min((uint32_t)JB_STUFF_TILE, nfull - t * JB_STUFF_TILE) + total;
+      // shared byte position of output byte k of the tile: 4 + k
+      uint8_t* o = sob + 4 + threadIdx.x * 16 + ex;
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 16; i++) {
@@ -379,6 +388,22 @@ __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
           const uint8_t by = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
           *o++ = by;
           if (by == 0xFF) *o++ = 0;
+        }
+      }
+      __syncthreads();
+      // aligned word j of the output covers tile bytes [4j - mis, 4j - mis + 4)
+      const uint32_t nw = (mis + nbytes + 3) >> 2;
+      uint32_t* ga = reinterpret_cast<uint32_t*>(g - mis);
+      for (uint32_t j = threadIdx.x; j < nw; j += 256) {
+        const uint32_t b0 = 4 + 4 * j - mis;                            // shared byte position of the word's first byte (>= 1)
+        const uint32_t lo = so[b0 >> 2], hi = so[(b0 >> 2) + 1];
+        const uint32_t word = __funnelshift_r(lo, hi, 8 * (b0 & 3));
+        const int first = (int)(4 * j) - (int)mis, last = first + 3;    // tile byte indices covered by this word
+        if (first >= 0 && last < (int)nbytes) ga[j] = word;
+        else {
+#pragma unroll
+          for (int q = 0; q < 4; q++)
+            if (first + q >= 0 && first + q < (int)nbytes) (g - mis)[4 * j + q] = (uint8_t)(word >> (8 * q));
         }
       }
     }

@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kind", default=KIND, choices=["natural", "noise", "ramp"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--shape", default=f"{W}x{H}", help="frame size WxH; 3840x2160 is SURVEY.md 8d config 5 (use --batch 256)")
     ap.add_argument("--frames-per-wave", type=int, default=64)
     ap.add_argument("--lanes", type=int, default=2)
     ap.add_argument("--e2e-frames-per-wave", type=int, default=16, help="smaller waves keep the PCIe pipeline of the host path full")
@@ -129,6 +130,9 @@ def main():
     ap.add_argument("--cpu-frames-per-proc", type=int, default=12)
     a = ap.parse_args()
     globals()["KIND"] = a.kind
+    sw, sh = (int(v) for v in a.shape.lower().split("x"))
+    globals().update(W=sw, H=sh, FRAME_MPIX=sw * sh / 1e6, METRIC=f"Mpix/s JPEG encode ({sw}x{sh} 4:2:0 batch)",
+                     SLOT=SLOT if sw * sh <= 1920 * 1280 else 2 * 1024 * 1024)
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     ncores = len(os.sched_getaffinity(0))
@@ -136,7 +140,7 @@ def main():
                           f"cyclically shifted per frame; SURVEY.md 8d config 4), 4:2:0, per-image optimal Huffman tables, 3 scans",
               "frames_per_gpu": a.batch, "global_frames": a.batch * world, "width": W, "height": H,
               "parallelism": f"frames sharded over {world} GPU(s), no collective",
-              "l2": "inputs (7.5 GB per GPU) are far larger than L2; no explicit flush needed",
+              "l2": f"inputs ({a.batch * W * H * 3 / 1e9:.1f} GB per GPU) are far larger than L2; no explicit flush needed",
               "frames_per_wave": a.frames_per_wave, "lanes": a.lanes, "slot_bytes": SLOT}
 
     # ---------------- reference arm: CPU only, rank 0 only
@@ -190,7 +194,7 @@ def main():
     else:
         for i in range(n):
             d_in[i] = torch.from_numpy(fr.GENERATORS[a.kind](first + i, W, H)).to(dev)
-    slot = SLOT if a.kind != "noise" else 1024 * 1024
+    slot = SLOT if a.kind != "noise" else max(1024 * 1024, W * H)
     d_out = torch.zeros((n, slot), dtype=torch.uint8, device=dev)
     d_sizes = torch.zeros(n, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()

@@ -324,6 +324,28 @@ def test_subsample_ppm_file(api, frames, tmp_path, golden):
     assert sha(open(p, "rb").read()) == golden["comparator"]["640_A_vs_diffs"]["subA_ppm_sha256"]
 
 
+@pytest.mark.parametrize("mode", ["stages", "fused"])
+def test_board_tester_cli(frames, golden, tmp_path, mode):
+    """tools/board_tester (plain C against the seven reference entry points, app_main's call order, main.c:119-165) on the
+    seed/diffs pair: region list, per-region JPEG files and the rotated stored.ppm must equal the reference's."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "board_tester")
+    assert os.path.exists(exe), "tools/board_tester is built by __graft_entry__.build()"
+    g = golden["comparator"]["640_A_vs_diffs"]
+    a, b, out = str(tmp_path / "A.ppm"), str(tmp_path / "B.ppm"), str(tmp_path / "out")
+    frames.write_ppm(a, frames.sample_rgb("640"))
+    frames.write_ppm(b, frames.sample_rgb("640_diffs"))
+    cmd = [exe] + (["--fused"] if mode == "fused" else []) + [out, a, b]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    want = "frame 1: %d regions" % g["n"] + "".join(" {%d,%d,%d,%d}->%d" % (*reg, j["bytes"]) for reg, j in zip(g["regions"], g["jpgs"]))
+    assert r.stdout.strip() == want
+    for i, j in enumerate(g["jpgs"]):
+        assert sha(open(os.path.join(out, "frame1-jpg-%d" % i), "rb").read()) == j["sha256"], i
+    assert sha(open(os.path.join(out, "stored.ppm"), "rb").read()) == g["subB_ppm_sha256"]
+    assert not os.path.exists(os.path.join(out, "sub.ppm"))
+
+
 def test_comparator_micro_cases(api, golden):
     for nm, case in golden["comparator"]["micro_128"].items():
         if nm == "dark_on_bright":

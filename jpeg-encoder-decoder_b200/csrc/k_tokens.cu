@@ -107,7 +107,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
   for (int pr = 0; pr < 4; pr++) {
     uint32_t cbs[4] = {0, 0, 0, 0}, crs[4] = {0, 0, 0, 0};
     uint32_t scr_y = 0xFFFFFFFFu, scr_c = 0xFFFFFFFFu;
-    if (live) {
+    {                                    // lanes past the end of the crop convert stale bytes into their own, unused slots
       uint32_t* ydst = &sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4];
 #pragma unroll 1
       for (int dr = 0; dr < 2; dr++) {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           uint4 v[4];
 #pragma unroll
           for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const uint4*>(&sm.smp[slot * 16 + ((k ^ (slot >> 1)) & 3) * 4]);
-          badrows = block_fast_regs(v, comp, magic, out, &mask, &dcq);
+          badrows = block_fast_regs(v, (TK_ABLATE & 8) ? 0 : comp, magic, out, &mask, &dcq);   // ablation 8: code-size experiment (wrong chroma)
         }
         if (!ok) { badrows = 0; mask = 0; }          // lanes past the end of the crop transformed stale samples
         // the zig-zagged block goes to the lane's private row: the token walk indexes it, the exact replay patches it

@@ -52,7 +52,14 @@ def aan(d):
     o[1], o[7] = add(z11, z4), add(z11, z4, -1)
     return o
 
-def main():
+QUANT = {
+    "luma": [16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
+             18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99],
+    "chroma": [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99] + [99] * 32}
+
+
+def position_bounds(verbose=False):
+    """{comp: 8x8 array B[v][u]}: worst-case |d*K - v_true| of every coefficient, in units of the quantised value."""
     # 2-D: rows first (index [y][x] -> pass over x), then columns
     X = [[Node(np.eye(64)[y * 8 + x]) for x in range(8)] for y in range(8)]
     R = [aan(X[y]) for y in range(8)]                       # R[y][u]
@@ -60,33 +67,32 @@ def main():
     # true unnormalised 2-D DCT linear forms (reference convention): F[v][u] = sum_y sum_x p[y][x] cos((2y+1)v pi/16) cos((2x+1)u pi/16)
     n = np.arange(8)
     Ct = np.cos((2 * n[:, None] + 1) * n[None, :] * np.pi / 16)   # Ct[t][f]
-    quant = {
-        "luma": [16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57, 69, 56, 14, 17, 22, 29, 51, 87, 80, 62,
-                 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64, 81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99],
-        "chroma": [17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99, 99, 99, 47, 66, 99, 99, 99, 99, 99, 99] + [99] * 32}
-    # AAN output scale: out_k = X_k / r_k  (r_0 = 1, r_k = 2*cos(k pi/16)*... determined numerically from the exact-constant algorithm)
-    worst = {}
-    for comp, q in quant.items():
-        w = 0.0
+    out = {}
+    for comp, q in QUANT.items():
+        B = np.zeros((8, 8))
         for v in range(8):
             for u in range(8):
                 node = Cc[u][v]
                 true = np.outer(Ct[:, v], Ct[:, u]).reshape(64)        # [y*8+x]
-                # scale s.t. node.lin ~= true / r ; least squares
-                r = float(true @ true) / float(node.lin @ true)
+                r = float(true @ true) / float(node.lin @ true)        # AAN output scale: node.lin ~= true / r
                 cu = (0.5 ** 0.5 if u == 0 else 1.0) * (0.5 ** 0.5 if v == 0 else 1.0)
-                K = f32(r * cu / (4.0 * q[v * 8 + u]))                  # the FP32 multiplier the kernel uses
-                Ktrue = r * cu / (4.0 * q[v * 8 + u])
+                K = f32(r * cu / (4.0 * q[v * 8 + u]))                  # the FP32 multiplier the kernel brackets around
                 sys_err = 128.0 * np.abs(node.lin * K - true * cu / (4.0 * q[v * 8 + u])).sum()   # constants' rounding + K rounding
                 rnd_err = node.err * K
-                final_rounding = U * (node.mag() * K + 2 ** 11)        # the quantising FFMA rounds at <= ulp of the magic range
-                tot = sys_err + rnd_err
-                w = max(w, tot)
-                if (u, v) in ((0, 0), (1, 0), (0, 1), (1, 1), (7, 7), (4, 4)):
+                B[v, u] = sys_err + rnd_err
+                if verbose and (u, v) in ((0, 0), (1, 0), (0, 1), (1, 1), (7, 7), (4, 4)):
                     print(f"{comp} (u={u},v={v}) q={q[v*8+u]:3d} r={r:.6f} max|v~|={node.mag()*K:8.2f} sys={sys_err:.2e} rnd={rnd_err:.2e}")
-        worst[comp] = w
-        print(comp, "worst-case |v~ - v_true| =", w)
-    print("bound:", max(worst.values()))
+        out[comp] = B
+    return out
+
+
+def main():
+    B = position_bounds(verbose=True)
+    np.set_printoptions(linewidth=200, precision=2)
+    for comp, b in B.items():
+        print(comp, "worst-case |v~ - v_true| =", b.max(), "; per position (x 1e-5, rows = vertical frequency):")
+        print(b * 1e5)
+    print("bound:", max(b.max() for b in B.values()))
 
 if __name__ == "__main__":
     main()

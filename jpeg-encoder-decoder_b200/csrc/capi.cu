@@ -67,7 +67,7 @@ struct WaveDims {
 struct Lane {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr, sizes_ready = nullptr;
-  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base;
+  DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base, fixtok;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
@@ -95,6 +95,7 @@ struct Lane {
       if ((e = tok2.ensure(d.toks * sizeof(uint32_t))) != cudaSuccess) return e;
       if ((e = tchunk_bits.ensure(d.tchunks * sizeof(uint32_t))) != cudaSuccess) return e;
       if ((e = tchunk_base.ensure(d.tchunks * sizeof(uint32_t))) != cudaSuccess) return e;
+      if ((e = fixtok.ensure(d.blocks * sizeof(uint4))) != cudaSuccess) return e;
       tchunk_bytes = d.tchunks * sizeof(uint32_t);
     }
     if ((e = huff.ensure(d.njobs * 4 * sizeof(JbHuff))) != cudaSuccess) return e;
@@ -123,10 +124,11 @@ struct Lane {
     ws.tok2 = (uint32_t*)tok2.p;
     ws.tchunk_bits = (uint32_t*)tchunk_bits.p;
     ws.tchunk_base = (uint32_t*)tchunk_base.p;
+    ws.fixtok_list = (uint4*)fixtok.p;
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &tok2, &tchunk_bits, &tchunk_base, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &tok2, &tchunk_bits, &tchunk_base, &fixtok, &in, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -250,6 +252,7 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
     { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, st); }
+    { StageTimer t(c, st, ST_FIX); jb_launch_fix_tokens(ws, st); }
     CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
     { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }
     { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }

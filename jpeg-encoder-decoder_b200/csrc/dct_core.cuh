@@ -131,33 +131,6 @@ __device__ __forceinline__ uint4 block_dct(const uint32_t (&px)[8], int comp, co
   return out;
 }
 
-// Literal chain of encoder.c:87-108 for the 8 coefficients of natural row v (vertical frequency v) of one block, by 8
-// lanes: lane i owns sample column i in the first pass (col8: byte t = sample of row t) and horizontal frequency u = i in
-// the second.  x*1.0 and 0.0+x are exact, so the unspecialised loops reproduce the reference bit for bit.  Returns the
-// quantised coefficient of natural index 8v+i.  All 32 lanes must call (shuffles inside groups of 8).
-__device__ __noinline__ int exact_row_coef(uint2 col8, int comp, int v, int lane) {
-  const int i = lane & 7;
-  double inner = 0.0;
-#pragma unroll
-  for (int t = 0; t < 8; t++) {
-    const double p = sample_to_double(((t < 4 ? col8.x : col8.y) >> (8 * (t & 3))) & 0xFFu);
-    const double pr = __dmul_rn(p, c_cos[t * 8 + v]);
-    inner = t == 0 ? pr : __dadd_rn(inner, pr);
-  }
-  double f = 0.0;
-#pragma unroll
-  for (int x = 0; x < 8; x++) {
-    const double in_x = __shfl_sync(0xFFFFFFFFu, inner, x, 8);
-    const double pr = __dmul_rn(in_x, g_cos[x * 8 + i]);
-    f = x == 0 ? pr : __dadd_rn(f, pr);
-  }
-  if (i == 0) f = __dmul_rn(f, JB_INV_SQRT2);           // encoder.c:104 (x_f == 0)
-  if (v == 0) f = __dmul_rn(f, JB_INV_SQRT2);           // encoder.c:105 (y_f == 0)
-  const double q = (double)g_quant[comp][v * 8 + i];
-  const int n = (int)(short)__double2int_rz(__ddiv_rn(__dmul_rn(f, 0.25), q));       // encoder.c:106-108
-  return min(max(n, -2048), 2047);                                                    // encoder.c:109
-}
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");

@@ -85,6 +85,9 @@ __device__ __forceinline__ uint32_t jb_token(int v, int cat, int idx, int zrl) {
 // The bit packer works on *token chunks*: JB_TCHUNK consecutive tokens of one scan, after k_compact_tokens has copied the
 // runs' tokens into scan order (ws.tok2).  Each scan's region of tok2 starts on a chunk boundary.
 #define JB_TCHUNK 256
+// A void token: table index 511 has no code (the packers' tables are zero there), no magnitude bits: it occupies a slot
+// and contributes nothing.  k_pixels_to_tokens reserves slots with it for blocks whose tokens k_fix_tokens writes.
+#define JB_TOKEN_VOID (511u << 15)
 // runs of one chroma plane that lie in MCU rows < my (mw = MCUs per row); luma has twice as many (two block rows per MCU row)
 __host__ __device__ inline uint32_t jb_runs_before(uint32_t mw, uint32_t my) {
   // every `period` = 16 / gcd(mw, 16) MCU rows a row starts on a tile boundary; period = 1 << sh
@@ -118,6 +121,7 @@ struct JbWs {
   uint32_t* tok2;       // token path: tokens in scan order
   uint32_t* tchunk_bits;  // token path: per token chunk, entropy-coded bits (zeroed per wave, accumulated by k_compact_tokens)
   uint32_t* tchunk_base;  // token path: per token chunk, bit offset inside its scan
+  uint4* fixtok_list;   // token path: (job, block id inside the job, index of its first token, reserved tokens) of undecided blocks
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -146,6 +150,7 @@ __host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
 void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st);
+void jb_launch_fix_tokens(const JbWs& ws, cudaStream_t st);
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st);
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st);
 void jb_launch_build_huffman(const JbWs& ws, int njobs, bool wide_keys, cudaStream_t st);

@@ -390,6 +390,35 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int
   }
 }
 
+// The lane's column (i = lane & 7) of the 8x8 samples of block `blk` of a job, recomputed from the pixels with the exact
+// colour path (encoder.c:129-138); returns the component (0 luma, 1 chroma).
+__device__ __forceinline__ int fix_block_samples(const JbJob& job, uint32_t blk, int i, uint32_t (&px)[8]) {
+  const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
+  const int comp = blk < nby ? 0 : 1;
+  if (comp == 0) {
+    const uint32_t bw = job.w / 8, by = blk / bw, bx = blk - by * bw;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      const uint8_t* p = job.src + (size_t)(job.y + by * 8 + t) * job.pitch + 3u * (uint32_t)(job.x + bx * 8 + i);
+      px[t] = ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) & 0xFF;
+    }
+  } else {
+    const int ch = blk < nby + nbc ? 0 : 1;
+    const uint32_t cblk = blk - nby - (ch ? nbc : 0), bw = job.w / 16, by = cblk / bw, bx = cblk - by * bw;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint8_t* p = job.src + (size_t)(job.y + (by * 8 + t) * 2 + (q >> 1)) * job.pitch + 3u * (uint32_t)(job.x + (bx * 8 + i) * 2 + (q & 1));
+        s += (ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) >> (ch ? 16 : 8)) & 0xFF;
+      }
+      px[t] = s >> 2;
+    }
+  }
+  return comp;
+}
+
 // Recompute the listed blocks with the literal reference arithmetic; 8 lanes per block, 4 blocks per warp.
 __global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
   __shared__ double tr[4][4 * TR_STRIDE];
@@ -408,31 +437,9 @@ __global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
     const bool live = base + b < count;
     const uint2 e = ws.fix_list[live ? base + b : base];
     const JbJob job = ws.jobs[e.x];
-    const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
     const uint32_t blk = e.y;
-    const int comp = blk < nby ? 0 : 1;
     uint32_t px[8];
-    if (comp == 0) {
-      const uint32_t bw = job.w / 8, by = blk / bw, bx = blk - by * bw;
-#pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const uint8_t* p = job.src + (size_t)(job.y + by * 8 + t) * job.pitch + 3u * (uint32_t)(job.x + bx * 8 + i);
-        px[t] = ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) & 0xFF;
-      }
-    } else {
-      const int ch = blk < nby + nbc ? 0 : 1;
-      const uint32_t cblk = blk - nby - (ch ? nbc : 0), bw = job.w / 16, by = cblk / bw, bx = cblk - by * bw;
-#pragma unroll
-      for (int t = 0; t < 8; t++) {
-        uint32_t s = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const uint8_t* p = job.src + (size_t)(job.y + (by * 8 + t) * 2 + (q >> 1)) * job.pitch + 3u * (uint32_t)(job.x + (bx * 8 + i) * 2 + (q & 1));
-          s += (ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) >> (ch ? 16 : 8)) & 0xFF;
-        }
-        px[t] = s >> 2;
-      }
-    }
+    const int comp = fix_block_samples(job, blk, i, px);
     uint64_t mask;
     const uint4 out = block_dct(px, comp, rqs[comp][i], izzrow, tr[warp], zz[warp], lane, &mask);
     if (live) {
@@ -442,6 +449,52 @@ __global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
         ws.dcraw[job.blk_off + blk] = (int16_t)(out.x & 0xFFFF);
       }
     }
+  }
+}
+
+// Token path: the blocks k_pixels_to_tokens could not decide.  It reserved their token slots (DC written, the rest void);
+// here the literal chain gives the block, one lane writes its AC tokens and EOB over the void slots and adds the symbols
+// to the job's histograms.  8 lanes per block, 4 blocks per warp.
+__global__ void __launch_bounds__(128) k_fix_tokens(JbWs ws) {
+  __shared__ double tr[4][4 * TR_STRIDE];
+  __shared__ int16_t zz[4][4 * 64];
+  __shared__ double rqs[2][8][10];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const int comp = tid >> 6, r = (tid >> 3) & 7, u = tid & 7;
+    rqs[comp][r][u] = __dmul_rn(__drcp_rn((double)c_quant[comp][r * 8 + u]), 0x1.00000004p-2);
+  }
+  __syncthreads();
+  const uint32_t count = *ws.fix_count;
+  const int b = lane >> 3, i = lane & 7;
+  const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
+  for (uint32_t base = (blockIdx.x * 4 + warp) * 4; base < count; base += gridDim.x * 16) {
+    const bool live = base + b < count;
+    const uint4 e = ws.fixtok_list[live ? base + b : base];          // job, block id inside the job, first token, reserved tokens
+    const JbJob job = ws.jobs[e.x];
+    uint32_t px[8];
+    const int comp = fix_block_samples(job, e.y, i, px);
+    uint64_t mask;
+    block_dct(px, comp, rqs[comp][i], izzrow, tr[warp], zz[warp], lane, &mask);
+    if (live && i == 0) {
+      const int16_t* blk = zz[warp] + b * 64;
+      int* hist_ac = ws.hist + (size_t)e.x * 4 * 257 + (comp ? 3 * 257 : 257);
+      uint32_t* out = ws.tok + e.z + 1;                                // slot 0 holds the DC token
+      int prev1 = 1;
+      for (uint64_t m = mask; m; m &= m - 1) {
+        const int p = __ffsll((long long)m) - 1;
+        const int v = blk[p];
+        const int run = p - prev1;
+        prev1 = p + 1;
+        const int cat = 32 - __clz(abs(v));
+        const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
+        atomicAdd(&hist_ac[sym], 1);
+        if (zrl) atomicAdd(&hist_ac[0xF0], zrl);
+        *out++ = jb_token(v, cat, sym, zrl);
+      }
+      if (!(mask >> 63)) { atomicAdd(&hist_ac[0], 1); *out++ = 0; }   // EOB
+    }
+    __syncwarp();
   }
 }
 
@@ -472,6 +525,7 @@ void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool ro
 }
 
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148 * 3, 128, 0, st>>>(ws); }
+void jb_launch_fix_tokens(const JbWs& ws, cudaStream_t st) { k_fix_tokens<<<148 * 3, 128, 0, st>>>(ws); }
 
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st) {
   uint32_t threads = max_blocks * 8;

@@ -38,12 +38,13 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t* total) 
 // run r of the job -> scan (0 Y, 1 Cb, 2 Cr); scans 1 and 2 share the chroma tables
 __device__ __forceinline__ int run_scan(uint32_t r, uint32_t nrc) { return r < 2u * nrc ? 0 : (r < 3u * nrc ? 1 : 2); }
 
-// enc[t][i]: code << 5 | length of table index i (0..255 AC symbols, 256..271 DC categories) of table set t (0 luma, 1 chroma)
-__device__ __forceinline__ void load_enc(const JbWs& ws, uint32_t job, uint32_t (*enc)[272]) {
+// enc[t][i]: code << 5 | length of table index i (0..255 AC symbols, 256..271 DC categories, 0 above: void tokens) of table
+// set t (0 luma, 1 chroma)
+__device__ __forceinline__ void load_enc(const JbWs& ws, uint32_t job, uint32_t (*enc)[512]) {
   const uint32_t* g = ws.enc + (size_t)job * 4 * 256;
-  for (int k = threadIdx.x; k < 2 * 272; k += blockDim.x) {
-    const int t = k / 272, i = k - t * 272;
-    enc[t][i] = i < 256 ? g[(2 * t + 1) * 256 + i] : g[(2 * t) * 256 + (i - 256)];
+  for (int k = threadIdx.x; k < 2 * 512; k += blockDim.x) {
+    const int t = k >> 9, i = k & 511;
+    enc[t][i] = i < 256 ? g[(2 * t + 1) * 256 + i] : (i < 272 ? g[(2 * t) * 256 + (i - 256)] : 0u);
   }
 }
 
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(256) k_runs_prepare(JbWs ws) {
 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
-  __shared__ uint32_t enc[2][272];
+  __shared__ uint32_t enc[2][512];
   const JbJob job = ws.jobs[blockIdx.y];
   const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
   load_enc(ws, blockIdx.y, enc);
@@ -192,7 +193,7 @@ __device__ __forceinline__ void or_bits_s(uint32_t* img, uint32_t pos, uint32_t 
 }
 
 __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
-  __shared__ uint32_t enc[2][272];
+  __shared__ uint32_t enc[2][512];
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;

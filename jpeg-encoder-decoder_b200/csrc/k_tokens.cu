@@ -53,6 +53,8 @@ struct __align__(128) TkSmem {
   uint32_t pad[2];
   uint8_t ties[128];                    // patches (row pair * 32 + lane) of the 8 staged rows with a pixel on an integer boundary
 };
+// zig-zag positions (1..63) of the coefficients of natural row v (vertical frequency v)
+__constant__ unsigned long long c_rowzz[8] = {0x000000001800c062ull, 0x0000040024012094ull, 0x00000a0042021108ull, 0x0020110081040a00ull, 0x0050208100880400ull, 0x1088404200500000ull, 0x2904802400200000ull, 0xc603001800000000ull};
 constexpr int TK_TIE_COOP_MAX = 48;     // longer tie lists (grey images) are replayed one patch per lane instead of 16 lanes per patch
 
 struct TkTile {
@@ -286,47 +288,27 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           badrows = block_fast_regs(v, (TK_ABLATE & 8) ? 0 : comp, magic, out, &mask, &dcq);   // ablation 8: code-size experiment (wrong chroma)
         }
         if (!ok) { badrows = 0; mask = 0; }          // lanes past the end of the crop transformed stale samples
-        // the zig-zagged block goes to the lane's private row: the token walk indexes it, the exact replay patches it
+        if (TK_ABLATE & 4) badrows = 0;
+        // the zig-zagged block goes to the lane's private row, where the token walk indexes it
         uint32_t* cb = sm.cbuf + lane * 33;
 #pragma unroll
         for (int j = 0; j < 32; j++) cb[j] = out[j];
-        // ---- exact replay of the natural rows that hold an undecided coefficient (8 lanes per row, 4 copies in step) -----
-        uint32_t badm = (TK_ABLATE & 4) ? 0u : __ballot_sync(FULL, badrows != 0);
-        if (badm) __syncwarp();
-        while (badm) {
-          const int L = __ffs(badm) - 1;
-          badm &= badm - 1;
-          uint32_t rows = __shfl_sync(FULL, badrows, L);
-          const int s = role * 32 + L, i = lane & 7;
-          uint32_t colb[8];
-          const uint8_t* sb = reinterpret_cast<const uint8_t*>(sm.smp);
-#pragma unroll
-          for (int tt = 0; tt < 8; tt++) colb[tt] = sb[(s * 16 + (((tt >> 1) ^ (s >> 1)) & 3) * 4 + (tt & 1) * 2) * 4 + i];
-          const uint2 col8 = make_uint2(colb[0] | (colb[1] << 8) | (colb[2] << 16) | (colb[3] << 24), colb[4] | (colb[5] << 8) | (colb[6] << 16) | (colb[7] << 24));
-          while (rows) {
-            const int v = __ffs(rows) - 1;
-            rows &= rows - 1;
-            const int n = exact_row_coef(col8, comp, v, lane);
-            const int pos = g_izz[v * 8 + i];
-            // position 0 (DC) already went through the literal chain inside block_fast
-            if (lane < 8 && pos) reinterpret_cast<int16_t*>(sm.cbuf + L * 33)[pos] = (int16_t)n;
-            const uint64_t bit = pos ? 1ull << pos : 0ull, set = n ? bit : 0ull;
-            uint32_t b0 = (uint32_t)bit, b1 = (uint32_t)(bit >> 32), s0 = (uint32_t)set, s1 = (uint32_t)(set >> 32);
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1) {
-              b0 |= __shfl_xor_sync(FULL, b0, o); b1 |= __shfl_xor_sync(FULL, b1, o);
-              s0 |= __shfl_xor_sync(FULL, s0, o); s1 |= __shfl_xor_sync(FULL, s1, o);
-            }
-            if (lane == L) mask = (mask & ~(((uint64_t)b1 << 32) | b0)) | (((uint64_t)s1 << 32) | s0);
-          }
-          __syncwarp();
-        }
       }
 
       phase_sync(3);
       if (active && !(TK_ABLATE & 1)) {
         // ---- runs, token offsets --------------------------------------------------------------------------------------
-        const uint32_t cnt = ok ? 2u + (uint32_t)__popcll(mask) - (uint32_t)(mask >> 63) : 0u;
+        // A block with an undecided coefficient (0.5 % of photographic blocks) is deferred: its DC token is written here, its
+        // other tokens by k_fix_tokens after the literal chain; it reserves one slot for every coefficient that may turn out
+        // non-zero (its decided non-zeros and the whole natural rows that hold an undecided one) and one for the EOB.
+        const bool defer = badrows != 0;
+        uint32_t cnt = ok ? 2u + (uint32_t)__popcll(mask) - (uint32_t)(mask >> 63) : 0u;
+        if (defer) {
+          uint64_t rm = mask;
+          for (uint32_t rws = badrows; rws; rws &= rws - 1) rm |= c_rowzz[__ffs(rws) - 1];
+          cnt = 2u + (uint32_t)__popcll(rm);
+          mask = 0;                                  // nothing to walk
+        }
         uint32_t inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -380,11 +362,15 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
         uint32_t* hist_dc = sm.hist + comp * 272;
         uint32_t* hist_ac = hist_dc + 16;
         const uint32_t ac = (uint32_t)__popcll(mask);
-        const uint32_t lt = (1u << lane) - 1u;
-        const uint32_t b63 = __ballot_sync(FULL, (mask >> 63) != 0);
-        const uint32_t acex = excl - 2u * (uint32_t)__popc(okb & lt) + (uint32_t)__popc(b63 & lt);
-        const uint32_t total_ac = total - 2u * (uint32_t)__popc(okb) + (uint32_t)__popc(b63);
+        uint32_t acinc = ac;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t n = __shfl_up_sync(FULL, acinc, o);
+          if (lane >= o) acinc += n;
+        }
+        const uint32_t acex = acinc - ac, total_ac = __shfl_sync(FULL, acinc, 31);
         const uint32_t ne = __ballot_sync(FULL, ac != 0);
+        const uint32_t noeob = __ballot_sync(FULL, !ok || defer || (mask >> 63) != 0);
         const int diff = dcq - prev_dc;
         __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
         s_mask[lane] = make_uint2(__brev((uint32_t)mask), __brev((uint32_t)(mask >> 32)));
@@ -400,12 +386,10 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
             atomicAdd(&hist_dc[cat], 1u);
           }
           dst[excl] = tok;
-          if (!(mask >> 63)) dst[excl + 1 + ac] = 0;                           // EOB: table index 0, no magnitude bits
+          if (defer) for (uint32_t j = 1; j < cnt; j++) dst[excl + j] = JB_TOKEN_VOID;
+          else if (!(mask >> 63)) dst[excl + 1 + ac] = 0;                      // EOB: table index 0, no magnitude bits
         }
-        {
-          const uint32_t eb = okb & ~b63;
-          if (lane == 0 && eb) atomicAdd(&hist_ac[0], (uint32_t)__popc(eb));
-        }
+        if (lane == 0 && ~noeob) atomicAdd(&hist_ac[0], (uint32_t)__popc(~noeob));
         __syncwarp();
         const uint32_t T = (total_ac + 31) >> 5;
         uint32_t g = min(lane * T, total_ac);
@@ -464,6 +448,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           for (uint32_t k = lane; k < total; k += 32) gdst[k] = stage[k];
         }
         if (run_rid != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(&ws.runs[job.run_off + run_rid]) = make_uint4(round_tok + excl, run_ntok, run_dc, 0u);
+        if (defer) ws.fixtok_list[atomicAdd(ws.fix_count, 1u)] = make_uint4((uint32_t)p.job, blk, round_tok + excl, cnt);
         __syncwarp();
       }
     }

@@ -525,7 +525,7 @@ void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool ro
 }
 
 void jb_launch_fix_blocks(const JbWs& ws, cudaStream_t st) { k_fix_blocks<<<148 * 3, 128, 0, st>>>(ws); }
-void jb_launch_fix_tokens(const JbWs& ws, cudaStream_t st) { k_fix_tokens<<<148 * 3, 128, 0, st>>>(ws); }
+void jb_launch_fix_tokens(const JbWs& ws, cudaStream_t st) { k_fix_tokens<<<148 * 8, 128, 0, st>>>(ws); }
 
 void jb_launch_plane_masks(const JbWs& ws, int njobs, uint32_t max_blocks, cudaStream_t st) {
   uint32_t threads = max_blocks * 8;

@@ -480,6 +480,10 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   }
   const int mcus = (max_w / 16) * (max_h / 16), tiles_per_job = (mcus + JB_TILE_MCUS - 1) / JB_TILE_MCUS, ntiles = tiles_per_job * njobs;
   const int want = (ntiles + TK_WARPS - 1) / TK_WARPS;
-  const int grid = want < sms * ctas_per_sm[v] ? want : sms * ctas_per_sm[v];
+  static int spare = -1;                 // CTAs left out of the persistent grid (development knob: JPEGB200_TK_SPARE)
+  if (spare < 0) { const char* e = getenv("JPEGB200_TK_SPARE"); spare = e ? atoi(e) : 0; }
+  int cap = sms * ctas_per_sm[v] - spare;
+  if (cap < 1) cap = 1;
+  const int grid = want < cap ? want : cap;
   kern<<<grid, TK_WARPS * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
 }

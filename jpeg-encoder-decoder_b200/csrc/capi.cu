@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -65,8 +66,10 @@ struct WaveDims {
 };
 
 struct Lane {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr, sizes_ready = nullptr;
+  cudaStream_t stream = nullptr;      // the lane's ordering stream: copies, k_pixels_to_tokens, everything of the plane path
+  cudaStream_t stream_hi = nullptr;   // token path: the kernels after k_pixels_to_tokens run here at high priority, so that they
+                                      // get the SM slots the other lanes' k_pixels_to_tokens CTAs free as they retire
+  cudaEvent_t done = nullptr, sizes_ready = nullptr, pass1_done = nullptr, pass2_done = nullptr;
   DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base, fixtok;
   DevBuf in, out, sizes;      // host-path staging on the device
   PinBuf h_jobs, h_sizes;
@@ -134,6 +137,9 @@ struct Lane {
     h_sizes.release();
     if (done) cudaEventDestroy(done);
     if (sizes_ready) cudaEventDestroy(sizes_ready);
+    if (pass1_done) cudaEventDestroy(pass1_done);
+    if (pass2_done) cudaEventDestroy(pass2_done);
+    if (stream_hi) cudaStreamDestroy(stream_hi);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -189,6 +195,8 @@ struct jpegb200_ctx {
   int device = 0;
   int frames_per_wave = 8;
   int exact_dct = 0;          // 1 = literal FP64 chain for every block (the on-device checker of the fast path)
+  int overlap_waves = 0;      // set by the batched entry points when several waves will be in flight on different lanes
+  int split_streams = 1;      // token path: run the kernels after k_pixels_to_tokens on the lane's high-priority stream
   int token_path = 1;         // batched entry points: 1 = k_pixels_to_tokens + k_pack_runs, 0 = coefficient planes (k_dct.cu + chunk kernels)
   std::vector<Lane> lanes;
   cudaEvent_t fork = nullptr;
@@ -212,8 +220,13 @@ int make_lanes(jpegb200_ctx* c, int n) {
   for (auto& l : c->lanes) l.release();
   c->lanes.clear();
   c->lanes.resize(n);
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
   for (auto& l : c->lanes) {
-    CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&l.stream_hi, cudaStreamNonBlocking, prio_hi));
+    CK(cudaEventCreateWithFlags(&l.pass1_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.pass2_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.sizes_ready, cudaEventDisableTiming));
   }
@@ -251,7 +264,13 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
-    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, st); }
+    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, c->overlap_waves ? 4 : 0, st); }
+    cudaStream_t lo = st;
+    if (c->split_streams && c->overlap_waves) {   // the rest of the chain at high priority; the lane's stream rejoins at the end
+      CK(cudaEventRecord(l.pass1_done, lo));
+      CK(cudaStreamWaitEvent(l.stream_hi, l.pass1_done, 0));
+      st = l.stream_hi;
+    }
     { StageTimer t(c, st, ST_FIX); jb_launch_fix_tokens(ws, st); }
     CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
     { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }
@@ -264,6 +283,10 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, st); }
     { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
     { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, tail_ctas, st); }
+    if (c->split_streams && c->overlap_waves) {
+      CK(cudaEventRecord(l.pass2_done, st));
+      CK(cudaStreamWaitEvent(lo, l.pass2_done, 0));
+    }
     CK(cudaGetLastError());
     return 0;
   }
@@ -362,6 +385,7 @@ int jpegb200_create(jpegb200_ctx** out, int device) {
   if (prop.major != 10) return fail("device %d is sm_%d%d; libjpegb200 is built for sm_100a only", device, prop.major, prop.minor);
   jpegb200_ctx* c = new jpegb200_ctx();
   c->device = device;
+  if (const char* e = getenv("JPEGB200_SPLIT_STREAMS")) c->split_streams = atoi(e) != 0;
   if (make_lanes(c, 3) != 0) { delete c; return -1; }
   if (cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return fail("cudaEventCreate failed"); }
   *out = c;
@@ -467,6 +491,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   const int nwaves = (n + G - 1) / G;
   const int nl = std::min<int>((int)c->lanes.size(), nwaves);
   for (int i = 0; i < nl; i++) CK(c->lanes[i].ensure(wd));
+  c->overlap_waves = nl >= 2;
   CK(cudaEventRecord(c->fork, user));
   for (int i = 0; i < nl; i++) CK(cudaStreamWaitEvent(c->lanes[i].stream, c->fork, 0));
   for (int k = 0; k < nwaves; k++) {
@@ -512,6 +537,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     CK(l.h_sizes.ensure(g * sizeof(uint32_t)));
     l.pending_first = -1;
   }
+  c->overlap_waves = nl >= 2;
   // Retire the wave in flight on a lane: wait for its sizes, then fetch exactly the bytes produced.
   auto retire = [&](Lane& l) -> int {
     if (l.pending_first < 0) return 0;
@@ -551,6 +577,7 @@ int jpegb200_encode_regions(jpegb200_ctx* c, const uint8_t* d_frame, int frame_w
   CK(cudaSetDevice(c->device));
   cudaStream_t user = (cudaStream_t)stream;
   Lane& l = c->lanes[0];
+  c->overlap_waves = 0;
   std::vector<JbJob> jobs(nareas);
   std::vector<size_t> slots(nareas, slot);
   for (int i = 0; i < nareas; i++) {

@@ -162,7 +162,7 @@ void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 
 // token path (k_tokens.cu, k_pack_runs.cu)
-void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st);
 void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
 void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st);

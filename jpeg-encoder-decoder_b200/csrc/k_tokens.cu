@@ -463,7 +463,9 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
 
 }  // namespace
 
-void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st) {
+// tiles_per_warp = 0: persistent grid (one CTA per SM slot, each warp walks its share of the wave); n > 0: short-lived CTAs of
+// n tiles per warp, so that the high-priority kernels of other lanes get SM slots as CTAs retire (multi-lane batches).
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st) {
   static int ctas_per_sm[2] = {0, 0}, sms = 0;
   const int v = rows_aligned ? 1 : 0;
   auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
@@ -484,6 +486,10 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   if (spare < 0) { const char* e = getenv("JPEGB200_TK_SPARE"); spare = e ? atoi(e) : 0; }
   int cap = sms * ctas_per_sm[v] - spare;
   if (cap < 1) cap = 1;
+  static int iters_env = -2;             // development override: JPEGB200_TK_ITERS
+  if (iters_env == -2) { const char* e = getenv("JPEGB200_TK_ITERS"); iters_env = e ? atoi(e) : -1; }
+  const int iters = iters_env >= 0 ? iters_env : tiles_per_warp;
+  if (iters > 0) cap = (ntiles + TK_WARPS * iters - 1) / (TK_WARPS * iters);
   const int grid = want < cap ? want : cap;
   kern<<<grid, TK_WARPS * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
 }

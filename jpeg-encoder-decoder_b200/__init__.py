@@ -223,7 +223,7 @@ class Encoder:
         if self.lib.jpegb200_create(C.byref(self.ctx), device) != 0:
             raise JpegB200Error(self.lib.jpegb200_last_error().decode())
         if frames_per_wave is not None or lanes is not None:
-            self.configure(frames_per_wave or 8, lanes or 3)
+            self.configure(frames_per_wave or 32, lanes or 3)
 
     def _check(self, rc):
         if rc < 0:

@@ -193,7 +193,7 @@ __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t fram
 
 struct jpegb200_ctx {
   int device = 0;
-  int frames_per_wave = 8;
+  int frames_per_wave = 32;
   int exact_dct = 0;          // 1 = literal FP64 chain for every block (the on-device checker of the fast path)
   int overlap_waves = 0;      // set by the batched entry points when several waves will be in flight on different lanes
   int split_streams = 1;      // token path: run the kernels after k_pixels_to_tokens on the lane's high-priority stream

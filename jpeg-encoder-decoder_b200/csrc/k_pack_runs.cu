@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
         const uint32_t k = k0 + 32 * j + lane;
         if (k < run.ntok) {
           const uint32_t t = t8[j];
-          tok2[d0 + k] = t;
-          const uint32_t len = (e[(t >> 15) & 0x1FF] & 31u) + ((t >> 11) & 15u) + (t >> 24) * zrl_len;
+          const uint32_t ent = e[(t >> 15) & 0x1FF], cat = (t >> 11) & 15u, z = t >> 24;
+          const uint32_t clen = (ent & 31u) + cat;                                  // <= 27 bits: code + magnitude bits
+          // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
+          tok2[d0 + k] = z ? (t << 5) | 31u : ((((ent >> 5) << cat) | (t & 0x7FFu)) << 5) | clen;
+          const uint32_t len = clen + z * zrl_len;
           if ((d0 + k) / JB_TCHUNK == ca) la += len; else lb += len;
         }
       }
@@ -193,16 +196,12 @@ __device__ __forceinline__ void or_bits_s(uint32_t* img, uint32_t pos, uint32_t 
 }
 
 __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
-  __shared__ uint32_t enc[2][512];
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
   if (st->error) return;
   uint32_t nchunk[3], total_chunks = 0;
   for (int s = 0; s < 3; s++) { nchunk[s] = (st->tok_total[s] + JB_TCHUNK - 1) / JB_TCHUNK; total_chunks += nchunk[s]; }
-  if (blockIdx.x * PR_WARPS >= total_chunks) return;           // the grid is sized for the worst case
-  load_enc(ws, blockIdx.y, enc);
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* stage = stage_all[warp];
   for (uint32_t f = blockIdx.x * PR_WARPS + warp; f < total_chunks; f += gridDim.x * PR_WARPS) {
@@ -210,8 +209,6 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
     const uint32_t c = f - (s == 0 ? 0u : s == 1 ? nchunk[0] : nchunk[0] + nchunk[1]);
     const uint32_t cg = st->tok_start[s] / JB_TCHUNK + c;                      // chunk id inside the job
     const uint32_t ntok = min((uint32_t)JB_TCHUNK, st->tok_total[s] - c * JB_TCHUNK);
-    const uint32_t* e = enc[s ? 1 : 0];
-    const uint32_t zrl_code = e[0xF0] >> 5, zrl_len = e[0xF0] & 31u;
     const uint32_t base_bits = ws.tchunk_base[job.tchunk_off + cg], total = ws.tchunk_bits[job.tchunk_off + cg];
     const uint32_t phase = base_bits & 31;
     uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the chunk's first bit
@@ -225,18 +222,25 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
       if (lane * PR_TOK + 4 < ntok) b = __ldg(tp + 1);
       t8[0] = a.x; t8[1] = a.y; t8[2] = a.z; t8[3] = a.w; t8[4] = b.x; t8[5] = b.y; t8[6] = b.z; t8[7] = b.w;
     }
-    uint32_t word[PR_TOK], len[PR_TOK], zr = 0, nbits = 0;
+    // resolved tokens (k_compact_tokens): code word << 5 | length; length 31 escapes to a raw token that carries ZRLs
+    const uint32_t* enc_ac = ws.enc + ((size_t)blockIdx.y * 4 + (s ? 3 : 1)) * 256;
+    uint32_t word[PR_TOK], len[PR_TOK], zr = 0, nbits = 0, zrl_code = 0, zrl_len = 0;
 #pragma unroll
     for (int j = 0; j < PR_TOK; j++) {
       const bool live = lane * PR_TOK + j < ntok;             // a partly filled vector carries stale tokens past the end
       const uint32_t t = live ? t8[j] : 0u;
-      const uint32_t ent = e[(t >> 15) & 0x1FF];
-      const uint32_t cat = (t >> 11) & 15u;
-      word[j] = ((ent >> 5) << cat) | (t & 0x7FFu);
-      len[j] = live ? (ent & 31u) + cat : 0u;
-      const uint32_t z = t >> 24;
-      zr |= z << (2 * j);
-      nbits += len[j] + z * zrl_len;
+      word[j] = t >> 5;
+      len[j] = t & 31u;
+      if (len[j] == 31u) {                                    // rare: decode the raw token with the table in global memory
+        const uint32_t raw = t >> 5, ent = __ldg(enc_ac + ((raw >> 15) & 0xFFu)), cat = (raw >> 11) & 15u, z = raw >> 24;
+        const uint32_t ez = __ldg(enc_ac + 0xF0);
+        zrl_code = ez >> 5; zrl_len = ez & 31u;
+        word[j] = ((ent >> 5) << cat) | (raw & 0x7FFu);
+        len[j] = (ent & 31u) + cat;
+        zr |= z << (2 * j);
+        nbits += z * zrl_len;
+      }
+      nbits += len[j];
     }
     uint32_t chunk_total;
     const uint32_t ex = warp_excl_scan(nbits, &chunk_total);

@@ -214,6 +214,11 @@ def main():
     sizes = d_sizes.cpu().numpy().astype(np.int64)
     assert (sizes > 0).all(), "an output did not fit its slot"
     jpeg_bytes = int(sizes.sum())
+    # bookkeeping only (outside every timed region): the global (rank, offset, size) table a caller needs to find frame f's
+    # stream in rank r's output; the data path itself has no collective
+    shard = importlib.import_module("jpeg-encoder-decoder_b200.sharding")
+    table = shard.gather_tables(sizes, n * world, rank, world, device=dev)
+    assert table.shape == (n * world, 3) and int(table[first:first + n, 2].sum()) == jpeg_bytes
 
     # ---- device-resident timing: EXACTLY K steps between two events on the launching stream
     enc.lib.jpegb200_set_timing.argtypes = [ctypes.c_void_p, ctypes.c_int]

@@ -417,24 +417,32 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
             else { const int pz = __clz(rhi); rhi &= ~(0x80000000u >> pz); prev1 = pz + 33; }
           }
         }
+        // branch-free up to the stores: divergent branches cost more here than the few selects that replace them
 #pragma unroll 1
         for (uint32_t it = 0; it < T; it++) {
-          if (g < gend) {
-            if ((rlo | rhi) == 0) {                  // next block that has AC tokens
-              b = __ffs(ne & ~((2u << b) - 1u)) - 1;
-              const uint2 mm = s_mask[b];
-              rlo = mm.x; rhi = mm.y;
-              pos = (s_meta[b] >> 16) + 1u;
-              prev1 = 1;
-            }
-            int p;
-            if (rlo) { const int pz = __clz(rlo); rlo &= ~(0x80000000u >> pz); p = pz; }
-            else { const int pz = __clz(rhi); rhi &= ~(0x80000000u >> pz); p = pz + 32; }
-            const int v = reinterpret_cast<const int16_t*>(sm.cbuf + b * 33)[p];
-            const int run = p - prev1;
+          const bool act = g < gend;
+          const bool adv = act && (rlo | rhi) == 0;                  // next block that has AC tokens
+          const int nb = __ffs(ne & ~((2u << b) - 1u)) - 1;
+          b = adv ? nb : b;
+          const uint2 mm = s_mask[b & 31];
+          const uint32_t me = s_meta[b & 31];
+          rlo = adv ? mm.x : rlo;
+          rhi = adv ? mm.y : rhi;
+          pos = adv ? (me >> 16) + 1u : pos;
+          prev1 = adv ? 1 : prev1;
+          const bool in_lo = rlo != 0;
+          const uint32_t rs = in_lo ? rlo : rhi;
+          const int pz = __clz(rs);                                  // 32 on a lane that has nothing left
+          const uint32_t rest = rs & ~__funnelshift_rc(0x80000000u, 0u, pz);   // (0x80000000 >> pz), 0 for pz = 32
+          const int p = pz + (in_lo ? 0 : 32);
+          const int v = reinterpret_cast<const int16_t*>(sm.cbuf)[(b & 31) * 66 + (p & 63)];
+          const int run = p - prev1;
+          const int cat = 32 - __clz(abs(v));
+          const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
+          if (act) {
+            rlo = in_lo ? rest : rlo;
+            rhi = in_lo ? rhi : rest;
             prev1 = p + 1;
-            const int cat = 32 - __clz(abs(v));
-            const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
             atomicAdd(&hist_ac[sym], 1u);
             if (zrl) atomicAdd(&hist_ac[0xF0], (uint32_t)zrl);
             dst[pos] = jb_token(v, cat, sym, zrl);

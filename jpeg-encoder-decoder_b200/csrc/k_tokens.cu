@@ -270,7 +270,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
       const int mcu = role < 2 ? lane >> 1 : lane & 15;
       const bool ok = active && mcu < p.valid;
       int my = p.my0, mx = p.mx0 + mcu;
-      if (active) while (mx >= p.mw) { mx -= p.mw; my++; }
+      {                                              // a tile wraps at most once when the crop is at least a tile wide
+        const bool wrap = active && mx >= p.mw;
+        mx -= wrap ? p.mw : 0;
+        my += wrap ? 1 : 0;
+        if (active && p.mw < JB_TILE_MCUS) while (mx >= p.mw) { mx -= p.mw; my++; }
+      }
       uint32_t blk;                  // block id inside the job (Y blocks, then Cb, then Cr)
       if (role < 2) blk = (uint32_t)(my * 2 + role) * (uint32_t)(job.w / 8) + (uint32_t)(mx * 2 + (lane & 1));
       else blk = (lane < 16 ? nby : nby + nbc) + (uint32_t)(p.m0 + mcu);
@@ -337,16 +342,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           const uint32_t inrun = okb & (next < 32 ? (1u << next) - 1u : FULL) & ~((1u << lane) - 1u);
           const int lastl = inrun ? 31 - __clz(inrun) : lane;
           const int dc_last = __shfl_sync(FULL, dcq, lastl);
-          if (head) {
+          {                                          // every lane computes, head lanes keep: no divergent region
             const uint32_t R0 = jb_runs_before((uint32_t)p.mw, (uint32_t)my), tfirst = (uint32_t)(my * p.mw) / JB_TILE_MCUS;
-            uint32_t rid;
-            if (role < 2) {
-              const uint32_t R1 = jb_runs_before((uint32_t)p.mw, (uint32_t)my + 1u);
-              rid = 2u * R0 + (uint32_t)role * (R1 - R0) + ((uint32_t)p.tile - tfirst);
-            } else {
-              rid = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
-            }
-            run_rid = rid;
+            const uint32_t R1 = jb_runs_before((uint32_t)p.mw, (uint32_t)my + 1u);
+            const uint32_t rid_y = 2u * R0 + (uint32_t)role * (R1 - R0) + ((uint32_t)p.tile - tfirst);
+            const uint32_t rid_c = 2u * nrc + (lane < 16 ? 0u : nrc) + R0 + ((uint32_t)p.tile - tfirst);
+            run_rid = head ? (role < 2 ? rid_y : rid_c) : 0xFFFFFFFFu;
             run_ntok = run_end - excl;
             run_dc = ((uint32_t)dcq & 0xFFFFu) | ((uint32_t)dc_last << 16);
           }
@@ -378,27 +379,28 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
         uint32_t round_tok = 0;
         if (total > TK_WINDOW) round_tok = job.tok_off + __shfl_sync(FULL, claim, 0);
         uint32_t* dst = total <= TK_WINDOW ? stage : ws.tok + round_tok;        // generic pointer: shared or global
-        if (ok) {
-          uint32_t tok = 0;                          // a run's first DC is predicted across runs: k_dc_fix fills it in
-          if (!head) {
-            const int cat = 32 - __clz(abs(diff));
-            tok = jb_token(diff, cat, 256 + cat, 0);
-            atomicAdd(&hist_dc[cat], 1u);
+        {
+          // a run's first DC is predicted across runs: k_runs_prepare fills it in (token 0 meanwhile)
+          const int dcat = 32 - __clz(abs(diff));
+          const uint32_t dtok = head ? 0u : jb_token(diff, dcat, 256 + dcat, 0);
+          if (ok && !head) atomicAdd(&hist_dc[dcat], 1u);
+          if (ok) dst[excl] = dtok;
+          if (ok && !defer && !(mask >> 63)) dst[excl + 1 + ac] = 0;           // EOB: table index 0, no magnitude bits
+          if (__any_sync(FULL, defer)) {
+            if (defer) for (uint32_t j = 1; j < cnt; j++) dst[excl + j] = JB_TOKEN_VOID;
           }
-          dst[excl] = tok;
-          if (defer) for (uint32_t j = 1; j < cnt; j++) dst[excl + j] = JB_TOKEN_VOID;
-          else if (!(mask >> 63)) dst[excl + 1 + ac] = 0;                      // EOB: table index 0, no magnitude bits
         }
         if (lane == 0 && ~noeob) atomicAdd(&hist_ac[0], (uint32_t)__popc(~noeob));
         __syncwarp();
         const uint32_t T = (total_ac + 31) >> 5;
         uint32_t g = min(lane * T, total_ac);
         const uint32_t gend = min(g + T, total_ac);
-        int b = 0;
-        uint32_t rlo = 0, rhi = 0, pos = 0;
+        // block that holds AC token g: the last one with acex <= g (lanes without tokens search too: no divergence)
+        int b;
+        uint32_t rlo, rhi, pos;
         int prev1 = 1;
-        if (g < gend) {
-          int lo = 0, hi = 32;                       // block that holds AC token g: the last one with acex <= g
+        {
+          int lo = 0, hi = 32;
 #pragma unroll
           for (int it = 0; it < 5; it++) {
             const int mid = (lo + hi) >> 1;
@@ -410,11 +412,18 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           const uint2 mm = s_mask[b];
           const uint32_t meta = s_meta[b];
           rlo = mm.x; rhi = mm.y;
-          uint32_t skip = g - (meta & 0xFFFFu);
+          const uint32_t skip = g < gend ? g - (meta & 0xFFFFu) : 0u;       // tokens of this block that belong to the previous lane
           pos = (meta >> 16) + 1u + skip;
-          for (; skip; skip--) {                     // tokens of this block that belong to the previous lane
-            if (rlo) { const int pz = __clz(rlo); rlo &= ~(0x80000000u >> pz); prev1 = pz + 1; }
-            else { const int pz = __clz(rhi); rhi &= ~(0x80000000u >> pz); prev1 = pz + 33; }
+          const uint32_t smax = __reduce_max_sync(FULL, skip);
+#pragma unroll 1
+          for (uint32_t k = 0; k < smax; k++) {
+            const bool sk = k < skip, in_lo = rlo != 0;
+            const uint32_t rs = in_lo ? rlo : rhi;
+            const int pz = __clz(rs);
+            const uint32_t rest = rs & ~__funnelshift_rc(0x80000000u, 0u, pz);
+            rlo = (sk && in_lo) ? rest : rlo;
+            rhi = (sk && !in_lo) ? rest : rhi;
+            prev1 = sk ? pz + (in_lo ? 1 : 33) : prev1;
           }
         }
         // branch-free up to the stores: divergent branches cost more here than the few selects that replace them
@@ -424,12 +433,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           const bool adv = act && (rlo | rhi) == 0;                  // next block that has AC tokens
           const int nb = __ffs(ne & ~((2u << b) - 1u)) - 1;
           b = adv ? nb : b;
-          const uint2 mm = s_mask[b & 31];
-          const uint32_t me = s_meta[b & 31];
-          rlo = adv ? mm.x : rlo;
-          rhi = adv ? mm.y : rhi;
-          pos = adv ? (me >> 16) + 1u : pos;
-          prev1 = adv ? 1 : prev1;
+          if (adv) {                                                 // two predicated loads, no divergent region
+            const uint2 mm = s_mask[b];
+            rlo = mm.x; rhi = mm.y;
+            pos = (s_meta[b] >> 16) + 1u;
+            prev1 = 1;
+          }
           const bool in_lo = rlo != 0;
           const uint32_t rs = in_lo ? rlo : rhi;
           const int pz = __clz(rs);                                  // 32 on a lane that has nothing left

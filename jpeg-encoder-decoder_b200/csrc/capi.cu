@@ -264,7 +264,7 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
   const JbWs& ws = l.ws;
   CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
   if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
-    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, c->overlap_waves ? 4 : 0, st); }
+    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, c->overlap_waves ? 8 : 0, st); }
     cudaStream_t lo = st;
     if (c->split_streams && c->overlap_waves) {   // the rest of the chain at high priority; the lane's stream rejoins at the end
       CK(cudaEventRecord(l.pass1_done, lo));

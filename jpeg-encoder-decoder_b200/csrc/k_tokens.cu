@@ -5,8 +5,9 @@
 // so that neither the coefficient planes nor a second walk over them are needed: the bit packer (k_pack_runs.cu) streams
 // tokens.  Results are bit-identical with the plane path (k_dct.cu + k_symbol_stats); the parity suite compares both.
 //
-// Work decomposition: every warp is an independent worker — no CTA barrier anywhere.  A worker owns a contiguous range of
-// tiles (16 consecutive MCUs).  Per tile:
+// Work decomposition: every warp is an independent worker — no data moves between warps; the only CTA barrier (one per
+// tile) keeps the warps of an SM in the same phase for the instruction caches' sake.  A worker takes tiles (16 consecutive
+// MCUs) of its CTA's range.  Per tile:
 //   rows 0-7  of the tile arrive by bulk async copies (mbarrier) -> colour conversion -> samples of luma block row 0 and
 //             chroma rows 0-3; the copies of rows 8-15 are issued, and overlap
 //   round 0   (32 luma blocks, one per lane): FP32 AAN filter + bracketed quantisation, exact FP64 replay of undecided
@@ -24,16 +25,16 @@
 namespace {
 
 #ifndef TK_WARPS_PER_CTA
-#define TK_WARPS_PER_CTA 4
+#define TK_WARPS_PER_CTA 12
 #endif
 #ifndef TK_SYNC
-#define TK_SYNC 2
+#define TK_SYNC 1
 #endif
 #ifndef TK_ABLATE
 #define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
 #endif
 #ifndef TK_CTAS_PER_SM
-#define TK_CTAS_PER_SM 3
+#define TK_CTAS_PER_SM 1
 #endif
 constexpr int TK_WARPS = TK_WARPS_PER_CTA;   // workers per CTA
 constexpr int TK_WINDOW = 384;          // a round with at most this many tokens is staged in shared memory (the round's dead sample
@@ -180,9 +181,11 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
     }
   }
   __syncwarp();
-  // The CTA owns a contiguous range of tiles; its warps take them round-robin and stay in step (phase_sync): the warps of
-  // a CTA then fetch the same instructions at the same time — with every warp on its own schedule the 80 KB of code
-  // thrash the instruction caches (measured: 56 % of the stall samples were no_inst).
+  // The CTA (one per SM, 12 warps) owns a contiguous range of tiles; its warps take them round-robin and re-align once per
+  // tile (phase_sync): all warps of the SM then run the same phase at about the same time and fetch the same instructions —
+  // with every warp on its own schedule the code thrashes the instruction caches (first version: 56 % of the stall
+  // samples were no_inst).  Measured per 32 frames: 12-warp CTA 261 us (sync per tile), 267 (none), 271 (per step),
+  // 282 (per phase); three 4-warp CTAs 281-296.
   const int cta_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), cta_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
   const int t_begin = cta_begin + warp, t_end = cta_end;
 
@@ -314,13 +317,17 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           cnt = 2u + (uint32_t)__popcll(rm);
           mask = 0;                                  // nothing to walk
         }
-        uint32_t inc = cnt;
+        // one scan for both prefixes: token slots in the low half, walkable AC tokens in the high half (both < 2^16)
+        const uint32_t ac = (uint32_t)__popcll(mask);
+        const uint32_t both = cnt | (ac << 16);
+        uint32_t inc = both;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const uint32_t n = __shfl_up_sync(FULL, inc, o);
           if (lane >= o) inc += n;
         }
-        const uint32_t excl = inc - cnt, total = __shfl_sync(FULL, inc, 31);
+        const uint32_t exb = inc - both, totb = __shfl_sync(FULL, inc, 31);
+        const uint32_t excl = exb & 0xFFFFu, total = totb & 0xFFFFu, acex = exb >> 16, total_ac = totb >> 16;
         const uint32_t prev_blk = __shfl_up_sync(FULL, blk, 1);
         const int prev_dc = __shfl_up_sync(FULL, dcq, 1);
         const uint32_t okb = __ballot_sync(FULL, ok);
@@ -362,14 +369,6 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
         uint32_t* s_meta = stage + TK_WINDOW + 64;                             // AC tokens before the block | tokens before it << 16
         uint32_t* hist_dc = sm.hist + comp * 272;
         uint32_t* hist_ac = hist_dc + 16;
-        const uint32_t ac = (uint32_t)__popcll(mask);
-        uint32_t acinc = ac;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t n = __shfl_up_sync(FULL, acinc, o);
-          if (lane >= o) acinc += n;
-        }
-        const uint32_t acex = acinc - ac, total_ac = __shfl_sync(FULL, acinc, 31);
         const uint32_t ne = __ballot_sync(FULL, ac != 0);
         const uint32_t noeob = __ballot_sync(FULL, !ok || defer || (mask >> 63) != 0);
         const int diff = dcq - prev_dc;
@@ -400,15 +399,15 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
         uint32_t rlo, rhi, pos;
         int prev1 = 1;
         {
-          int lo = 0, hi = 32;
+          // two levels of independent loads (6 fixed entries, then up to 4 neighbours) instead of a 5-deep chain
+          int c1 = 0;
 #pragma unroll
-          for (int it = 0; it < 5; it++) {
-            const int mid = (lo + hi) >> 1;
-            const bool ge = (s_meta[mid] & 0xFFFFu) <= g;
-            lo = ge ? mid : lo;
-            hi = ge ? hi : mid;
-          }
-          b = lo;
+          for (int k = 1; k <= 6; k++) c1 += (s_meta[5 * k] & 0xFFFFu) <= g ? 1 : 0;
+          b = 5 * c1;
+          int c2 = 0;
+#pragma unroll
+          for (int j = 1; j <= 4; j++) c2 += (b + j < 32 && (s_meta[(b + j) & 31] & 0xFFFFu) <= g) ? 1 : 0;
+          b += c2;
           const uint2 mm = s_mask[b];
           const uint32_t meta = s_meta[b];
           rlo = mm.x; rhi = mm.y;

@@ -33,6 +33,14 @@ namespace {
 #ifndef TK_ABLATE
 #define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
 #endif
+#ifndef TK_UNROLL_DR
+#define TK_UNROLL_DR 2    // pixel rows of a patch: rolled (half the colour code) or unrolled (2)
+#endif
+#if TK_UNROLL_DR == 2
+#define TK_DR_PRAGMA _Pragma("unroll")
+#else
+#define TK_DR_PRAGMA _Pragma("unroll 1")
+#endif
 #ifndef TK_CTAS_PER_SM
 #define TK_CTAS_PER_SM 1
 #endif
@@ -112,7 +120,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
     uint32_t scr_y = 0xFFFFFFFFu, scr_c = 0xFFFFFFFFu;
     {                                    // lanes past the end of the crop convert stale bytes into their own, unused slots
       uint32_t* ydst = &sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4];
-#pragma unroll 1
+      TK_DR_PRAGMA
       for (int dr = 0; dr < 2; dr++) {
         uint32_t w[6], yb[8], cbb[8], crb[8];
         const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);

@@ -289,6 +289,31 @@ def test_full_batch_properties(enc, frames):
     enc.configure(8, 3)
 
 
+def test_large_and_extreme_aspect_frames(oracle, frames):
+    """Single big frames and extreme aspect ratios through both batched paths: 16.8 Mpix of noise (every round of the
+    token kernel overflows its shared-memory window and stores straight to global memory), an 8K-wide natural frame, a
+    tall narrow frame (tiles that cover many MCU rows) and one-MCU-high / one-MCU-wide strips."""
+    tok, plane = pkg.Encoder(0, 2, 2), pkg.Encoder(0, 2, 2)
+    plane.set_token_path(False)
+    try:
+        rng = np.random.default_rng(5)
+        cases = [("noise", 4096, 4096), ("natural", 7680, 2160), ("rand", 1024, 8192), ("rand", 16384, 16), ("rand", 16, 4112)]
+        for kind, w, h in cases:
+            if kind == "noise":
+                img = frames.noise_frame(3, w, h)
+            elif kind == "natural":
+                img = np.ascontiguousarray(np.tile(frames.natural_frame(1, 3840, 2160), (1, 2, 1))[:h, :w])
+            else:
+                img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            slot = 3 * w * h + 65536
+            want = oracle.encode(img)["jpg"].tobytes()
+            assert tok.encode_frames(img[None], slot)[0] == want, (kind, w, h, "token path")
+            assert plane.encode_frames(img[None], slot)[0] == want, (kind, w, h, "plane path")
+    finally:
+        tok.close()
+        plane.close()
+
+
 # ------------------------------------------------------------------ comparator
 
 def test_comparator_golden_flow(api, enc, oracle, frames, golden):

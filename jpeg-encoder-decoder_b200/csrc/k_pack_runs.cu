@@ -101,24 +101,35 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* tok2 = ws.tok2 + job.tok_off;
   uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
-  for (uint32_t r = blockIdx.x * PR_WARPS + warp; r < nr; r += gridDim.x * PR_WARPS) {
-    const JbRun run = ws.runs[job.run_off + r];
+  // the record of the next run is fetched while the current one is copied (one dependent global load less per run)
+  const uint32_t stride = gridDim.x * PR_WARPS;
+  uint32_t r = blockIdx.x * PR_WARPS + warp;
+  uint4 rec = make_uint4(0, 0, 0, 0);
+  uint32_t dnext = 0;
+  if (r < nr) { rec = __ldg(reinterpret_cast<const uint4*>(ws.runs + job.run_off + r)); dnext = __ldg(ws.run_base + job.run_off + r); }
+  for (; r < nr; r += stride) {
+    JbRun run;
+    run.tok = rec.x; run.ntok = rec.y; run.dc = rec.z; run.pad = rec.w;
+    const uint32_t d0 = dnext;
+    if (r + stride < nr) { rec = __ldg(reinterpret_cast<const uint4*>(ws.runs + job.run_off + r + stride)); dnext = __ldg(ws.run_base + job.run_off + r + stride); }
     const uint32_t* e = enc[run_scan(r, nrc) ? 1 : 0];
     const uint32_t zrl_len = e[0xF0] & 31u;
     const uint32_t* tok = ws.tok + run.tok;
-    const uint32_t d0 = ws.run_base[job.run_off + r];
-    for (uint32_t k0 = 0; k0 < run.ntok; k0 += 256) {       // 8 independent loads per lane in flight
+    for (uint32_t k0 = 0; k0 < run.ntok; k0 += 256) {       // up to 8 independent loads per lane in flight
+      const int nj = (int)min(8u, (run.ntok - k0 + 31u) >> 5);      // warp-uniform: short runs (chroma) skip the empty slices
       uint32_t t8[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const uint32_t k = k0 + 32 * j + lane;
-        t8[j] = k < run.ntok ? __ldg(tok + k) : 0u;
+        t8[j] = 0u;
+        if (j < nj && k < run.ntok) t8[j] = __ldg(tok + k);
       }
       // the 256 tokens of this step land in at most two chunks
       const uint32_t ca = (d0 + k0) / JB_TCHUNK;
       uint32_t la = 0, lb = 0;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
+        if (j >= nj) break;                                           // uniform
         const uint32_t k = k0 + 32 * j + lane;
         if (k < run.ntok) {
           const uint32_t t = t8[j];

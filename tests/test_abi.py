@@ -67,3 +67,24 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"liboracle|libref|cpu_checkers|oracle/_|#include\s+\"[^\"]*oracle", txt):
                     bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_fast_tables_match_the_error_bound_analysis(tmp_path):
+    """fast_tables.cuh (the FP32 bracket multipliers of the filter DCT) must be exactly what tools/analysis/gen_fast_tables.py
+    derives from the rigorous per-position error bound: a stale or hand-edited table would silently void the exactness
+    argument of DESIGN.md §2."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_fast_tables", os.path.join(ROOT, "tools", "analysis", "gen_fast_tables.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = tmp_path / "fast_tables.cuh"
+    mod.main(str(out))
+    committed = open(os.path.join(ROOT, "jpeg-encoder-decoder_b200", "csrc", "fast_tables.cuh")).read()
+    assert out.read_text() == committed
+    # every bracket must be wider than its bound and narrower than the uniform 2^-14 of the first version
+    B = mod.BOUNDS
+    for comp in ("luma", "chroma"):
+        for v in range(8):
+            for u in range(8):
+                rho = mod.rho_of(comp, v, u)
+                assert B[comp][v, u] < rho <= 2.0 ** -14

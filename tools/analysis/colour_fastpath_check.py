@@ -29,7 +29,21 @@ def check(D, nmax, name):
     print(f"{name}: D={D} inv={float(inv)!r} (bits {inv.view(np.uint32):#x}) M={M} n<= {nmax}: floor mismatches {bad.size}, missed ties {miss.size}, false-positive rate {fp:.2e}")
     assert bad.size == 0 and miss.size == 0
 
+def check_remainder(D, nmax, name):
+    """k_pixels_to_tokens' exact screen: r' = n_bits - q_bits * D (mod 2^32) on the float bit patterns 0x4B000000 + n and
+    0x4B000000 + n // D.  It must equal K_D = 0x4B000000 * (1 - D) mod 2^32 exactly when D divides n, and stay in
+    [K_D, K_D + D) (no wrap-around), so that the running unsigned minimum detects a tie."""
+    n = np.arange(0, nmax + 1, dtype=np.uint64)
+    nb, qb = (0x4B000000 + n) & 0xFFFFFFFF, (0x4B000000 + n // D) & 0xFFFFFFFF
+    r = (nb - qb * D) & 0xFFFFFFFF
+    K = (0x4B000000 * (1 - D)) % (1 << 32)
+    assert K + D < (1 << 32), "wrap-around"
+    assert ((r >= K) & (r < K + D)).all() and ((r == K) == (n % D == 0)).all()
+    print(f"{name}: exact remainder screen K_D = {K:#010x}, range [K_D, K_D + {D}) without wrap-around: ok")
+
 check(1000, 255 * 1000, "Y ")
+check_remainder(1000, 255 * 1000, "Y ")
+check_remainder(31250, 4_000_000 + 255 * 15625, "Cb/Cr")
 check(31250, 4_000_000 + 255 * 15625, "Cb/Cr")
 # reachable numerator ranges
 R, G, B = np.meshgrid(np.arange(256), np.arange(256), np.arange(256), indexing="ij")

@@ -44,12 +44,14 @@ int jpegb200_debug_fix_count(jpegb200_ctx *ctx, int lane, uint32_t *count);
 /* Number of kernels launched by this context so far (bench.py reports it as gpu_launches). */
 uint64_t jpegb200_launch_count(const jpegb200_ctx *ctx);
 
-/* CUDA-event timing of the dominant kernel (k_bgr_to_coef) on the stream it is launched on: switch on,
- * run, then read the summed duration and the number of launches timed (also resets the record). */
-int jpegb200_set_timing(jpegb200_ctx *ctx, int level);   /* 0 off, 1 = k_bgr_to_coef, 2 = every stage */
+/* CUDA-event timing of the dominant kernel (k_pixels_to_tokens; k_bgr_to_coef* on the plane path) on the stream it is
+ * launched on: switch on, run, then read the summed duration and the number of launches timed (also resets the record). */
+int jpegb200_set_timing(jpegb200_ctx *ctx, int level);   /* 0 off, 1 = dominant kernel only, 2 = every stage */
 int jpegb200_get_timing(jpegb200_ctx *ctx, double *ms_total, uint64_t *launches);
-/* Per-stage sums; index: 0 dct, 1 plane masks, 2 symbol stats, 3 huffman build, 4 table pack, 5 block bits,
- * 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff, 11 fix-up of undecided blocks.  ms and n have 16 entries. */
+/* Per-stage sums; index: 0 pixels -> tokens (plane path: pixels -> coefficient planes), 1 plane masks, 2 symbol stats,
+ * 3 huffman build, 4 table pack, 5 block bits, 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff, 11 undecided blocks
+ * (k_fix_tokens / k_fix_blocks), 12 run preparation (first DC of every run, token prefix), 13 token compaction.
+ * ms and n have 16 entries. */
 int jpegb200_get_stage_timing(jpegb200_ctx *ctx, double *ms, uint64_t *n);
 
 /* ---- batched encode, device resident (the fast path) -------------------------------------------

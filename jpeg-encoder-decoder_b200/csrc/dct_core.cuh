@@ -231,6 +231,36 @@ __device__ __forceinline__ void ycc_row8x(const uint32_t (&w)[6], uint32_t (&yb)
   }
 }
 
+// The same conversion without the two FADDs per value that removed the 2^23 offset before the division: the numerator n is
+// biased so that the float x = 2^23 + bias + n is T + n with T a multiple of D, and one FFMA.RZ gives 2^23 + floor:
+//   luma    T = 8 389 000 = 8389 * 1000     x * INV1000_UP   + (2^23 - 8389)
+//   chroma  T = 12 500 000 = 400 * 31250    x * INV31250_DN  + (2^23 + 128 - 400)   (numerator without the +128 * 31250)
+// Exhaustively checked against integer division (tools/analysis/colour_fastpath_check.py): luma is exact for every n in
+// [0, 255000]; chroma (multiplier rounded DOWN: rounded up, the 400 extra quotient units push 240 non-tie numerators over
+// the next integer) is exact for every numerator that D does not divide and one too small for every one that D divides.
+// Those are the ties that are replayed anyway; their remainder reads D instead of 0, so the chroma screen keeps a MAXIMUM.
+constexpr float INV31250_DN = 0x1.0c6f7ap-15f;    // largest float < 1/31250     (bits 0x380637bd)
+constexpr int NF_BASE_Y = 392, NF_BASE_C = 12500000 - 8388608;
+constexpr uint32_t TIE_KN_Y = TIE_K_Y + 392u;                                  // remainder 0 of a luma value
+constexpr uint32_t TIE_KN_C = TIE_K_C + (uint32_t)(NF_BASE_C - 4000000) + 31250u;   // remainder D of a chroma value
+__device__ __forceinline__ void ycc_row8n(const uint32_t (&w)[6], uint32_t (&yb)[8], uint32_t (&cbb)[8], uint32_t (&crb)[8], uint32_t& scr_y, uint32_t& scr_c) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t ny[4], nb[4], nr[4];
+    numer4<114, 587, 299, NF_BASE_Y>(w[3 * h], w[3 * h + 1], w[3 * h + 2], ny);
+    numer4<15625, -10352, -5273, NF_BASE_C>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nb);
+    numer4<-2541, -13084, 15625, NF_BASE_C>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nr);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      yb[4 * h + k] = __float_as_uint(__fmaf_rz(__uint_as_float(ny[k]), INV1000_UP, 8380219.0f));
+      cbb[4 * h + k] = __float_as_uint(__fmaf_rz(__uint_as_float(nb[k]), INV31250_DN, 8388336.0f));
+      crb[4 * h + k] = __float_as_uint(__fmaf_rz(__uint_as_float(nr[k]), INV31250_DN, 8388336.0f));
+      scr_y = min(scr_y, ny[k] - yb[4 * h + k] * 1000u);
+      scr_c = max(scr_c, max(nb[k] - cbb[4 * h + k] * 31250u, nr[k] - crb[4 * h + k] * 31250u));
+    }
+  }
+}
+
 // In-place forward AAN butterfly on 8 floats; out[k] = X[k] / r_k (tools/analysis/gen_fast_tables.py).
 __device__ __forceinline__ void aan8(float& d0, float& d1, float& d2, float& d3, float& d4, float& d5, float& d6, float& d7) {
   using namespace jbfast;

@@ -30,6 +30,12 @@ namespace {
 #ifndef TK_SYNC
 #define TK_SYNC 1
 #endif
+#ifndef TK_NOFADD
+#define TK_NOFADD 1       // colour stage: biased numerators, one FFMA.RZ per value (ycc_row8n) instead of FADD + FFMA.RZ (ycc_row8x)
+#endif
+#ifndef TK_SKIP_CLOSED
+#define TK_SKIP_CLOSED 1  // token walk: a lane that starts inside a block finds its first coefficient by binary descent, not by stepping
+#endif
 #ifndef TK_ABLATE
 #define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
 #endif
@@ -117,7 +123,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
 #pragma unroll 1
   for (int pr = 0; pr < 4; pr++) {
     uint32_t cbs[4] = {0, 0, 0, 0}, crs[4] = {0, 0, 0, 0};
-    uint32_t scr_y = 0xFFFFFFFFu, scr_c = 0xFFFFFFFFu;
+    uint32_t scr_y = 0xFFFFFFFFu, scr_c = TK_NOFADD ? 0u : 0xFFFFFFFFu;
     {                                    // lanes past the end of the crop convert stale bytes into their own, unused slots
       uint32_t* ydst = &sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4];
       TK_DR_PRAGMA
@@ -126,7 +132,8 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
         const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
 #pragma unroll
         for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
-        ycc_row8x(w, yb, cbb, crb, scr_y, scr_c);
+        if (TK_NOFADD) ycc_row8n(w, yb, cbb, crb, scr_y, scr_c);
+        else ycc_row8x(w, yb, cbb, crb, scr_y, scr_c);
         *reinterpret_cast<uint2*>(ydst + 2 * dr) = make_uint2(pack4(yb[0], yb[1], yb[2], yb[3]), pack4(yb[4], yb[5], yb[6], yb[7]));
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -139,7 +146,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
       sm.smp[(64 + mcu) * 16 + cw] = pack4(cbs[0] >> 2, cbs[1] >> 2, cbs[2] >> 2, cbs[3] >> 2);
       sm.smp[(80 + mcu) * 16 + cw] = pack4(crs[0] >> 2, crs[1] >> 2, crs[2] >> 2, crs[3] >> 2);
     }
-    const bool tie = !(TK_ABLATE & 2) && live && (scr_y == TIE_K_Y || scr_c == TIE_K_C);
+    const bool tie = !(TK_ABLATE & 2) && live && (TK_NOFADD ? (scr_y == TIE_KN_Y || scr_c == TIE_KN_C) : (scr_y == TIE_K_Y || scr_c == TIE_K_C));
     const uint32_t tb = __ballot_sync(FULL, tie);
     if (tie) sm.ties[ntie + __popc(tb & ((1u << lane) - 1u))] = (uint8_t)(pr * 32 + lane);
     ntie += __popc(tb);
@@ -193,7 +200,9 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
   // tile (phase_sync): all warps of the SM then run the same phase at about the same time and fetch the same instructions —
   // with every warp on its own schedule the code thrashes the instruction caches (first version: 56 % of the stall
   // samples were no_inst).  Measured per 32 frames: 12-warp CTA 261 us (sync per tile), 267 (none), 271 (per step),
-  // 282 (per phase); three 4-warp CTAs 281-296.
+  // 282 (per phase); three 4-warp CTAs 281-296.  Round 2 tried the opposite, too: the three warps of a scheduler held one
+  // sub-phase apart (colour / DCT / token walk, a barrier at every sub-phase boundary) so that their pipes would complement
+  // each other: 589 us per 64 frames against 454; no barrier at all: 494.  In-phase warps win because of instruction fetch.
   const int cta_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), cta_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
   const int t_begin = cta_begin + warp, t_end = cta_end;
 
@@ -421,6 +430,31 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
           rlo = mm.x; rhi = mm.y;
           const uint32_t skip = g < gend ? g - (meta & 0xFFFFu) : 0u;       // tokens of this block that belong to the previous lane
           pos = (meta >> 16) + 1u + skip;
+#if TK_SKIP_CLOSED
+          {
+            // drop the block's first `skip` tokens in closed form: binary descent (popcounts of the upper halves) to the position
+            // of the skip-th set flag; a loop of `max skip over the warp` single steps cost 160 instructions per round here
+            uint32_t k = skip;
+            const uint32_t clo = (uint32_t)__popc(rlo);
+            const bool hi = k > clo;
+            uint32_t x = hi ? rhi : rlo;
+            k -= hi ? clo : 0u;
+            int pp = hi ? 32 : 0;
+#pragma unroll
+            for (int h = 16; h >= 1; h >>= 1) {
+              const uint32_t c = (uint32_t)__popc(x >> (32 - h));
+              const bool down = k > c;
+              k -= down ? c : 0u;
+              x = down ? x << h : x;
+              pp += down ? h : 0;
+            }
+            const uint32_t keep = 0x7FFFFFFFu >> (pp & 31);          // flags of the positions after pp in pp's word
+            const uint32_t nlo = hi ? 0u : rlo & keep, nhi = hi ? rhi & keep : rhi;
+            rlo = skip ? nlo : rlo;
+            rhi = skip ? nhi : rhi;
+            prev1 = skip ? pp + 1 : 1;
+          }
+#else
           const uint32_t smax = __reduce_max_sync(FULL, skip);
 #pragma unroll 1
           for (uint32_t k = 0; k < smax; k++) {
@@ -432,6 +466,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
             rhi = (sk && !in_lo) ? rest : rhi;
             prev1 = sk ? pz + (in_lo ? 1 : 33) : prev1;
           }
+#endif
         }
         // branch-free up to the stores: divergent branches cost more here than the few selects that replace them
 #pragma unroll 1

@@ -55,3 +55,32 @@ cb6 = 128_000_000 - 168736 * R - 331264 * G + 500000 * B
 cr6 = 128_000_000 + 500000 * R - 418688 * G - 81312 * B
 assert (cb6 == 32 * cb).all() and (cr6 == 32 * cr).all()
 print("ok")
+
+
+# ---- round 2: the FADD-free form (ycc_row8n in dct_core.cuh) ---------------------------------------------------------
+# x = T + n is the float whose bits are 0x4B000000 + (T - 2^23) + n; q_bits = RZ_f32(x * inv + C) with C = 2^23 + off - T / D.
+def mant_exp(bits):
+    return (bits & 0x7FFFFF) | 0x800000, 150 - ((bits >> 23) & 0xFF)      # value = M * 2^-e exactly
+
+def check_nofadd(D, T, off, inv_bits, lo, hi, name, tie_delta):
+    M, e = mant_exp(inv_bits)
+    n = np.arange(lo, hi + 1, dtype=np.int64)                              # numerator without any bias
+    assert T % D == 0 and T + lo >= 2 ** 23 and T + hi < 2 ** 24
+    C = 2 ** 23 + off - T // D
+    q = (((T + n) * M + (C << e)) >> e) - 2 ** 23 - off                    # exact product + C, rounded toward zero (positive)
+    want = n // D
+    tie = (n % D) == 0
+    assert (q[~tie] == want[~tie]).all(), name
+    assert (q[tie] == want[tie] + tie_delta).all(), name
+    # remainder screen on the bit patterns
+    xb = (0x4B000000 + T - 2 ** 23 + n) & 0xFFFFFFFF
+    qb = (0x4B000000 + off + q) & 0xFFFFFFFF
+    r = (xb - qb * D) & 0xFFFFFFFF
+    K = (0x4B000000 * (1 - D) + T - 2 ** 23 - off * D) % (1 << 32)
+    assert K + D < (1 << 32)
+    flag = K if tie_delta == 0 else K + D
+    assert ((r == flag) == tie).all() and (r >= K).all() and (r <= K + D).all()
+    print(f"{name}: FADD-free floor exact off ties, ties read {tie_delta:+d}; screen constant {flag:#010x} ({'min' if tie_delta == 0 else 'max'})")
+
+check_nofadd(1000, 8_389_000, 0, 0x3a83126f, 0, 255_000, "Y  (no FADD)", 0)
+check_nofadd(31250, 12_500_000, 128, 0x380637bd, -255 * 15625, 255 * 15625, "C  (no FADD)", -1)

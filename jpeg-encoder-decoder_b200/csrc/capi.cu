@@ -387,6 +387,9 @@ int jpegb200_create(jpegb200_ctx** out, int device) {
   c->device = device;
   if (const char* e = getenv("JPEGB200_SPLIT_STREAMS")) c->split_streams = atoi(e) != 0;
   if (make_lanes(c, 3) != 0) { delete c; return -1; }
+  jb_init_grey_tokens(nullptr);
+  jb_init_grey_dct(nullptr);
+  if (cudaDeviceSynchronize() != cudaSuccess) { for (auto& l : c->lanes) l.release(); delete c; return fail("grey-level table: %s", cudaGetErrorString(cudaGetLastError())); }
   if (cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return fail("cudaEventCreate failed"); }
   *out = c;
   return 0;

@@ -29,8 +29,17 @@ __device__ __noinline__ uint32_t ycc_exact(uint32_t b0, uint32_t b1, uint32_t b2
   return Y | (Cb << 8) | (Cr << 16);
 }
 
+// Grey pixels (B = G = R = v) sit on an integer boundary in all three planes: 0.299v + 0.587v + 0.114v, 128 - ... + 0.5v and
+// 128 + 0.5v - ... are exactly v, 128, 128 in real arithmetic and the double chain lands on either side (65 of the 256 levels
+// give Y = v - 1, 59 give Cr = 127).  g_grey[v] holds what the literal chain returns for them; it is filled on
+// the device by jb_init_grey (every translation unit that includes this header has its own copy), so that grey content
+// (night / IR frames, the `ramp` class) costs a load per replayed pixel, not 17 FP64 operations.
+__device__ uint32_t g_grey[256];
+__global__ void k_init_grey() { g_grey[threadIdx.x] = ycc_exact(threadIdx.x, threadIdx.x, threadIdx.x); }
+
 // Returns Y | Cb<<8 | Cr<<16 (each already truncated to 8 bits like the uint8 stores of encoder.c:133-135).
 __device__ __forceinline__ uint32_t ycc_pixel(uint32_t b0, uint32_t b1, uint32_t b2) {
+  if (b0 == b1 && b1 == b2) return g_grey[b0];
   uint32_t y3 = 299u * b2 + 587u * b1 + 114u * b0;                         // 1000 * Y, exact
   uint32_t yq = __umulhi(y3, 274877907u) >> 6;                             // y3 / 1000   (verified for 0..255000)
   uint32_t c6 = 128000000u - 168736u * b2 - 331264u * b1 + 500000u * b0;   // 1e6 * Cb, in [5e5, 2.555e8]

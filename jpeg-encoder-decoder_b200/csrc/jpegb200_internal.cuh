@@ -161,6 +161,10 @@ void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaSt
 void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 
+// grey-level table of the colour replay (dct_core.cuh): one copy per translation unit, filled once per context
+void jb_init_grey_tokens(cudaStream_t st);
+void jb_init_grey_dct(cudaStream_t st);
+
 // token path (k_tokens.cu, k_pack_runs.cu)
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st);
 void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);

@@ -500,6 +500,8 @@ __global__ void __launch_bounds__(128) k_fix_tokens(JbWs ws) {
 
 }  // namespace
 
+void jb_init_grey_dct(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
+
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st) {
   int tiles = ((max_w + TILE_W - 1) / TILE_W) * (max_h / 16);
   k_bgr_to_coef<<<dim3(tiles, njobs), K1_THREADS, 0, st>>>(ws);

@@ -50,14 +50,22 @@ namespace {
 #ifndef TK_CTAS_PER_SM
 #define TK_CTAS_PER_SM 1
 #endif
-constexpr int TK_WARPS = TK_WARPS_PER_CTA;   // workers per CTA
+constexpr int TK_WARPS_ALIGNED = TK_WARPS_PER_CTA;   // workers per CTA
+constexpr int TK_WARPS_UNALIGNED = 8;                // the wider staging rows of the unaligned loader leave room for 8
+template <bool ALIGNED> struct TkWarps { static constexpr int value = ALIGNED ? TK_WARPS_ALIGNED : TK_WARPS_UNALIGNED; };
 constexpr int TK_WINDOW = 384;          // a round with at most this many tokens is staged in shared memory (the round's dead sample
                                         // slots: 1.5 KB of tokens + 0.5 KB of per-block walk state) and flushed with coalesced stores;
                                         // busier rounds store their tokens straight to global memory
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
-struct __align__(128) TkSmem {
-  uint32_t raw[8][JB_TILE_MCUS * 12];   // 8 pixel rows x (16 MCUs x 48 B) of B,G,R bytes
+// ALIGNED = every crop row starts on a 16-byte boundary (whole frames; crops with 3 * x a multiple of 16).  Otherwise the bulk
+// copies start at the aligned-down address: the bytes of a row land `shift` = (address of the crop's first byte) & 15 bytes
+// late (the same for every row: the pitch 3 * WIDTH is a multiple of 48), and every further MCU-row run of the tile is placed
+// 16 bytes further on, so that its copy cannot touch the tail of the previous one: MCU m of the tile sits at byte
+// 48 m + shift + 16 * (runs before it).  A tile holds up to 16 runs (crop 16 pixels wide): rows of 768 + 272 bytes.
+template <bool ALIGNED>
+struct __align__(128) TkSmemT {
+  uint32_t raw[8][ALIGNED ? JB_TILE_MCUS * 12 : JB_TILE_MCUS * 12 + 68];   // 8 pixel rows x (16 MCUs x 48 B) of B,G,R bytes
   uint32_t smp[96 * 16];                // 8-bit samples, 64 B per block: luma slot = (block row)*32 + mcu*2 + (block column),
                                         // Cb of MCU m in slot 64+m, Cr in slot 80+m.  The 16-byte chunk c (sample rows 2c, 2c+1)
                                         // of slot s lives at chunk (c ^ (s >> 1)) & 3  -> conflict-free LDS.128 / STS.128
@@ -67,6 +75,14 @@ struct __align__(128) TkSmem {
   unsigned long long full;              // mbarrier: the 8 rows in flight have landed
   uint32_t pad[2];
   uint8_t ties[128];                    // patches (row pair * 32 + lane) of the 8 staged rows with a pixel on an integer boundary
+};
+// where the tile's MCUs sit in a staged row (bytes)
+struct TkShift {
+  uint32_t shift;     // 0..15
+  int mx0, mw;        // first MCU column of the tile, MCUs per crop row
+  template <bool ALIGNED> __device__ __forceinline__ uint32_t mcu_byte(int mcu) const {
+    return ALIGNED ? 48u * (uint32_t)mcu : 48u * (uint32_t)mcu + shift + 16u * (uint32_t)((mx0 + mcu) / mw);
+  }
 };
 // zig-zag positions (1..63) of the coefficients of natural row v (vertical frequency v)
 __constant__ unsigned long long c_rowzz[8] = {0x000000001800c062ull, 0x0000040024012094ull, 0x00000a0042021108ull, 0x0020110081040a00ull, 0x0050208100880400ull, 0x1088404200500000ull, 0x2904802400200000ull, 0xc603001800000000ull};
@@ -90,13 +106,14 @@ __device__ __forceinline__ bool tk_tile(const JbWs& ws, int t, int tiles_per_job
 }
 
 // Cold path of the colour stage (see replay_patch in k_dct.cu): exact replay of one 8x2 patch.
-__device__ __noinline__ void tk_replay_patch(TkSmem& sm, int half, int mcu, int pr, int pc) {
+template <bool ALIGNED>
+__device__ __noinline__ void tk_replay_patch(TkSmemT<ALIGNED>& sm, const TkShift& sh, int half, int mcu, int pr, int pc) {
   uint32_t cb[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
   const int slot = half * 32 + mcu * 2 + pc;
 #pragma unroll 1
   for (int dr = 0; dr < 2; dr++) {
     const int r = 2 * pr + dr;                   // row inside the half = sample row of the luma block
-    const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[r][mcu * 12 + 6 * pc]);
+    const uint8_t* px = reinterpret_cast<const uint8_t*>(&sm.raw[r][0]) + sh.mcu_byte<ALIGNED>(mcu) + 24 * pc;
     uint8_t* ydst = reinterpret_cast<uint8_t*>(&sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4 + dr * 2]);
 #pragma unroll
     for (int c = 0; c < 8; c++) {
@@ -115,8 +132,10 @@ __device__ __noinline__ void tk_replay_patch(TkSmem& sm, int half, int mcu, int 
 // time (the row loop is kept rolled: half the code).  Patches with a pixel whose Y, Cb or Cr is an exact integer (the
 // reference's double chain decides between n and n-1 there) are listed and replayed afterwards, 16 lanes per patch:
 // about one patch in 150 on photographic content, every patch on grey content.
-__device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, int lane) {
+template <bool ALIGNED>
+__device__ __forceinline__ void tk_colour_half(TkSmemT<ALIGNED>& sm, const TkShift& sh, int half, int valid, int lane) {
   const int mcu = lane >> 1, pc = lane & 1;
+  const uint32_t mbyte = sh.mcu_byte<ALIGNED>(mcu) + 24u * (uint32_t)pc;      // the lane's 8 pixels inside a staged row
   const bool live = mcu < valid;
   const int slot = half * 32 + lane;
   uint32_t ntie = 0;
@@ -129,9 +148,19 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
       TK_DR_PRAGMA
       for (int dr = 0; dr < 2; dr++) {
         uint32_t w[6], yb[8], cbb[8], crb[8];
-        const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
+        if (ALIGNED) {
+          const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
 #pragma unroll
-        for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+          for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+        } else {                               // seven aligned words, funnel-shifted by the byte phase
+          const uint32_t* src = &sm.raw[2 * pr + dr][mbyte >> 2];
+          const uint32_t bits = 8u * (mbyte & 3u);
+          uint32_t v[7];
+#pragma unroll
+          for (int k = 0; k < 7; k++) v[k] = src[k];
+#pragma unroll
+          for (int k = 0; k < 6; k++) w[k] = __funnelshift_r(v[k], v[k + 1], bits);
+        }
         if (TK_NOFADD) ycc_row8n(w, yb, cbb, crb, scr_y, scr_c);
         else ycc_row8x(w, yb, cbb, crb, scr_y, scr_c);
         *reinterpret_cast<uint2*>(ydst + 2 * dr) = make_uint2(pack4(yb[0], yb[1], yb[2], yb[3]), pack4(yb[4], yb[5], yb[6], yb[7]));
@@ -156,7 +185,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
   if (ntie > TK_TIE_COOP_MAX) {
     for (uint32_t k = lane; k < ntie; k += 32) {
       const int id = sm.ties[k];
-      tk_replay_patch(sm, half, (id & 31) >> 1, id >> 5, id & 1);
+      tk_replay_patch<ALIGNED>(sm, sh, half, (id & 31) >> 1, id >> 5, id & 1);
     }
     return;
   }
@@ -167,7 +196,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
     const uint32_t e = k + (lane >> 4);
     const int id = sm.ties[e < ntie ? e : k];
     const int tl = id & 31, tpr = id >> 5, tmcu = tl >> 1, tpc = tl & 1, tslot = half * 32 + tl;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(&sm.raw[2 * tpr + dr][tmcu * 12 + 6 * tpc]) + 3 * c;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(&sm.raw[2 * tpr + dr][0]) + sh.mcu_byte<ALIGNED>(tmcu) + 24 * tpc + 3 * c;
     const uint32_t v = ycc_pixel(src[0], src[1], src[2]);
     uint32_t cb = (v >> 8) & 0xFFu, cr = v >> 16;
     cb += __shfl_xor_sync(FULL, cb, 1); cr += __shfl_xor_sync(FULL, cr, 1);
@@ -183,17 +212,17 @@ __device__ __forceinline__ void tk_colour_half(TkSmem& sm, int half, int valid, 
   }
 }
 
-template <bool BULK>
-__global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
+template <bool ALIGNED>
+__global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
+  constexpr int TK_WARPS = TkWarps<ALIGNED>::value;
+  using TkSmem = TkSmemT<ALIGNED>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TkSmem& sm = reinterpret_cast<TkSmem*>(smem_raw)[warp];
   for (int k = lane; k < 544; k += 32) sm.hist[k] = 0;
-  if (BULK) {
-    if (lane == 0) {
-      mbar_init(&sm.full, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+  if (lane == 0) {
+    mbar_init(&sm.full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   // The CTA (one per SM, 12 warps) owns a contiguous range of tiles; its warps take them round-robin and re-align once per
@@ -206,30 +235,32 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
   const int cta_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), cta_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
   const int t_begin = cta_begin + warp, t_end = cta_end;
 
-  // Fetch the 8 pixel rows `half` of tile t.  BULK: asynchronous (lane r < 8 owns row r); otherwise synchronous byte loads.
+  // Fetch the 8 pixel rows `half` of tile t: bulk async copies (lane r < 8 owns row r), one per MCU-row run of the tile.
+  // Unaligned crops copy from the aligned-down address (see TkSmemT); the bytes read before and after the crop row belong to
+  // the same frame row or, at the frame's corners, to the 16-byte granule that holds its first / last byte.
   auto fetch = [&](const TkTile& p, const JbJob& job, int half) {
-    if (BULK) {
-      if (lane == 0) mbar_expect_tx(&sm.full, (uint32_t)p.valid * 384u);
-      __syncwarp();
-      if (lane < 8) {
-        int mcu = 0, my = p.my0, mx = p.mx0;
-        while (mcu < p.valid) {
-          const int run = min(p.valid - mcu, p.mw - mx);
-          const uint8_t* g = job.src + (size_t)(job.y + my * 16 + half * 8 + lane) * job.pitch + 3u * (uint32_t)job.x + (size_t)mx * 48;
-          bulk_g2s(&sm.raw[lane][mcu * 12], g, (uint32_t)run * 48u, &sm.full);
-          mcu += run; mx = 0; my++;
-        }
+    const uint32_t shift = ALIGNED ? 0u : (uint32_t)(((uintptr_t)job.src + 3u * (uint32_t)job.x) & 15u);
+    uint32_t tx = (uint32_t)p.valid * 384u;
+    if (!ALIGNED) {                         // per row: every run's bytes, with the shift, rounded up to 16
+      tx = 0;
+      for (int mcu = 0, mx = p.mx0; mcu < p.valid;) {
+        const int run = min(p.valid - mcu, p.mw - mx);
+        tx += (shift + (uint32_t)run * 48u + 15u) & ~15u;
+        mcu += run; mx = 0;
       }
-    } else {
-      uint8_t* rawb = reinterpret_cast<uint8_t*>(&sm.raw[0][0]);
-      for (int row = 0; row < 8; row++)
-        for (int j = lane; j < p.valid * 48; j += 32) {
-          const int mcu = j / 48, c = j - mcu * 48;
-          int my = p.my0, mx = p.mx0 + mcu;
-          while (mx >= p.mw) { mx -= p.mw; my++; }
-          rawb[row * (JB_TILE_MCUS * 48) + j] = __ldg(job.src + (size_t)(job.y + my * 16 + half * 8 + row) * job.pitch + 3u * (uint32_t)(job.x + mx * 16) + c);
-        }
-      __syncwarp();
+      tx *= 8u;
+    }
+    if (lane == 0) mbar_expect_tx(&sm.full, tx);
+    __syncwarp();
+    if (lane < 8) {
+      int mcu = 0, my = p.my0, mx = p.mx0, k = 0;
+      while (mcu < p.valid) {
+        const int run = min(p.valid - mcu, p.mw - mx);
+        const uint8_t* g = job.src + (size_t)(job.y + my * 16 + half * 8 + lane) * job.pitch + 3u * (uint32_t)job.x + (size_t)mx * 48;
+        if (ALIGNED) bulk_g2s(&sm.raw[lane][mcu * 12], g, (uint32_t)run * 48u, &sm.full);
+        else bulk_g2s(&sm.raw[lane][mcu * 12 + 4 * k], g - shift, (shift + (uint32_t)run * 48u + 15u) & ~15u, &sm.full);
+        mcu += run; mx = 0; my++; k++;
+      }
     }
   };
   auto next_valid = [&](int t, TkTile& p, JbJob& job) {      // tiles of this warp: t_begin, t_begin + TK_WARPS, ...
@@ -274,8 +305,12 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
       phase_sync(step == 0 ? 1 : 2);
       if (step < 2) {
         if (active) {
-          if (BULK) { mbar_wait(&sm.full, parity); parity ^= 1u; }
-          tk_colour_half(sm, step, p.valid, lane);
+          mbar_wait(&sm.full, parity);
+          parity ^= 1u;
+          TkShift sh;
+          sh.shift = ALIGNED ? 0u : (uint32_t)(((uintptr_t)job.src + 3u * (uint32_t)job.x) & 15u);
+          sh.mx0 = p.mx0; sh.mw = p.mw;
+          tk_colour_half<ALIGNED>(sm, sh, step, p.valid, lane);
           __syncwarp();
           if (step == 0) fetch(p, job, 1);
           else {
@@ -522,25 +557,28 @@ __global__ void __launch_bounds__(TK_WARPS * 32, TK_CTAS_PER_SM) k_pixels_to_tok
 
 }  // namespace
 
+void jb_init_grey_tokens(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
+
 // tiles_per_warp = 0: persistent grid (one CTA per SM slot, each warp walks its share of the wave); n > 0: short-lived CTAs of
 // n tiles per warp, so that the high-priority kernels of other lanes get SM slots as CTAs retire (multi-lane batches).
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st) {
   static int ctas_per_sm[2] = {0, 0}, sms = 0;
   const int v = rows_aligned ? 1 : 0;
   auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
-  const int smem = (int)sizeof(TkSmem) * TK_WARPS;
+  const int warps = rows_aligned ? TkWarps<true>::value : TkWarps<false>::value;
+  const int smem = rows_aligned ? (int)sizeof(TkSmemT<true>) * warps : (int)sizeof(TkSmemT<false>) * warps;
   if (!ctas_per_sm[v]) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, TK_WARPS * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, warps * 32, smem);
     ctas_per_sm[v] = n > 0 ? n : 1;
     if (getenv("JPEGB200_DEBUG")) fprintf(stderr, "k_pixels_to_tokens<%d>: %d SMs x %d CTAs, %d B smem (%s)\n", v, sms, n, smem, cudaGetErrorString(cudaGetLastError()));
   }
   const int mcus = (max_w / 16) * (max_h / 16), tiles_per_job = (mcus + JB_TILE_MCUS - 1) / JB_TILE_MCUS, ntiles = tiles_per_job * njobs;
-  const int want = (ntiles + TK_WARPS - 1) / TK_WARPS;
+  const int want = (ntiles + warps - 1) / warps;
   static int spare = -1;                 // CTAs left out of the persistent grid (development knob: JPEGB200_TK_SPARE)
   if (spare < 0) { const char* e = getenv("JPEGB200_TK_SPARE"); spare = e ? atoi(e) : 0; }
   int cap = sms * ctas_per_sm[v] - spare;
@@ -548,7 +586,7 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   static int iters_env = -2;             // development override: JPEGB200_TK_ITERS
   if (iters_env == -2) { const char* e = getenv("JPEGB200_TK_ITERS"); iters_env = e ? atoi(e) : -1; }
   const int iters = iters_env >= 0 ? iters_env : tiles_per_warp;
-  if (iters > 0) cap = (ntiles + TK_WARPS * iters - 1) / (TK_WARPS * iters);
+  if (iters > 0) cap = (ntiles + warps * iters - 1) / (warps * iters);
   const int grid = want < cap ? want : cap;
-  kern<<<grid, TK_WARPS * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
+  kern<<<grid, warps * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
 }

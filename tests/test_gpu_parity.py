@@ -458,7 +458,9 @@ def test_fast_dct_equals_exact_dct_large(frames):
 
 def test_token_path_small_shapes_and_crops(enc, oracle, frames):
     """Token path (the default of the batched entry points) on ragged tiles, rows narrower than a tile, tiles that
-    straddle several MCU rows, crops with unaligned origins (synchronous loader) and heterogeneous region batches."""
+    straddle several MCU rows, crops with unaligned origins (bulk copies from the aligned-down address: every byte phase
+    0..15, up to 16 MCU-row runs per tile, crops that touch the frame's right and bottom edges) and heterogeneous region
+    batches."""
     import torch
     rng = np.random.default_rng(13)
     for (h, w) in [(16, 16), (16, 272), (48, 80), (32, 528), (240, 320), (112, 48), (64, 64), (16, 4112), (400, 16), (96, 112)]:
@@ -469,7 +471,9 @@ def test_token_path_small_shapes_and_crops(enc, oracle, frames):
                 assert jp[k] == oracle.encode(batch[k])["jpg"].tobytes(), (w, h, kind, k)
     img = frames.sample_bgr("640_diffs")
     areas = [(2, 36, 112, 432), (358, 66, 256, 336), (406, 476, 192, 160), (146, 412, 176, 144), (0, 0, 16, 16), (624, 624, 16, 16),
-             (3, 5, 48, 32), (101, 7, 528, 16), (16, 32, 144, 48), (5, 0, 272, 640), (0, 0, 640, 640), (16, 16, 608, 16)]
+             (3, 5, 48, 32), (101, 7, 528, 16), (16, 32, 144, 48), (5, 0, 272, 640), (0, 0, 640, 640), (16, 16, 608, 16),
+             (5, 3, 16, 624), (623, 0, 16, 320), (1, 0, 32, 64), (9, 9, 96, 96), (7, 624, 624, 16), (11, 1, 80, 48), (13, 2, 256, 32),
+             (15, 608, 624, 32), (6, 17, 304, 64), (10, 100, 32, 512), (4, 0, 16, 16), (14, 7, 64, 16), (8, 8, 624, 624)]
     d_frame = _torch_batch(img)
     slot = 640 * 640 * 3 // 2 + 65536
     d_out = torch.zeros((len(areas), slot), dtype=torch.uint8, device="cuda")
@@ -479,6 +483,15 @@ def test_token_path_small_shapes_and_crops(enc, oracle, frames):
     sizes, out = d_sizes.cpu().numpy(), d_out.cpu().numpy()
     for i, a in enumerate(areas):
         assert out[i, : sizes[i]].tobytes() == oracle.encode(img, a)["jpg"].tobytes(), a
+    # the same crops of a grey frame: every pixel goes through the tie replay (grey-level table) of the unaligned loader
+    grey = np.ascontiguousarray(np.repeat(img[..., 1:2], 3, axis=2))
+    d_grey = _torch_batch(grey)
+    sub = areas[:4] + areas[12:20]
+    enc.encode_regions_ptr(d_grey.data_ptr(), 640, 640, sub, d_out.data_ptr(), slot, d_sizes.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    sizes, out = d_sizes.cpu().numpy(), d_out.cpu().numpy()
+    for i, a in enumerate(sub):
+        assert out[i, : sizes[i]].tobytes() == oracle.encode(grey, a)["jpg"].tobytes(), ("grey", a)
 
 
 def test_fast_dct_small_shapes_and_crops(api, oracle, frames):

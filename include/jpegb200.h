@@ -72,7 +72,11 @@ int jpegb200_encode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_bgr, int n, i
                                size_t slot, uint32_t *h_sizes);
 
 /* Encode `nareas` crops (x,y,w,h quadruples in host memory) of ONE device-resident frame; what
- * app_main does per detected region (main.c:142-153).  Asynchronous like jpegb200_encode_batch. */
+ * app_main does per detected region (main.c:142-153).  The kernels are enqueued behind `stream` and the
+ * results are stream-ordered like those of jpegb200_encode_batch, but the call itself blocks the host
+ * until the work queued on `stream` so far has finished (the workspace may have to grow and the job
+ * descriptors go through a staging buffer).  Crops may start at any pixel: rows that do not start on a
+ * 16-byte boundary are fetched by bulk copies from the aligned-down address. */
 int jpegb200_encode_regions(jpegb200_ctx *ctx, const uint8_t *d_frame, int frame_w, int frame_h, const int *areas_xywh,
                             int nareas, uint8_t *d_out, size_t slot, uint32_t *d_sizes, void *stream);
 
@@ -107,6 +111,23 @@ int jpegb200_enlarge_adjust(jpegb200_ctx *ctx, int *area_xywh, int frame_w, int 
  * seed != 0: only sub-sample and store (the start-up step, main.c:125-128); returns 0. */
 int jpegb200_compare_encode(jpegb200_ctx *ctx, const uint8_t *h_frame, int frame_w, int frame_h, int seed, int *outs_xywh,
                             uint8_t *h_out, size_t slot, uint32_t *h_sizes, uint8_t *h_sub_optional);
+
+/* The same loop for `nframes` consecutive frames in ONE call, with the hand-off from the comparator to the
+ * encoder on the device (main.c:137-162 without a host round trip between compare() and the encodes):
+ * frame f is compared with frame f-1 of the batch, frame 0 with the context's saved image (seeded by
+ * jpegb200_compare_encode(seed=1) or left by an earlier call); the last frame becomes the saved image.
+ *   frames        frame f at frames + f*frame_stride (B,G,R); host memory unless frames_on_device != 0
+ *   max_regions   region slots per frame that may be encoded (1..100); a frame's further regions are reported, not encoded
+ *   counts        [nframes]      what compare() returns for each frame
+ *   boxes_xywh    [nframes*400]  100 boxes per frame exactly as compare() leaves them (unused = -1)
+ *   sizes,offsets [nframes*max_regions]  stream of (frame f, region i) = arena[offsets[k] .. +sizes[k]), k = f*max_regions+i;
+ *                 size 0: not a well-formed crop (the > 99 overflow of brain.c:158-170), over the arena budget, or too large
+ *   arena         host memory for all streams; a region reserves w*h + 4096 bytes of it, so nframes * frame_w*frame_h
+ *                 + 4096 * nframes * max_regions is enough unless regions overlap heavily
+ * Returns the number of encoded regions, < 0 on failure.  Synchronous. */
+int jpegb200_compare_encode_batch(jpegb200_ctx *ctx, const uint8_t *frames, int frames_on_device, int nframes, int frame_w,
+                                  int frame_h, size_t frame_stride, int max_regions, int *counts, int *boxes_xywh,
+                                  uint32_t *sizes, uint64_t *offsets, uint8_t *arena, size_t arena_bytes);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ C_ABI_SYMBOLS = [
     "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_debug_fix_count",
     "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_regions",
     "jpegb200_stage_dct", "jpegb200_stage_huffman", "jpegb200_stage_write", "jpegb200_debug_build_tables",
-    "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode",
+    "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode", "jpegb200_compare_encode_batch",
 ]
 REFERENCE_SYMBOLS = ["rgb_to_dct", "init_huffman", "write_jpg", "subsample", "store", "compare", "enlargeAdjust"]
 
@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
     L.jpegb200_compare.argtypes = [vp, u8p, u8p, C.c_int, C.c_int, ip]
     L.jpegb200_enlarge_adjust.argtypes = [vp, ip, C.c_int, C.c_int]
     L.jpegb200_compare_encode.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, ip, u8p, C.c_size_t, u32p, u8p]
+    L.jpegb200_compare_encode_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, ip, ip, u32p, C.POINTER(C.c_uint64), vp, C.c_size_t]
     # the reference's own entry points (include/encoder.h, include/brain.h)
     L.jpegb200_set_dims.argtypes = [C.c_int, C.c_int]
     L.jpegb200_set_dims.restype = None
@@ -298,6 +299,36 @@ class Encoder:
         out = (HuffCode * T)()
         self._check(self.lib.jpegb200_debug_build_tables(self.ctx, freqs.ctypes.data_as(C.POINTER(C.c_int)), T, out))
         return [_huff_dict(out[i]) for i in range(T)]
+
+    def compare_encode_batch(self, frames, max_regions: int = 16, arena_bytes: int | None = None, on_device: bool = False):
+        """app_main's loop (main.c:137-162) for a batch of consecutive frames, compare -> encode hand-off on the device.
+        frames: (F, H, W, 3) uint8 numpy array (host) or, with on_device, a tuple (device pointer, F, H, W).
+        Returns (counts[F], boxes[F][100], jpgs[F][<=max_regions] (None where a region was not encoded))."""
+        if on_device:
+            ptr, F, H, W = frames
+        else:
+            frames = np.ascontiguousarray(frames)
+            F, H, W, _ = frames.shape
+            ptr = frames.ctypes.data
+        arena_bytes = arena_bytes or (F * W * H + 4096 * F * max_regions + W * H + 4096)
+        counts = np.zeros(F, np.int32)
+        boxes = np.zeros((F, 100, 4), np.int32)
+        sizes = np.zeros(F * max_regions, np.uint32)
+        offsets = np.zeros(F * max_regions, np.uint64)
+        arena = np.empty(arena_bytes, np.uint8)
+        n = self._check(self.lib.jpegb200_compare_encode_batch(
+            self.ctx, C.c_void_p(ptr), int(on_device), F, W, H, W * H * 3, max_regions, counts.ctypes.data_as(C.POINTER(C.c_int)),
+            boxes.ctypes.data_as(C.POINTER(C.c_int)), sizes.ctypes.data_as(C.POINTER(C.c_uint32)), offsets.ctypes.data_as(C.POINTER(C.c_uint64)),
+            C.c_void_p(arena.ctypes.data), arena_bytes))
+        jpgs = []
+        for f in range(F):
+            row = []
+            for i in range(min(int(counts[f]), max_regions)):
+                k = f * max_regions + i
+                row.append(arena[int(offsets[k]): int(offsets[k]) + int(sizes[k])].tobytes() if sizes[k] else None)
+            jpgs.append(row)
+        self.last_encoded = n
+        return counts, boxes, jpgs
 
     def compare_encode(self, frame: np.ndarray, seed: bool = False, slot: int | None = None):
         """One iteration of app_main's loop (main.c:137-162).  Returns (regions, jpgs, sub)."""

@@ -144,26 +144,8 @@ struct Lane {
   }
 };
 
-// Per-job workspace footprint for a w x h crop whose output slot holds `slot` bytes.
-struct JobDims {
-  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs, tchunks;
-};
-JobDims job_dims(int w, int h, size_t slot) {
-  JobDims d;
-  uint32_t nby = jb_nby(w, h), nbc = jb_nbc(w, h);
-  d.coefs = 64u * (nby + 2 * nbc);
-  d.blocks = nby + 2 * nbc;
-  d.chunks = jb_chunks(nby) + 2 * jb_chunks(nbc);
-  // un-stuffed scan bits never exceed the finished file; three scans add alignment slack
-  size_t words = (slot + 3) / 4 + 3 * 8;
-  words = (words + 3) & ~(size_t)3;
-  d.scratch_words = (uint32_t)words;
-  d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
-  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS + 3u * JB_TCHUNK;     // + the alignment of the three scans in scan order
-  d.runs = 4u * jb_runs_chroma(w, h);
-  d.tchunks = d.toks / JB_TCHUNK + 1u;
-  return d;
-}
+typedef JbJobDims JobDims;
+static JobDims job_dims(int w, int h, size_t slot) { return jb_job_dims(w, h, slot); }
 
 __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t frame_stride, int w, int h, uint8_t* out0, size_t slot,
                             JobDims d) {
@@ -206,7 +188,7 @@ struct jpegb200_ctx {
   std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> timed;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spare;
   // comparator state
-  DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_bits, cmp_outs;
+  DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_saved_in, cmp_bits, cmp_outs, cmp_rout, cmp_misc, cmp_arena;
   PinBuf cmp_host;
   bool have_saved = false;
   int saved_w = 0, saved_h = 0;
@@ -259,12 +241,12 @@ struct StageTimer {
 
 // Enqueue the chain of launches for the `njobs` jobs already described in lane.ws.jobs.
 int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_t max_blocks, uint32_t max_chunks, ChainFrom from,
-              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false, uint32_t max_runs = 0, uint32_t max_tchunks = 0) {
+              bool stop_after_dct, bool stop_after_tables, uint32_t* d_sizes, bool rows_aligned = false, uint32_t max_runs = 0, uint32_t max_tchunks = 0, bool device_jobs = false) {
   cudaStream_t st = l.stream;
   const JbWs& ws = l.ws;
-  CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
+  if (!device_jobs) CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));      // (a device-built wave has cleared it before k_region_jobs)
   if (max_runs) {             // token path: pixels -> tokens + histograms -> tables -> run bits -> scan -> bits
-    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, c->overlap_waves ? 8 : 0, st); }
+    { StageTimer t(c, st, ST_DCT); jb_launch_pixels_to_tokens(ws, njobs, max_w, max_h, rows_aligned, c->overlap_waves ? 8 : 0, st, device_jobs); }
     cudaStream_t lo = st;
     if (c->split_streams && c->overlap_waves) {   // the rest of the chain at high priority; the lane's stream rejoins at the end
       CK(cudaEventRecord(l.pass1_done, lo));
@@ -390,7 +372,7 @@ int jpegb200_create(jpegb200_ctx** out, int device) {
   jb_init_grey_tokens(nullptr);
   jb_init_grey_dct(nullptr);
   if (cudaDeviceSynchronize() != cudaSuccess) { for (auto& l : c->lanes) l.release(); delete c; return fail("grey-level table: %s", cudaGetErrorString(cudaGetLastError())); }
-  if (cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) != cudaSuccess) { delete c; return fail("cudaEventCreate failed"); }
+  if (cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming) != cudaSuccess) { for (auto& l : c->lanes) l.release(); delete c; return fail("cudaEventCreate failed"); }
   *out = c;
   return 0;
 }
@@ -400,7 +382,7 @@ void jpegb200_destroy(jpegb200_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   for (auto& l : c->lanes) l.release();
-  for (DevBuf* b : {&c->cmp_frame, &c->cmp_sub, &c->cmp_saved, &c->cmp_bits, &c->cmp_outs}) b->release();
+  for (DevBuf* b : {&c->cmp_frame, &c->cmp_sub, &c->cmp_saved, &c->cmp_saved_in, &c->cmp_bits, &c->cmp_outs, &c->cmp_rout, &c->cmp_misc, &c->cmp_arena}) b->release();
   c->cmp_host.release();
   if (c->fork) cudaEventDestroy(c->fork);
   delete c;
@@ -742,25 +724,27 @@ int jpegb200_subsample(jpegb200_ctx* c, const uint8_t* bgr, int fw, int fh, uint
   CK(c->cmp_frame.ensure(fb));
   CK(c->cmp_sub.ensure(sb));
   CK(cudaMemcpyAsync(c->cmp_frame.p, bgr, fb, cudaMemcpyHostToDevice, st));
-  jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, st);
+  jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, 1, fb, st);
   c->launches++;
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(sub, c->cmp_sub.p, sb, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
 }
 
-static int compare_on_device(jpegb200_ctx* c, const uint8_t* d_sub, const uint8_t* d_saved, int fw, int fh, int* outs_xywh, cudaStream_t st) {
+// diff mask + region replay of `nframes` sub-sampled frames (frame f against f - 1, frame 0 against d_saved); results stay on the device
+static int compare_launch(jpegb200_ctx* c, const uint8_t* d_sub, const uint8_t* d_saved, int fw, int fh, int nframes, cudaStream_t st) {
   const int sw = fw / 4, sh = fh / 4, wpr = (sw + 31) / 32;
-  CK(c->cmp_bits.ensure((size_t)wpr * sh * 4));
-  CK(c->cmp_outs.ensure(401 * sizeof(int)));
-  CK(c->cmp_host.ensure(401 * sizeof(int)));
-  jb_launch_diff_mask(d_sub, d_saved, sw, sh, (uint32_t*)c->cmp_bits.p, st);
-  jb_launch_regions((const uint32_t*)c->cmp_bits.p, fw, fh, (int*)c->cmp_outs.p, (int*)c->cmp_outs.p + 400, st);
+  CK(c->cmp_bits.ensure((size_t)nframes * wpr * sh * 4));
+  CK(c->cmp_outs.ensure((size_t)nframes * 401 * sizeof(int)));
+  int* d_outs = (int*)c->cmp_outs.p;
+  jb_launch_diff_mask(d_sub, d_saved, sw, sh, (uint32_t*)c->cmp_bits.p, nframes, st);
+  CK(cudaGetLastError());
+  if (!jb_launch_regions((const uint32_t*)c->cmp_bits.p, fw, fh, d_outs, d_outs + (size_t)nframes * 400, nframes, st))
+    return fail("frame width %d: the comparator's run lists do not fit in shared memory", fw);
+  CK(cudaGetLastError());
   c->launches += 2;
-  CK(cudaMemcpyAsync(c->cmp_host.p, c->cmp_outs.p, 401 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  memcpy(outs_xywh, c->cmp_host.p, 400 * sizeof(int));
-  return ((int*)c->cmp_host.p)[400];
+  return 0;
 }
 
 int jpegb200_compare(jpegb200_ctx* c, const uint8_t* sub, const uint8_t* saved, int fw, int fh, int* outs_xywh) {
@@ -770,13 +754,15 @@ int jpegb200_compare(jpegb200_ctx* c, const uint8_t* sub, const uint8_t* saved, 
   cudaStream_t st = c->lanes[0].stream;
   const size_t sb = (size_t)3 * fw * fh / 16;
   CK(c->cmp_sub.ensure(sb));
-  DevBuf tmp;
-  CK(tmp.ensure(sb));
+  CK(c->cmp_saved_in.ensure(sb));                // the caller's `saved` (the context keeps its own for compare_encode)
+  CK(c->cmp_host.ensure(401 * sizeof(int)));
   CK(cudaMemcpyAsync(c->cmp_sub.p, sub, sb, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(tmp.p, saved, sb, cudaMemcpyHostToDevice, st));
-  int n = compare_on_device(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)tmp.p, fw, fh, outs_xywh, st);
-  tmp.release();
-  return n;
+  CK(cudaMemcpyAsync(c->cmp_saved_in.p, saved, sb, cudaMemcpyHostToDevice, st));
+  if (compare_launch(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)c->cmp_saved_in.p, fw, fh, 1, st)) return -1;
+  CK(cudaMemcpyAsync(c->cmp_host.p, c->cmp_outs.p, 401 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(outs_xywh, c->cmp_host.p, 400 * sizeof(int));
+  return ((int*)c->cmp_host.p)[400];
 }
 
 int jpegb200_enlarge_adjust(jpegb200_ctx* c, int* area, int fw, int fh) {
@@ -787,65 +773,161 @@ int jpegb200_enlarge_adjust(jpegb200_ctx* c, int* area, int fw, int fh) {
   CK(cudaMemcpyAsync(c->cmp_outs.p, area, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
   jb_launch_enlarge_adjust((int*)c->cmp_outs.p, fw, fh, st);
   c->launches++;
+  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(area, c->cmp_outs.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;
+}
+
+// The device part of the fused loop for `nframes` frames that are already on the device: sub-sample, compare, build the jobs
+// of the changed regions on the device, encode them, store the last sub-sampled frame.  Nothing returns to the host in
+// between.  Leaves on the device: cmp_outs (boxes, counts), cmp_rout (job / offset per (frame, region slot)),
+// cmp_misc ([0..3] totals, then sizes per (frame, region slot)), cmp_arena (the streams).
+static int compare_encode_device(jpegb200_ctx* c, const uint8_t* d_frames, size_t frame_stride, int nframes, int fw, int fh, int max_regions,
+                                 size_t arena_bytes, bool seed_only) {
+  Lane& l = c->lanes[0];
+  cudaStream_t st = l.stream;
+  const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
+  CK(c->cmp_sub.ensure((size_t)nframes * sb));
+  CK(c->cmp_saved.ensure(sb));
+  if (c->have_saved && (c->saved_w != fw || c->saved_h != fh)) c->have_saved = false;
+  jb_launch_subsample(d_frames, fw, fh, (uint8_t*)c->cmp_sub.p, nframes, frame_stride, st);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (!seed_only) {
+    if (!c->have_saved) return fail("compare_encode called before a seed frame was stored");
+    if (compare_launch(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)c->cmp_saved.p, fw, fh, nframes, st)) return -1;
+    // capacities of the wave, all derived from the arena: a region reserves w*h + 4096 bytes of it (jb_region_slot)
+    const size_t J = (size_t)nframes * max_regions, P = arena_bytes;
+    const JobDims full = job_dims(fw, fh, jb_region_slot(fw, fh));
+    WaveDims wd;
+    wd.planes = false;
+    wd.njobs = J;
+    const size_t tiles = P / 4096 + J;                                         // 16-MCU pixel tiles
+    wd.toks = tiles * 3 * JB_ROUND_TOKENS + J * 3 * JB_TCHUNK;
+    wd.runs = std::min<size_t>(4 * (tiles + J * (size_t)(fh / 16 + 1)), J * (size_t)full.runs);
+    wd.tchunks = wd.toks / JB_TCHUNK + J + 1;
+    wd.scratch_words = P / 4 + J * 1060;
+    wd.tiles = 3 * (P / JB_STUFF_TILE + 4 * J);
+    wd.blocks = P / 64 * 3 / 2 + J * 8;
+    if (wd.toks > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || P > 0xFFFFFFFFull) return fail("arena too large for one wave; pass fewer frames per call");
+    CK(l.ensure(wd));
+    CK(c->cmp_rout.ensure(J * sizeof(JbRegionOut)));
+    CK(c->cmp_misc.ensure((4 + 2 * J + 1) * sizeof(uint32_t)));
+    CK(c->cmp_arena.ensure(P));
+    CK(l.sizes.ensure(J * sizeof(uint32_t)));
+    uint32_t* totals = (uint32_t*)c->cmp_misc.p;
+    uint32_t* region_sizes = totals + 4;
+    uint32_t* tile_first = region_sizes + J;
+    JbRegionBudget budget;
+    budget.jobs = (uint32_t)J; budget.toks = (uint32_t)wd.toks; budget.runs = (uint32_t)wd.runs; budget.scratch_words = (uint32_t)wd.scratch_words;
+    budget.tiles = (uint32_t)wd.tiles; budget.blocks = (uint32_t)wd.blocks; budget.arena_bytes = P;
+    CK(cudaMemsetAsync(l.jobs.p, 0, J * sizeof(JbJob), st));
+    CK(cudaMemsetAsync(l.state_hist.p, 0, l.sh_bytes, st));
+    CK(cudaMemsetAsync(l.sizes.p, 0, J * sizeof(uint32_t), st));
+    const int* d_outs = (const int*)c->cmp_outs.p;
+    jb_launch_region_jobs(l.ws, d_frames, frame_stride, fw, fh, nframes, max_regions, d_outs, d_outs + (size_t)nframes * 400, (uint8_t*)c->cmp_arena.p, budget,
+                          (JbRegionOut*)c->cmp_rout.p, totals, tile_first, st);
+    c->launches++;
+    CK(cudaGetLastError());
+    l.ws.tile_first = tile_first;
+    l.ws.live = totals;
+    c->overlap_waves = 0;
+    const int rc = run_chain(c, l, (int)J, fw, fh, full.blocks, full.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, false, full.runs, full.tchunks, true);
+    l.ws.tile_first = nullptr;
+    l.ws.live = nullptr;
+    if (rc) return -1;
+    jb_launch_region_sizes((const JbRegionOut*)c->cmp_rout.p, (const uint32_t*)l.sizes.p, region_sizes, (int)J, st);
+    c->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaMemcpyAsync(c->cmp_saved.p, (const uint8_t*)c->cmp_sub.p + (size_t)(nframes - 1) * sb, sb, cudaMemcpyDeviceToDevice, st));   // store(), brain.c:51-58
+  c->have_saved = true; c->saved_w = fw; c->saved_h = fh;
+  return 0;
+}
+
+int jpegb200_compare_encode_batch(jpegb200_ctx* c, const uint8_t* frames, int frames_on_device, int nframes, int fw, int fh, size_t frame_stride,
+                                  int max_regions, int* counts, int* boxes_xywh, uint32_t* sizes, uint64_t* offsets, uint8_t* arena, size_t arena_bytes) {
+  if (!c || !frames || !counts || !boxes_xywh || !sizes || !offsets || !arena) return fail("null argument");
+  if (nframes <= 0) return 0;
+  if (check_dims(fw, fh)) return -1;
+  if (max_regions < 1 || max_regions > JB_MAX_REGIONS) return fail("max_regions must be 1..%d", JB_MAX_REGIONS);
+  const size_t fb = (size_t)3 * fw * fh;
+  if (frame_stride < fb) return fail("frame_stride smaller than a frame");
+  if (arena_bytes < jb_region_slot(fw, fh)) return fail("arena smaller than one full-frame region (%u bytes)", jb_region_slot(fw, fh));
+  CK(cudaSetDevice(c->device));
+  Lane& l = c->lanes[0];
+  cudaStream_t st = l.stream;
+  const uint8_t* d_frames = frames;
+  if (!frames_on_device) {
+    CK(c->cmp_frame.ensure((size_t)nframes * fb));
+    CK(cudaMemcpy2DAsync(c->cmp_frame.p, fb, frames, frame_stride, fb, (size_t)nframes, cudaMemcpyHostToDevice, st));
+    d_frames = (const uint8_t*)c->cmp_frame.p;
+    frame_stride = fb;
+  }
+  if (compare_encode_device(c, d_frames, frame_stride, nframes, fw, fh, max_regions, arena_bytes, false)) return -1;
+  // one device -> host transfer of the small tables, then the bytes that were produced
+  const size_t J = (size_t)nframes * max_regions;
+  const size_t nb_outs = (size_t)nframes * 401 * sizeof(int), nb_rout = J * sizeof(JbRegionOut), nb_misc = (4 + J) * sizeof(uint32_t);
+  CK(c->cmp_host.ensure(nb_outs + nb_rout + nb_misc));
+  char* h = (char*)c->cmp_host.p;
+  CK(cudaMemcpyAsync(h, c->cmp_outs.p, nb_outs, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h + nb_outs, c->cmp_rout.p, nb_rout, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h + nb_outs + nb_rout, c->cmp_misc.p, nb_misc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const int* h_outs = (const int*)h;
+  const JbRegionOut* h_rout = (const JbRegionOut*)(h + nb_outs);
+  const uint32_t* h_tot = (const uint32_t*)(h + nb_outs + nb_rout);
+  memcpy(boxes_xywh, h_outs, (size_t)nframes * 400 * sizeof(int));
+  memcpy(counts, h_outs + (size_t)nframes * 400, (size_t)nframes * sizeof(int));
+  int encoded = 0;
+  size_t used = 0;
+  for (size_t k = 0; k < J; k++) {
+    sizes[k] = h_tot[4 + k];
+    offsets[k] = h_rout[k].offset;
+    if (h_rout[k].job >= 0 && sizes[k]) { encoded++; used = std::max(used, (size_t)h_rout[k].offset + sizes[k]); }
+  }
+  if (used) CK(cudaMemcpyAsync(arena, c->cmp_arena.p, used, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return encoded;
 }
 
 int jpegb200_compare_encode(jpegb200_ctx* c, const uint8_t* h_frame, int fw, int fh, int seed, int* outs_xywh, uint8_t* h_out, size_t slot,
                             uint32_t* h_sizes, uint8_t* h_sub) {
   if (!c || !h_frame) return fail("null argument");
   if (check_dims(fw, fh)) return -1;
+  if (!seed && (!outs_xywh || !h_out || !h_sizes)) return fail("null output argument");
   CK(cudaSetDevice(c->device));
   Lane& l = c->lanes[0];
   cudaStream_t st = l.stream;
   const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
   CK(c->cmp_frame.ensure(fb));
-  CK(c->cmp_sub.ensure(sb));
-  CK(c->cmp_saved.ensure(sb));
-  if (c->have_saved && (c->saved_w != fw || c->saved_h != fh)) c->have_saved = false;
   CK(cudaMemcpyAsync(c->cmp_frame.p, h_frame, fb, cudaMemcpyHostToDevice, st));
-  jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, st);
-  c->launches++;
+  // arena: the regions of one frame after the margin-2 merge rarely overlap; twice the frame leaves room for those that do
+  const size_t arena_bytes = 2 * ((size_t)fw * fh) + (size_t)JB_MAX_REGIONS * 4096 + jb_region_slot(fw, fh);
+  if (compare_encode_device(c, (const uint8_t*)c->cmp_frame.p, fb, 1, fw, fh, JB_MAX_REGIONS, arena_bytes, seed != 0)) return -1;
   if (h_sub) CK(cudaMemcpyAsync(h_sub, c->cmp_sub.p, sb, cudaMemcpyDeviceToHost, st));
-  int n = 0;
-  if (!seed) {
-    if (!c->have_saved) return fail("compare_encode called before a seed frame was stored");
-    if (!outs_xywh || !h_out || !h_sizes) return fail("null output argument");
-    n = compare_on_device(c, (const uint8_t*)c->cmp_sub.p, (const uint8_t*)c->cmp_saved.p, fw, fh, outs_xywh, st);
-    if (n < 0) return n;
-    const int nenc = std::min(n, JB_MAX_REGIONS);
-    if (nenc > 0) {
-      // a >99-region overflow returns raw sub-pixel boxes (brain.c:158-170); only encode well-formed crops
-      std::vector<int> ok;
-      for (int i = 0; i < nenc; i++) {
-        const int* a = outs_xywh + 4 * i;
-        bool good = a[0] >= 0 && a[1] >= 0 && a[2] > 0 && a[3] > 0 && a[2] % 16 == 0 && a[3] % 16 == 0 && a[0] + a[2] <= fw && a[1] + a[3] <= fh;
-        h_sizes[i] = 0;
-        if (good) ok.push_back(i);
-      }
-      if (!ok.empty()) {
-        const size_t dslot = (slot + 15) & ~(size_t)15;
-        CK(l.out.ensure(ok.size() * dslot));
-        CK(l.sizes.ensure(ok.size() * 4));
-        std::vector<int> areas;
-        for (int i : ok) areas.insert(areas.end(), outs_xywh + 4 * i, outs_xywh + 4 * i + 4);
-        if (jpegb200_encode_regions(c, (const uint8_t*)c->cmp_frame.p, fw, fh, areas.data(), (int)ok.size(), (uint8_t*)l.out.p, dslot,
-                                    (uint32_t*)l.sizes.p, st))
-          return -1;
-        std::vector<uint32_t> sz(ok.size());
-        CK(cudaMemcpyAsync(sz.data(), l.sizes.p, ok.size() * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        for (size_t k = 0; k < ok.size(); k++) {
-          h_sizes[ok[k]] = sz[k];
-          if (sz[k]) CK(cudaMemcpyAsync(h_out + (size_t)ok[k] * slot, (uint8_t*)l.out.p + k * dslot, sz[k], cudaMemcpyDeviceToHost, st));
-        }
-      }
-    }
+  if (seed) { CK(cudaStreamSynchronize(st)); return 0; }
+  const size_t J = JB_MAX_REGIONS;
+  const size_t nb_outs = 401 * sizeof(int), nb_rout = J * sizeof(JbRegionOut), nb_misc = (4 + J) * sizeof(uint32_t);
+  CK(c->cmp_host.ensure(nb_outs + nb_rout + nb_misc));
+  char* h = (char*)c->cmp_host.p;
+  CK(cudaMemcpyAsync(h, c->cmp_outs.p, nb_outs, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h + nb_outs, c->cmp_rout.p, nb_rout, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(h + nb_outs + nb_rout, c->cmp_misc.p, nb_misc, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));                 // the only host synchronisation before the streams are fetched
+  const int* h_outs = (const int*)h;
+  const JbRegionOut* h_rout = (const JbRegionOut*)(h + nb_outs);
+  const uint32_t* h_tot = (const uint32_t*)(h + nb_outs + nb_rout);
+  memcpy(outs_xywh, h_outs, 400 * sizeof(int));
+  const int n = h_outs[400];
+  for (int i = 0; i < std::min(n, JB_MAX_REGIONS); i++) {
+    uint32_t sz = h_rout[i].job >= 0 ? h_tot[4 + i] : 0u;
+    if (sz > slot) sz = 0;                       // the caller's slot is smaller than the stream
+    h_sizes[i] = sz;
+    if (sz) CK(cudaMemcpyAsync(h_out + (size_t)i * slot, (const uint8_t*)c->cmp_arena.p + h_rout[i].offset, sz, cudaMemcpyDeviceToHost, st));
   }
-  CK(cudaMemcpyAsync(c->cmp_saved.p, c->cmp_sub.p, sb, cudaMemcpyDeviceToDevice, st));   // store(), brain.c:51-58
   CK(cudaStreamSynchronize(st));
-  c->have_saved = true; c->saved_w = fw; c->saved_h = fh;
   return n;
 }
 

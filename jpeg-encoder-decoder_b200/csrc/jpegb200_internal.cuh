@@ -122,6 +122,8 @@ struct JbWs {
   uint32_t* tchunk_bits;  // token path: per token chunk, entropy-coded bits (zeroed per wave, accumulated by k_compact_tokens)
   uint32_t* tchunk_base;  // token path: per token chunk, bit offset inside its scan
   uint4* fixtok_list;   // token path: (job, block id inside the job, index of its first token, reserved tokens) of undecided blocks
+  const uint32_t* tile_first;   // device-built job lists (k_region_jobs) only, else null: first tile of every job in the wave's tile numbering
+  const uint32_t* live;         // device-built job lists only: [0] job slots in use, [1] output bytes placed, [2] tiles
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -146,6 +148,38 @@ __host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
   return g;
 }
 
+// Per-job workspace footprint for a w x h crop whose output slot holds `slot` bytes (host: wave planning; device: k_region_jobs).
+struct JbJobDims {
+  uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs, tchunks;
+};
+__host__ __device__ inline JbJobDims jb_job_dims(int w, int h, size_t slot) {
+  JbJobDims d;
+  const uint32_t nby = jb_nby(w, h), nbc = jb_nbc(w, h);
+  d.coefs = 64u * (nby + 2 * nbc);
+  d.blocks = nby + 2 * nbc;
+  d.chunks = jb_chunks(nby) + 2 * jb_chunks(nbc);
+  // un-stuffed scan bits never exceed the finished file; three scans add alignment slack
+  size_t words = (slot + 3) / 4 + 3 * 8;
+  words = (words + 3) & ~(size_t)3;
+  d.scratch_words = (uint32_t)words;
+  d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
+  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS + 3u * JB_TCHUNK;     // + the alignment of the three scans in scan order
+  d.runs = 4u * jb_runs_chroma(w, h);
+  d.tchunks = d.toks / JB_TCHUNK + 1u;
+  return d;
+}
+// Output bytes reserved for one region of the fused compare -> encode call: 1 byte per pixel (four times what uniform noise
+// needs at these quantisers) + headers, rounded to 16.  A stream that does not fit reports size 0 (JB_ERR_SLOT).
+__host__ __device__ inline uint32_t jb_region_slot(int w, int h) { return ((uint32_t)(w * h) + 4096u + 15u) & ~15u; }
+struct JbRegionBudget {          // capacities of the wave that k_region_jobs fills
+  uint32_t jobs, toks, runs, scratch_words, tiles, blocks;
+  size_t arena_bytes;
+};
+struct JbRegionOut {             // per (frame, region slot): job index (-1 not a job, -2 over budget) and byte offset of its stream in the arena
+  int job;
+  uint32_t offset;
+};
+
 // ---- launchers (each enqueues on `st`; defined in the k_*.cu files) -------------------------------
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st);
 void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st);
@@ -166,14 +200,17 @@ void jb_init_grey_tokens(cudaStream_t st);
 void jb_init_grey_dct(cudaStream_t st);
 
 // token path (k_tokens.cu, k_pack_runs.cu)
-void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st);
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st, bool strided = false);
 void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
 void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st);
 
 // comparator (brain.c)
-void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, cudaStream_t st);
-void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, int sh, uint32_t* d_bits, cudaStream_t st);
-void jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs /*100*4*/, int* d_n, cudaStream_t st);
+void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, int nframes, size_t frame_stride, cudaStream_t st);
+void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, int sh, uint32_t* d_bits, int nframes, cudaStream_t st);
+bool jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs /*nframes*100*4*/, int* d_n /*nframes*/, int nframes, cudaStream_t st);
+void jb_launch_region_jobs(const JbWs& ws, const uint8_t* frames, size_t frame_stride, int fw, int fh, int nframes, int max_regions, const int* d_outs, const int* d_n,
+                           uint8_t* arena, const JbRegionBudget& budget, JbRegionOut* rout, uint32_t* totals, uint32_t* tile_first, cudaStream_t st);
+void jb_launch_region_sizes(const JbRegionOut* rout, const uint32_t* job_sizes, uint32_t* sizes, int ncand, cudaStream_t st);
 void jb_launch_enlarge_adjust(int* d_area, int w, int h, cudaStream_t st);

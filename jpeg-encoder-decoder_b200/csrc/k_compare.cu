@@ -9,6 +9,11 @@
 //                 dependent (label fix-ups, swap-with-last compaction, the >99 overflow path) and has
 //                 to be replayed literally; one thread per frame walks the run lists that the bit
 //                 rows give it.  Then enlargeAdjust, the margin-2 merge and the small-box filter.
+//   k_region_jobs the hand-off to the encoder (main.c:142-153 encodes every returned region): turns the boxes of F frames
+//                 into job descriptors with their workspace and output placement, on the device: nothing returns to
+//                 the host between compare and encode.
+// All comparator kernels take a batch of frames (grid.y / grid.z / blockIdx.x = frame): frame f is compared with frame
+// f - 1 of the batch, frame 0 with the context's saved image (main.c:160 stores after every frame).
 #include "jpegb200_internal.cuh"
 
 namespace {
@@ -16,10 +21,12 @@ namespace {
 struct Box { int x, y, w, h; };
 struct Run { int beg, end, row, done; };
 
-__global__ void k_subsample(const uint8_t* __restrict__ bgr, int w, int h, uint8_t* __restrict__ sub) {
+__global__ void k_subsample(const uint8_t* __restrict__ bgr, int w, int h, uint8_t* __restrict__ sub, size_t frame_stride) {
   const int sw = w >> 2, sh = h >> 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sw * sh) return;
+  bgr += (size_t)blockIdx.y * frame_stride;
+  sub += (size_t)blockIdx.y * 3 * (size_t)sw * sh;
   const int sy = i / sw, sx = i - sy * sw;
   uint32_t acc0 = 0, acc1 = 0, acc2 = 0;     // byte 0 (B), byte 1 (G), byte 2 (R)
 #pragma unroll
@@ -36,9 +43,14 @@ __global__ void k_subsample(const uint8_t* __restrict__ bgr, int w, int h, uint8
   o[2] = (uint8_t)(acc0 >> 4);
 }
 
+// frame f = blockIdx.z: sub + f * (3 sw sh) against saved (f = 0) or the batch's frame f - 1
 __global__ void k_diff_mask(const uint8_t* __restrict__ sub, const uint8_t* __restrict__ saved, int sw, int sh, uint32_t* __restrict__ bits) {
   const int row = blockIdx.y, col = blockIdx.x * blockDim.x + threadIdx.x;
   const int wpr = (sw + 31) >> 5;
+  const size_t fb = 3 * (size_t)sw * sh;
+  if (blockIdx.z) saved = sub + (blockIdx.z - 1) * fb;
+  sub += blockIdx.z * fb;
+  bits += (size_t)blockIdx.z * wpr * sh;
   bool diff = false;
   if (col < sw) {
     const size_t i = 3 * ((size_t)row * sw + col);
@@ -82,12 +94,15 @@ __device__ void enlarge_adjust(Box* a, int fw, int fh) {     // brain.c:244-261
   if (a->y < 0) a->y = 0;
 }
 
-// One thread per frame.  Dynamic shared memory: 2 run lists of (fw/8 + 1) entries.
+// One thread per frame (blockIdx.x = frame).  Dynamic shared memory: 2 run lists of (fw/8 + 1) entries.
 __global__ void k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int* __restrict__ outs_g, int* __restrict__ n_g) {
   extern __shared__ Run s_runs[];
   __shared__ Box outs[JB_MAX_REGIONS];
   if (threadIdx.x != 0) return;
   const int sw = fw >> 2, sh = fh >> 2, wpr = (sw + 31) >> 5, cap = fw / 8 + 1;
+  bits += (size_t)blockIdx.x * wpr * sh;
+  outs_g += (size_t)blockIdx.x * 4 * JB_MAX_REGIONS;
+  n_g += blockIdx.x;
   Run* rows[2] = {s_runs, s_runs + cap};
   for (int i = 0; i < JB_MAX_REGIONS; i++) outs[i] = Box{-1, -1, -1, -1};
   int which = 0, nout = 0, ncur = 0, nprev = 0, result = -1;
@@ -189,17 +204,127 @@ __global__ void k_enlarge_adjust(int* a, int fw, int fh) {
   a[0] = b.x; a[1] = b.y; a[2] = b.w; a[3] = b.h;
 }
 
+// Device-side hand-off: one thread per (frame, region slot).  A region becomes a job when it is a well-formed crop
+// (a > 99-box overflow returns raw sub-pixel boxes, brain.c:158-170: those are reported, not encoded) and the wave's
+// budgets hold; jobs are numbered frame by frame.  Placement = exclusive prefix over the jobs' footprints (the same
+// arithmetic as the host's job_dims, jb_job_dims).  Unused descriptors stay zero: every kernel of the chain skips them.
+__global__ void __launch_bounds__(1024) k_region_jobs(JbWs ws, const uint8_t* __restrict__ frames, size_t frame_stride, int fw, int fh, int nframes,
+                                                       int max_regions, const int* __restrict__ outs_g, const int* __restrict__ n_g, uint8_t* arena,
+                                                       JbRegionBudget budget, JbRegionOut* __restrict__ rout, uint32_t* __restrict__ totals,
+                                                       uint32_t* __restrict__ tile_first) {
+  __shared__ uint32_t wsum[33];
+  __shared__ uint32_t carry[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 8) carry[tid] = 0;
+  __syncthreads();
+  const int ncand = nframes * max_regions;
+  for (int base = 0; base < ncand; base += 1024) {
+    const int c = base + tid, f = c / max_regions, i = c - f * max_regions;
+    Box b{0, 0, 0, 0};
+    bool good = false;
+    if (c < ncand) {
+      const int n = n_g[f];
+      if (i < min(n, JB_MAX_REGIONS)) {
+        const int* o = outs_g + ((size_t)f * JB_MAX_REGIONS + i) * 4;
+        b = Box{o[0], o[1], o[2], o[3]};
+        good = b.x >= 0 && b.y >= 0 && b.w > 0 && b.h > 0 && (b.w % 16) == 0 && (b.h % 16) == 0 && b.x + b.w <= fw && b.y + b.h <= fh;
+      }
+    }
+    JbJobDims d{};
+    uint32_t slot = 0;
+    if (good) { slot = jb_region_slot(b.w, b.h); d = jb_job_dims(b.w, b.h, slot); }
+    // exclusive prefixes of: jobs, tokens, runs, scratch words, stuffing tiles, output bytes, blocks, pixel tiles
+    uint32_t v[8] = {good ? 1u : 0u, d.toks, d.runs, d.scratch_words, 3u * d.tiles_per_seg, slot, d.blocks, good ? jb_tiles(b.w, b.h) : 0u}, ex[8];
+    for (int q = 0; q < 8; q++) {
+      uint32_t inc = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += n; }
+      __syncthreads();
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t w = wsum[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, winc, o); if (lane >= o) winc += n; }
+        wsum[lane] = winc - w;
+        if (lane == 31) wsum[32] = winc;
+      }
+      __syncthreads();
+      ex[q] = carry[q] + wsum[warp] + inc - v[q];
+      __syncthreads();
+      if (tid == 0) carry[q] += wsum[32];
+      __syncthreads();
+    }
+    if (c < ncand) {
+      JbRegionOut ro;
+      ro.job = -1; ro.offset = 0;
+      if (good && ex[0] < budget.jobs) tile_first[ex[0]] = ex[7];      // also for a job that is dropped below: its descriptor stays empty
+      if (good) {
+        const bool fits = ex[0] < budget.jobs && ex[1] + d.toks <= budget.toks && ex[2] + d.runs <= budget.runs && ex[3] + d.scratch_words <= budget.scratch_words &&
+                          ex[4] + 3u * d.tiles_per_seg <= budget.tiles && (size_t)ex[5] + slot <= budget.arena_bytes && ex[6] + d.blocks <= budget.blocks;
+        if (fits) {
+          JbJob j{};
+          j.src = frames + (size_t)f * frame_stride;
+          j.pitch = 3u * (uint32_t)fw;
+          j.x = b.x; j.y = b.y; j.w = b.w; j.h = b.h;
+          j.blk_off = ex[6];
+          j.tile_off = ex[4];
+          j.tiles_per_seg = d.tiles_per_seg;
+          j.scratch_off = ex[3];
+          j.scratch_cap = d.scratch_words;
+          j.out = arena + ex[5];
+          j.out_cap = slot;
+          j.src_bytes = 3u * (uint32_t)fw * (uint32_t)fh;
+          j.tok_off = ex[1];
+          j.run_off = ex[2];
+          j.tchunk_off = (ex[1] + JB_TCHUNK - 1) / JB_TCHUNK + ex[0];     // >= the sum of the earlier jobs' toks / JB_TCHUNK + 1
+          ws.jobs[ex[0]] = j;
+          ro.job = (int)ex[0];
+          ro.offset = ex[5];
+        } else {
+          ro.job = -2;                                        // over budget: reported, not encoded
+        }
+      }
+      rout[c] = ro;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { totals[0] = min(carry[0], budget.jobs); totals[1] = carry[5]; totals[2] = carry[7]; }
+}
+
+// sizes of the encoded regions back in (frame, region) order
+__global__ void k_region_sizes(const JbRegionOut* __restrict__ rout, const uint32_t* __restrict__ job_sizes, uint32_t* __restrict__ sizes, int ncand) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncand) return;
+  sizes[c] = rout[c].job >= 0 ? job_sizes[rout[c].job] : 0u;
+}
+
 }  // namespace
 
-void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, cudaStream_t st) {
+void jb_launch_region_jobs(const JbWs& ws, const uint8_t* frames, size_t frame_stride, int fw, int fh, int nframes, int max_regions, const int* d_outs, const int* d_n,
+                           uint8_t* arena, const JbRegionBudget& budget, JbRegionOut* rout, uint32_t* totals, uint32_t* tile_first, cudaStream_t st) {
+  k_region_jobs<<<1, 1024, 0, st>>>(ws, frames, frame_stride, fw, fh, nframes, max_regions, d_outs, d_n, arena, budget, rout, totals, tile_first);
+}
+void jb_launch_region_sizes(const JbRegionOut* rout, const uint32_t* job_sizes, uint32_t* sizes, int ncand, cudaStream_t st) {
+  k_region_sizes<<<(ncand + 255) / 256, 256, 0, st>>>(rout, job_sizes, sizes, ncand);
+}
+
+void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, int nframes, size_t frame_stride, cudaStream_t st) {
   int n = (w / 4) * (h / 4);
-  k_subsample<<<(n + 255) / 256, 256, 0, st>>>(d_bgr, w, h, d_sub);
+  k_subsample<<<dim3((n + 255) / 256, nframes), 256, 0, st>>>(d_bgr, w, h, d_sub, frame_stride);
 }
-void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, int sh, uint32_t* d_bits, cudaStream_t st) {
-  k_diff_mask<<<dim3((sw + 127) / 128, sh), 128, 0, st>>>(d_sub, d_saved, sw, sh, d_bits);
+void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, int sh, uint32_t* d_bits, int nframes, cudaStream_t st) {
+  k_diff_mask<<<dim3((sw + 127) / 128, sh, nframes), 128, 0, st>>>(d_sub, d_saved, sw, sh, d_bits);
 }
-void jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs, int* d_n, cudaStream_t st) {
+// Returns false when the frame is too wide for the run lists to fit in shared memory (the caller reports it).
+bool jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs, int* d_n, int nframes, cudaStream_t st) {
   size_t smem = 2 * (size_t)(w / 8 + 1) * sizeof(Run);
-  k_regions<<<1, 32, smem, st>>>(d_bits, w, h, d_outs, d_n);
+  if (smem > 200 * 1024) return false;
+  if (smem > 40 * 1024) {
+    static size_t opted = 0;
+    if (smem > opted) { if (cudaFuncSetAttribute(k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false; opted = smem; }
+  }
+  k_regions<<<nframes, 32, smem, st>>>(d_bits, w, h, d_outs, d_n);
+  return true;
 }
 void jb_launch_enlarge_adjust(int* d_area, int w, int h, cudaStream_t st) { k_enlarge_adjust<<<1, 1, 0, st>>>(d_area, w, h); }

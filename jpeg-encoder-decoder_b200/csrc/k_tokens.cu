@@ -92,8 +92,18 @@ struct TkTile {
   int job, tile, m0, valid, mw, my0, mx0;
 };
 __device__ __forceinline__ bool tk_tile(const JbWs& ws, int t, int tiles_per_job, TkTile& p, JbJob& job) {
-  p.job = t / tiles_per_job;
-  p.tile = t - p.job * tiles_per_job;
+  if (ws.tile_first) {                       // device-built job list: the job whose tile range holds t
+    int lo = 0, hi = (int)ws.live[0];
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)ws.tile_first[mid] <= t) lo = mid; else hi = mid;
+    }
+    p.job = lo;
+    p.tile = t - (int)ws.tile_first[lo];
+  } else {
+    p.job = t / tiles_per_job;
+    p.tile = t - p.job * tiles_per_job;
+  }
   job = ws.jobs[p.job];
   p.mw = job.w / 16;
   const int nm = p.mw * (job.h / 16);
@@ -213,7 +223,7 @@ __device__ __forceinline__ void tk_colour_half(TkSmemT<ALIGNED>& sm, const TkShi
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic) {
+__global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic, int strided) {
   constexpr int TK_WARPS = TkWarps<ALIGNED>::value;
   using TkSmem = TkSmemT<ALIGNED>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -232,7 +242,12 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
   // 282 (per phase); three 4-warp CTAs 281-296.  Round 2 tried the opposite, too: the three warps of a scheduler held one
   // sub-phase apart (colour / DCT / token walk, a barrier at every sub-phase boundary) so that their pipes would complement
   // each other: 589 us per 64 frames against 454; no barrier at all: 494.  In-phase warps win because of instruction fetch.
-  const int cta_begin = (int)((long long)ntiles * blockIdx.x / gridDim.x), cta_end = (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+  // `strided` (device-built job lists, k_region_jobs: the number of tiles is known on the device only, the grid is sized
+  // for the worst case): the CTAs interleave instead, tile t -> CTA (t / TK_WARPS) mod grid.
+  if (strided) ntiles = (int)ws.live[2];      // tiles of the live jobs (k_region_jobs)
+  const int cta_begin = strided ? (int)blockIdx.x * TK_WARPS : (int)((long long)ntiles * blockIdx.x / gridDim.x);
+  const int cta_end = strided ? ntiles : (int)((long long)ntiles * (blockIdx.x + 1) / gridDim.x);
+  const int tstep = strided ? (int)gridDim.x * TK_WARPS : TK_WARPS;
   const int t_begin = cta_begin + warp, t_end = cta_end;
 
   // Fetch the 8 pixel rows `half` of tile t: bulk async copies (lane r < 8 owns row r), one per MCU-row run of the tile.
@@ -264,7 +279,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
     }
   };
   auto next_valid = [&](int t, TkTile& p, JbJob& job) {      // tiles of this warp: t_begin, t_begin + TK_WARPS, ...
-    while (t < t_end && !tk_tile(ws, t, tiles_per_job, p, job)) t += TK_WARPS;
+    while (t < t_end && !tk_tile(ws, t, tiles_per_job, p, job)) t += tstep;
     return t;
   };
   // TK_SYNC: 1 = the CTA's warps re-align once per tile, 2 = once per step, 3 = before every phase
@@ -289,7 +304,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
   JbJob job, jobn;
   int t = next_valid(t_begin, p, job);
   if (t < t_end) fetch(p, job, 0);
-  const int niter = (cta_end - cta_begin + TK_WARPS - 1) / TK_WARPS;
+  const int niter = cta_end > cta_begin ? (cta_end - cta_begin + tstep - 1) / tstep : 0;
 #pragma unroll 1
   for (int it = 0; it < niter; it++) {
     const bool active = t < t_end;                  // warp-uniform; idle warps only keep the CTA's barriers company
@@ -314,7 +329,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
           __syncwarp();
           if (step == 0) fetch(p, job, 1);
           else {
-            tn = next_valid(t + TK_WARPS, pn, jobn);
+            tn = next_valid(t + tstep, pn, jobn);
             if (tn < t_end) fetch(pn, jobn, 0);
           }
         }
@@ -561,7 +576,7 @@ void jb_init_grey_tokens(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
 
 // tiles_per_warp = 0: persistent grid (one CTA per SM slot, each warp walks its share of the wave); n > 0: short-lived CTAs of
 // n tiles per warp, so that the high-priority kernels of other lanes get SM slots as CTAs retire (multi-lane batches).
-void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st) {
+void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st, bool strided) {
   static int ctas_per_sm[2] = {0, 0}, sms = 0;
   const int v = rows_aligned ? 1 : 0;
   auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
@@ -588,5 +603,5 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   const int iters = iters_env >= 0 ? iters_env : tiles_per_warp;
   if (iters > 0) cap = (ntiles + warps * iters - 1) / (warps * iters);
   const int grid = want < cap ? want : cap;
-  kern<<<grid, warps * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f);
+  kern<<<grid, warps * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f, strided ? 1 : 0);
 }

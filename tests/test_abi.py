@@ -28,7 +28,7 @@ def lib():
 def test_every_declared_symbol_is_exported(lib):
     names = set(_declared("jpegb200.h") + _declared("encoder.h") + _declared("brain.h"))
     assert {"rgb_to_dct", "init_huffman", "write_jpg", "subsample", "store", "compare", "enlargeAdjust"} <= names
-    assert {"jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_compare_encode"} <= names
+    assert {"jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_compare_encode", "jpegb200_compare_encode_batch"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), n
     assert set(pkg.C_ABI_SYMBOLS) | set(pkg.REFERENCE_SYMBOLS) <= names

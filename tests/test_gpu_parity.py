@@ -343,6 +343,73 @@ def test_comparator_golden_flow(api, enc, oracle, frames, golden):
     assert regions == []
 
 
+def _moving_sequence(frames, n, seed=5):
+    """n frames of a 640x640 scene: the seed sample with rectangles of the `diffs` sample (and a few flat patches) pasted
+    at changing places, so that consecutive frames differ in a handful of regions, sometimes none, sometimes many."""
+    rng = np.random.default_rng(seed)
+    A, B = frames.sample_bgr("640"), frames.sample_bgr("640_diffs")
+    seq = []
+    for f in range(n):
+        img = A.copy()
+        for _ in range(int(rng.integers(0, 5)) if f % 7 else 0):
+            w, h = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+            x, y = int(rng.integers(0, 640 - w)), int(rng.integers(0, 640 - h))
+            if rng.integers(0, 3):
+                img[y:y + h, x:x + w] = B[y:y + h, x:x + w]
+            else:
+                img[y:y + h, x:x + w] = rng.integers(0, 256, 3, dtype=np.uint8)
+        seq.append(img)
+    seq[3] = seq[2].copy()                         # an unchanged frame
+    seq[5] = rng.integers(0, 256, (640, 640, 3), dtype=np.uint8)     # everything changes: > 99 boxes (brain.c:158-170)
+    return np.stack(seq)
+
+
+def test_compare_encode_batch_vs_oracle(enc, oracle, frames):
+    """The fused loop for 64 frames in one call (device-side compare -> encode hand-off) against the oracle run frame by frame
+    in app_main's order (main.c:137-162): counts, all 100 boxes of every frame, every region's JPEG bytes."""
+    F, R = 64, 12
+    seq = _moving_sequence(frames, F + 1)
+    enc.compare_encode(seq[0], seed=True)
+    counts, boxes, jpgs = enc.compare_encode_batch(seq[1:], max_regions=R)
+    saved = oracle.subsample(seq[0])
+    nenc = 0
+    for f in range(F):
+        img = seq[1 + f]
+        sub = oracle.subsample(img)
+        n, outs = oracle.compare(sub, saved, 640, 640)
+        assert int(counts[f]) == n, (f, int(counts[f]), n)
+        assert [tuple(int(v) for v in b) for b in boxes[f]] == outs, f
+        for i in range(min(n, 100, R)):
+            x, y, w, h = outs[i]
+            good = x >= 0 and y >= 0 and w > 0 and h > 0 and w % 16 == 0 and h % 16 == 0 and x + w <= 640 and y + h <= 640
+            if good:
+                assert jpgs[f][i] == oracle.encode(img, outs[i])["jpg"].tobytes(), (f, i, outs[i])
+                nenc += 1
+            else:
+                assert jpgs[f][i] is None, (f, i, outs[i])
+        saved = sub
+    assert nenc == enc.last_encoded and nenc > 40
+    # the context's saved image is now the last frame: the same frame again changes nothing
+    counts, _, _ = enc.compare_encode_batch(seq[-1:], max_regions=R)
+    assert int(counts[0]) == 0
+    # frames already on the device, full-HD, and an arena that is too small for everything: what does not fit reports size 0
+    import torch
+    big = np.stack([frames.natural_frame(f) for f in (0, 300, 301, 0)])
+    enc.compare_encode(big[0], seed=True)
+    d = torch.from_numpy(big[1:]).cuda()
+    counts, boxes, jpgs = enc.compare_encode_batch((d.data_ptr(), 3, 1280, 1920), max_regions=4, on_device=True)
+    saved = oracle.subsample(big[0])
+    for f in range(3):
+        sub = oracle.subsample(big[1 + f])
+        n, outs = oracle.compare(sub, saved, 1920, 1280)
+        assert int(counts[f]) == n
+        for i in range(min(n, 4)):
+            if jpgs[f][i] is not None:
+                assert jpgs[f][i] == oracle.encode(big[1 + f], outs[i])["jpg"].tobytes(), (f, i)
+        saved = sub
+    assert any(j is not None for row in jpgs for j in row)
+
+
 def test_subsample_ppm_file(api, frames, tmp_path, golden):
     p = str(tmp_path / "sub.ppm")
     api.subsample(frames.sample_bgr("640"), path=p)

@@ -14,10 +14,16 @@ encodes its own 1024 frames, no data-path collective — frames are independent,
   cpu_baseline : the reference's own C (oracle/_ref/libref.so, built from /root/reference by oracle/Makefile)
                  timed on this box's host cores, one process per core, on a bounded sample of the workload
 
+  parity_checked : SHA-256 of frames 0/1/121/1023 of the timed batch's output against tests/golden/golden.json (outside
+                 every timed region): the bytes that were timed are the reference's bytes
+  sub_records  : the other workloads of BASELINE.json (noise and ramp classes, config 5 = 3840x2160, config 3 = the
+                 comparator loop through jpegb200_compare_encode_batch beside the reference's loop on the host cores)
+
 `--impl reference` times only that CPU arm (all host cores) and prints the same JSON shape.
 """
 import argparse
 import ctypes
+import hashlib
 import importlib
 import json
 import multiprocessing as mp
@@ -75,6 +81,27 @@ def cpu_arm(frames_per_proc: int, nproc: int, reps: int = 1):
                 seconds=wall, per_core_mpix_s=float(np.median(per_core)), jpeg_bytes_per_frame=sum(r[1] for r in res) / nframes)
 
 
+def _cpu_loop_worker(args):
+    w, h, nframes, seed = args
+    import cpu_checkers
+    seq = frames_mod().moving_sequence(nframes, w, h, seed)
+    chk = cpu_checkers.Ref() if cpu_checkers.Ref.available() else cpu_checkers.Oracle()
+    chk.time_loop(seq[:2])
+    sec, regions, nbytes = chk.time_loop(seq)
+    return sec, regions, nbytes, nframes - 1, "reference" if cpu_checkers.Ref.available() else "port"
+
+
+def cpu_loop_arm(w: int, h: int, nframes: int, nproc: int):
+    """app_main's loop (subsample -> compare -> encode regions -> store, main.c:137-162) of the reference C on `nproc`
+    host cores, every process on the same scene (frames_mod().moving_sequence)."""
+    ctx = mp.get_context("fork")
+    with ctx.Pool(nproc) as pool:
+        res = pool.map(_cpu_loop_worker, [(w, h, nframes, 5)] * nproc)
+    wall = max(r[0] for r in res)
+    return dict(frames_per_s=sum(r[3] for r in res) / wall, cores=nproc, kind=res[0][4], regions_per_frame=res[0][1] / res[0][3],
+                sample=f"{nframes - 1} frames of the {w}x{h} moving scene per process x {nproc} processes, timed inside C")
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -127,6 +154,7 @@ def main():
     ap.add_argument("--e2e-lanes", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (noise / ramp / 3840x2160 / comparator loop)")
     ap.add_argument("--cpu-frames-per-proc", type=int, default=12)
     a = ap.parse_args()
     globals()["KIND"] = a.kind
@@ -156,7 +184,10 @@ def main():
         v = float(np.mean([r["value"] for r in used]))
         r = used[-1]
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "Mpix/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1000 * float(np.mean([x["seconds"] for x in used])), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": 1000 * float(np.mean([x["seconds"] for x in used])),
+                "step_sample": f"one reference step = {r['sample']} (a bounded sample of the 1024-frame workload; ms_per_step is the time of that sample, "
+                               f"value = its frames x Mpix / that time)",
+                "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
                                  "per_core_mpix_s": r["per_core_mpix_s"]},
@@ -171,6 +202,10 @@ def main():
         cpu = cpu_arm(a.cpu_frames_per_proc, ncores)
         single = cpu_arm(min(a.cpu_frames_per_proc, 8), 1)
         cpu["single_thread_mpix_s"] = single["value"]
+    cpu_loops = {}
+    if rank == 0 and world == 1 and not a.no_cpu and not a.no_sub:
+        for (lw, lh, lf) in ((640, 640, 33), (1920, 1280, 9)):
+            cpu_loops[(lw, lh)] = (cpu_loop_arm(lw, lh, lf, ncores), cpu_loop_arm(lw, lh, lf, 1))
 
     import torch
     import torch.distributed as dist
@@ -214,6 +249,18 @@ def main():
     sizes = d_sizes.cpu().numpy().astype(np.int64)
     assert (sizes > 0).all(), "an output did not fit its slot"
     jpeg_bytes = int(sizes.sum())
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["synthetic"]
+
+    def parity(kind, w, h, first_frame, nfr, out, szs):
+        """SHA-256 of the frames of this batch that tests/golden/golden.json pins (outputs of the reference itself)."""
+        res = []
+        for f in (0, 1, 121, 1023, 7):
+            key = f"{kind}_{w}x{h}_f{f}"
+            i = f - first_frame
+            if key in golden and 0 <= i < nfr:
+                got = hashlib.sha256(out[i, : int(szs[i])].cpu().numpy().tobytes()).hexdigest()
+                res.append({"frame": f, "bytes": int(szs[i]), "sha256_matches_reference": got == golden[key]["sha256"]})
+        return res
     # bookkeeping only (outside every timed region): the global (rank, offset, size) table a caller needs to find frame f's
     # stream in rank r's output; the data path itself has no collective
     shard = importlib.import_module("jpeg-encoder-decoder_b200.sharding")
@@ -235,6 +282,8 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = enc.launches - l0
     k1_ms, k1_n = get_timing(enc)
+    parity_checked = parity(a.kind, W, H, first, n, d_out, d_sizes.cpu().numpy())      # the output of the last timed step
+    assert all(p["sha256_matches_reference"] for p in parity_checked), parity_checked
     # the same kernel timed alone (one lane: no other kernel shares the SMs), as a second reading for the roofline object:
     # in the timed region above its launches are time-sliced with the high-priority kernels of the other lanes
     enc.configure(a.frames_per_wave, 1)
@@ -287,6 +336,95 @@ def main():
                "d2h_bytes_per_step": world * (jpeg_bytes + 4 * n), "ms_per_step": 1000 * dt / a.steps,
                "api": "jpegb200_encode_batch_host (pinned host buffers)", "frames_per_wave": a.e2e_frames_per_wave, "lanes": a.e2e_lanes}
 
+    # ---- sub-records (N = 1 only): the other workloads BASELINE.json names, each measured like `value` but with fewer steps
+    sub_records = []
+    if rank == 0 and world == 1 and not a.no_sub:
+        peaks0 = {}
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak0 = float(peaks0.get("hbm_gbs", 6650.0))
+        del d_in, d_out
+        if not a.no_e2e:
+            del h_in, h_out
+        torch.cuda.empty_cache()
+        enc.configure(a.frames_per_wave, a.lanes)
+
+        def device_record(kind, sw_, sh_, nfr, label):
+            x = torch.empty((nfr, sh_, sw_, 3), dtype=torch.uint8, device=dev)
+            if kind == "natural":
+                tile_ = torch.from_numpy(fr.tile_bgr(sw_, sh_)).to(dev)
+                for i in range(nfr):
+                    dx, dy = fr.natural_shift(i, sw_, sh_)
+                    x[i] = torch.roll(tile_, shifts=(dy, dx), dims=(0, 1))
+            else:
+                for i in range(nfr):
+                    x[i] = torch.from_numpy(fr.GENERATORS[kind](i, sw_, sh_)).to(dev)
+            slot_ = max(1024 * 1024, sw_ * sh_) if kind == "noise" else (SLOT if sw_ * sh_ <= 1920 * 1280 else 2 * 1024 * 1024)
+            o = torch.zeros((nfr, slot_), dtype=torch.uint8, device=dev)
+            z = torch.zeros(nfr, dtype=torch.int32, device=dev)
+
+            def st_():
+                enc.encode_batch_ptr(x.data_ptr(), nfr, sw_, sh_, sw_ * sh_ * 3, o.data_ptr(), slot_, z.data_ptr(), stream.cuda_stream)
+
+            for _ in range(3):
+                st_()
+            torch.cuda.synchronize()
+            zs = z.cpu().numpy().astype(np.int64)
+            assert (zs > 0).all(), (label, "an output did not fit its slot")
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            ea.record(stream)
+            for _ in range(reps):
+                st_()
+            eb.record(stream)
+            torch.cuda.synchronize()
+            msr = ea.elapsed_time(eb) / reps
+            alg = sw_ * sh_ * 3 + zs.sum() / nfr
+            rec = {"workload": label, "metric": f"Mpix/s JPEG encode ({sw_}x{sh_} 4:2:0 batch)", "value": nfr * sw_ * sh_ / 1e6 / (msr / 1e3), "unit": "Mpix/s",
+                   "frames": nfr, "steps": reps, "warmup": 3, "ms_per_step": msr, "jpeg_bytes_per_frame": float(zs.sum() / nfr),
+                   "whole_step": {"achieved": alg * nfr / (msr / 1e3) / 1e9, "frac": alg * nfr / (msr / 1e3) / 1e9 / peak0, "unit": "GB/s", "peak": peak0},
+                   "parity_checked": parity(kind, sw_, sh_, 0, nfr, o, zs)}
+            assert all(p_["sha256_matches_reference"] for p_ in rec["parity_checked"]), rec
+            del x, o, z
+            torch.cuda.empty_cache()
+            return rec
+
+        sub_records.append(device_record("noise", 1920, 1280, 128, "config 4, class 'noise': 128 x 1920x1280 (splitmix64 bytes: every block busy, 632 KB per frame)"))
+        sub_records.append(device_record("ramp", 1920, 1280, 128, "config 4, class 'ramp': 128 x 1920x1280 (R=G=B=(x+y+f)&255: every pixel on an exact-integer colour boundary)"))
+        sub_records.append(device_record("natural", 3840, 2160, 256, "config 5: 256 x 3840x2160 natural"))
+
+        # config 3: the comparator loop (main.c:137-162) through jpegb200_compare_encode_batch with HOST frames: H2D of the frames,
+        # subsample + compare + device-built region jobs + encode, D2H of the streams, all inside the timed region
+        for (lw, lh, nf) in ((640, 640, 65), (1920, 1280, 33)):
+            seq = fr.moving_sequence(nf, lw, lh, 5)
+            hs = torch.empty(seq.shape, dtype=torch.uint8, pin_memory=True)
+            hs.copy_(torch.from_numpy(seq))
+            host = hs.numpy()
+            enc.compare_encode(host[0], seed=True)
+            counts, boxes, jpgs = enc.compare_encode_batch(host[1:], max_regions=16)
+            enc.compare_encode(host[0], seed=True)
+            enc.compare_encode_batch(host[1:], max_regions=16)
+            torch.cuda.synchronize()
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                enc.compare_encode(host[0], seed=True)
+                enc.compare_encode_batch(host[1:], max_regions=16)
+            dt = (time.perf_counter() - t0) / reps
+            nreg = sum(1 for row in jpgs for j in row if j is not None)
+            rec = {"workload": f"config 3: comparator loop, {nf - 1} frames of a {lw}x{lh} moving scene per call (seed + jpegb200_compare_encode_batch, host frames in, "
+                               f"streams out)", "metric": "frames/s subsample+compare+encode regions+store", "value": (nf - 1) / dt, "unit": "frames/s",
+                   "regions_per_frame": nreg / (nf - 1), "jpeg_bytes": int(sum(len(j) for row in jpgs for j in row if j is not None)),
+                   "ms_per_call": 1000 * dt, "steps": reps, "warmup": 2}
+            if (lw, lh) in cpu_loops:
+                multi, single1 = cpu_loops[(lw, lh)]
+                rec["cpu_baseline"] = {"value": multi["frames_per_s"], "unit": "frames/s", "cores": multi["cores"], "kind": multi["kind"], "sample": multi["sample"],
+                                       "single_thread_frames_per_s": single1["frames_per_s"], "regions_per_frame": multi["regions_per_frame"]}
+            sub_records.append(rec)
+            del hs
+
     if rank == 0:
         peaks = {}
         try:
@@ -305,21 +443,28 @@ def main():
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json")))["dram_bytes_per_frame"] * frames_per_launch
             except Exception:
                 pass
-            roof = {"bound": "hbm", "kernel": "k_pixels_to_tokens", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
-                    "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n, "frames_per_launch": frames_per_launch,
+            # `achieved` / `frac` come from the kernel's EXCLUSIVE duration (single lane: nothing else on the SMs; CUDA events on its
+            # stream).  Inside the timed region its launches are time-sliced with the high-priority pass-2 kernels of the other
+            # lanes, so an event pair around a launch there measures elapsed time, not kernel time: reported under `in_region`.
+            iso_avg_ms = iso_ms / iso_n if iso_n else k1_avg_ms
+            iso_fpl = iso_frames if iso_n else frames_per_launch
+            ach_iso = alg_per_frame * iso_fpl / (iso_avg_ms / 1e3) / 1e9
+            roof = {"bound": "hbm", "kernel": "k_pixels_to_tokens", "achieved": ach_iso, "peak": peak, "unit": "GB/s", "frac": ach_iso / peak,
+                    "traffic": None if traffic is None else traffic * iso_fpl / frames_per_launch,
+                    "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
+                    "duration": "exclusive: the kernel alone on the GPU (single lane), CUDA events on its stream, live in this run",
+                    "avg_launch_ms": iso_avg_ms, "launches_timed": iso_n, "frames_per_launch": iso_fpl,
                     "algorithmic_bytes_per_frame": alg_per_frame,
-                    "isolated": None if not iso_n else {
-                        "what": "same kernel, single lane (nothing else on the SMs), CUDA events on its stream",
-                        "avg_launch_ms": iso_ms / iso_n, "frames_per_launch": iso_frames,
-                        "achieved": alg_per_frame * iso_frames / (iso_ms / iso_n / 1e3) / 1e9,
-                        "frac": alg_per_frame * iso_frames / (iso_ms / iso_n / 1e3) / 1e9 / peak},
+                    "in_region": {"what": "event pairs around the kernel's launches inside the timed region: elapsed time under time-slicing "
+                                          "with the other lanes' high-priority kernels, not an exclusive duration",
+                                  "avg_launch_ms": k1_avg_ms, "launches_timed": k1_n, "frames_per_launch": frames_per_launch,
+                                  "achieved": ach, "frac": ach / peak},
                     "whole_step": {"achieved": alg_per_frame * n / (ms_per_step / 1e3) / 1e9, "frac": alg_per_frame * n / (ms_per_step / 1e3) / 1e9 / peak}}
         line = {"metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core_mpix_s", "single_thread_mpix_s")},
-                "clocks": clk.summary(), "jpeg_bytes_per_frame": jpeg_bytes / n}
+                "clocks": clk.summary(), "jpeg_bytes_per_frame": jpeg_bytes / n, "parity_checked": parity_checked, "sub_records": sub_records}
         print(json.dumps(line))
     enc.close()
     if world > 1:

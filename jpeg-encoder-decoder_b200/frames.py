@@ -133,6 +133,30 @@ def ramp_frame(f: int, w: int = 1920, h: int = 1280) -> np.ndarray:
     return np.ascontiguousarray(np.repeat(v[:, :, None], 3, axis=2))
 
 
+def moving_sequence(n: int, w: int = 640, h: int = 640, seed: int = 5) -> np.ndarray:
+    """(n, h, w, 3) frames of one scene for the comparator workload (BASELINE.json config 3, app_main's loop main.c:137-162):
+    the seed image (640x640 sample / natural tile) with rectangles of its `diffs` counterpart (or flat patches) pasted at
+    changing places, so that consecutive frames differ in a handful of regions; every 7th frame repeats the plain scene."""
+    rng = np.random.default_rng(seed)
+    if (w, h) == (640, 640):
+        A, B = sample_bgr("640"), sample_bgr("640_diffs")
+    else:
+        A = tile_bgr(w, h)
+        B = np.ascontiguousarray(np.roll(A, (h // 2 // 16 * 16, 640), axis=(0, 1)))
+    out = np.empty((n, h, w, 3), np.uint8)
+    for f in range(n):
+        img = A.copy()
+        for _ in range(int(rng.integers(1, 5)) if f % 7 else 0):
+            rw, rh = int(rng.integers(8, w // 3)), int(rng.integers(8, h // 3))
+            x, y = int(rng.integers(0, w - rw)), int(rng.integers(0, h - rh))
+            if rng.integers(0, 3):
+                img[y:y + rh, x:x + rw] = B[y:y + rh, x:x + rw]
+            else:
+                img[y:y + rh, x:x + rw] = rng.integers(0, 256, 3, dtype=np.uint8)
+        out[f] = img
+    return out
+
+
 GENERATORS = {"natural": natural_frame, "noise": noise_frame, "ramp": ramp_frame}
 
 

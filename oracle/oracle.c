@@ -516,3 +516,35 @@ int orc_compare(const uint8_t *sub, const uint8_t *saved, int frame_w, int frame
   }
   return nout & 0xFF;
 }
+
+/* app_main's steady-state loop (main/main.c:137-162) over `nframes` frames, timed: subsample -> compare -> encode every
+ * well-formed region -> store.  `saved` is seeded from frame 0 (not timed).  bench.py's CPU arm for the comparator
+ * workload when the reference itself is not built (oracle/_ref). */
+double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int *regions_out, size_t *bytes_out) {
+  size_t npix = (size_t)w * h;
+  uint8_t *jpg = malloc(3 * npix), *sub = malloc(3 * npix / 16), *saved = malloc(3 * npix / 16);
+  area_t outs[100];
+  memset(jpg, 0, 3 * npix);
+  orc_subsample(frames, w, h, saved);
+  size_t total = 0;
+  int regions = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int f = 1; f < nframes; f++) {
+    const uint8_t *raw = frames + (size_t)f * frame_stride;
+    orc_subsample(raw, w, h, sub);
+    int n = orc_compare(sub, saved, w, h, outs);
+    for (int i = 0; i < n && i < 100; i++) {
+      area_t a = outs[i];
+      if (a.x < 0 || a.y < 0 || a.w <= 0 || a.h <= 0 || a.w % 16 || a.h % 16 || a.x + a.w > w || a.y + a.h > h) continue;
+      total += orc_encode(raw, w, a, jpg);
+      regions++;
+    }
+    memcpy(saved, sub, 3 * npix / 16);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (regions_out) *regions_out = regions;
+  if (bytes_out) *bytes_out = total;
+  free(jpg); free(sub); free(saved);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}

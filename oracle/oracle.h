@@ -43,6 +43,7 @@ void orc_enlarge_adjust(area_t *a, int frame_w, int frame_h);                   
 
 /* bench helper: seconds for reps x nframes full-frame encodes */
 double orc_time_encode(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int reps, size_t *bytes_out);
+double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int *regions_out, size_t *bytes_out);
 
 extern const uint64_t orc_cos_bits[64];
 extern const int orc_quant_luma[64], orc_quant_chroma[64], orc_zigzag[64];

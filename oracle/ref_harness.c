@@ -83,6 +83,43 @@ double ref_time_encode(uint8_t *frames, int nframes, size_t frame_stride, int re
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
 
+/* app_main's steady-state loop (main/main.c:137-162) over `nframes` frames, timed: subsample -> compare -> encode every
+ * well-formed region -> store.  `saved` is seeded from frame 0 (not timed), frames 1.. are processed.  Used by bench.py
+ * for the comparator workload (BASELINE.json config 3). */
+double ref_time_loop(uint8_t *frames, int nframes, size_t frame_stride, int *regions_out, size_t *bytes_out) {
+  size_t npix = (size_t)ref_width * ref_height;
+  int16_t *Y = malloc(npix * sizeof(int16_t)), *Cb = malloc(npix / 4 * sizeof(int16_t)), *Cr = malloc(npix / 4 * sizeof(int16_t));
+  uint8_t *jpg = malloc(3 * npix), *sub = malloc(3 * npix / 16), *saved = malloc(3 * npix / 16);
+  huff_code *luma = calloc(2, sizeof(huff_code)), *chroma = calloc(2, sizeof(huff_code));
+  pair_t *diffs = malloc(sizeof(pair_t) * 2 * (size_t)(ref_width / 8 + 1));
+  area_t outs[100];
+  memset(Y, 0, npix * 2);
+  memset(jpg, 0, 3 * npix);
+  subsample(get_sink(), frames, sub);
+  store(sub, saved);
+  size_t total = 0;
+  int regions = 0;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int f = 1; f < nframes; f++) {
+    uint8_t *raw = frames + (size_t)f * frame_stride;
+    subsample(get_sink(), raw, sub);
+    int n = compare(sub, saved, outs, (void *)diffs);
+    for (int i = 0; i < n && i < 100; i++) {
+      area_t a = outs[i];
+      if (a.x < 0 || a.y < 0 || a.w <= 0 || a.h <= 0 || a.w % 16 || a.h % 16 || a.x + a.w > ref_width || a.y + a.h > ref_height) continue;
+      total += ref_encode(raw, a.x, a.y, a.w, a.h, Y, Cb, Cr, luma, chroma, jpg);
+      regions++;
+    }
+    store(sub, saved);
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (regions_out) *regions_out = regions;
+  if (bytes_out) *bytes_out = total;
+  free(Y); free(Cb); free(Cr); free(jpg); free(sub); free(saved); free(luma); free(chroma); free(diffs);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 /* Comparator building blocks with caller buffers. */
 void ref_subsample(uint8_t *bgr, uint8_t *sub) { subsample(get_sink(), bgr, sub); }
 

@@ -93,6 +93,8 @@ class Oracle(_Base):
         L.orc_diff_mask.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_time_encode.restype = C.c_double
+        L.orc_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.orc_time_loop.restype = C.c_double
 
     def encode(self, bgr, area=None):
         H, W, _ = bgr.shape
@@ -144,6 +146,14 @@ class Oracle(_Base):
         return s, nb.value
 
 
+    def time_loop(self, frames):
+        """app_main's loop over frames[1:] with frames[0] as the seed.  Returns (seconds, regions encoded, jpeg bytes)."""
+        N, H, W, _ = frames.shape
+        nr, nb = C.c_int(0), C.c_size_t(0)
+        s = self.lib.orc_time_loop(_u8(frames), N, H * W * 3, W, H, C.byref(nr), C.byref(nb))
+        return s, nr.value, nb.value
+
+
 class Ref(_Base):
     name = "reference"
 
@@ -164,6 +174,8 @@ class Ref(_Base):
         L.ref_enlarge_adjust.argtypes = [C.POINTER(Area)]
         L.ref_time_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
         L.ref_time_encode.restype = C.c_double
+        L.ref_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
+        L.ref_time_loop.restype = C.c_double
 
     def encode(self, bgr, area=None):
         H, W, _ = bgr.shape
@@ -208,3 +220,10 @@ class Ref(_Base):
         nb = C.c_size_t(0)
         s = self.lib.ref_time_encode(_u8(frames), N, H * W * 3, reps, C.byref(nb))
         return s, nb.value
+
+    def time_loop(self, frames):
+        N, H, W, _ = frames.shape
+        self.lib.ref_set_dims(W, H)
+        nr, nb = C.c_int(0), C.c_size_t(0)
+        s = self.lib.ref_time_loop(_u8(frames), N, H * W * 3, C.byref(nr), C.byref(nb))
+        return s, nr.value, nb.value

@@ -71,6 +71,25 @@ int jpegb200_encode_batch(jpegb200_ctx *ctx, const uint8_t *d_bgr, int n, int w,
 int jpegb200_encode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_bgr, int n, int w, int h, uint8_t *h_out,
                                size_t slot, uint32_t *h_sizes);
 
+/* Input side (reference main/main.c:131-135 fills its B,G,R frame with fmt2rgb888 of
+ * espressif/esp32-camera 2.0.3): frames in one of the camera's packed formats are unpacked on the device, so that they
+ * cross PCIe at 2 or 1 byte per pixel.  Only the byte-shuffling branches of fmt2rgb888 are restated (k_formats.cu cites
+ * them); the camera's JPEG and YUV422 outputs go through arithmetic of the dependency and are not accepted. */
+enum { JPEGB200_FMT_BGR888 = 0, JPEGB200_FMT_RGB565 = 1, JPEGB200_FMT_GRAYSCALE = 2 };
+/* jpegb200_encode_batch_host with h_src in `fmt` (frame i at h_src + i * w*h*{3,2,1}). */
+int jpegb200_encode_batch_host_fmt(jpegb200_ctx *ctx, const uint8_t *h_src, int fmt, int n, int w, int h, uint8_t *h_out,
+                                   size_t slot, uint32_t *h_sizes);
+/* Device-resident form: n packed frames at d_src -> B,G,R frames at d_bgr (3*w*h bytes each), on `stream`. */
+int jpegb200_unpack(jpegb200_ctx *ctx, const uint8_t *d_src, int fmt, int n, int w, int h, uint8_t *d_bgr, void *stream);
+
+/* Multi-GPU form of the same call (batch-of-frames sharding, no collective, a frame is never split):
+ * `ctxs` holds one context per GPU (jpegb200_create(&ctxs[i], i)); context i encodes the contiguous range of
+ * ceil(n / nctx) frames starting at i * ceil(n / nctx) with its own host thread for the duration of the call, reading
+ * h_bgr and writing h_out / h_sizes in place, so the caller sees one batch.  Pinned host memory should be allocated
+ * with cudaHostAllocPortable (or by any context before the others are created) so that every device can DMA it. */
+int jpegb200_encode_batch_host_multi(jpegb200_ctx **ctxs, int nctx, const uint8_t *h_bgr, int n, int w, int h,
+                                     uint8_t *h_out, size_t slot, uint32_t *h_sizes);
+
 /* Encode `nareas` crops (x,y,w,h quadruples in host memory) of ONE device-resident frame; what
  * app_main does per detected region (main.c:142-153).  The kernels are enqueued behind `stream` and the
  * results are stream-ordered like those of jpegb200_encode_batch, but the call itself blocks the host
@@ -92,7 +111,9 @@ int jpegb200_stage_huffman(jpegb200_ctx *ctx, const int16_t *Y, const int16_t *C
 size_t jpegb200_stage_write(jpegb200_ctx *ctx, uint8_t *jpg, size_t cap, const int16_t *Y, const int16_t *Cb,
                             const int16_t *Cr, int w, int h, const void *luma2, const void *chroma2);
 
-/* Test hook: k_build_huffman on caller histograms (ntab x 257 ints in, ntab huff_code out); see tests/. */
+/* Test hook: k_build_huffman on caller histograms (ntab x 257 ints in, ntab huff_code out); see tests/.
+ * A histogram must use at least one and at most 255 of its 256 symbols: outside that the reference's init_huff_table
+ * (encoder.c:255-257, :277) reads and writes past its arrays, which is not replayed. */
 int jpegb200_debug_build_tables(jpegb200_ctx *ctx, const int *freq, int ntab, void *huff_out);
 
 /* ---- comparator (brain.c), HOST buffers (synchronous) — bound by main/brain.c -------------------- */

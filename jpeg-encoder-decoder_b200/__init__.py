@@ -26,7 +26,7 @@ ROOT = os.path.dirname(_HERE)
 C_ABI_SYMBOLS = [
     "jpegb200_create", "jpegb200_destroy", "jpegb200_last_error", "jpegb200_configure", "jpegb200_launch_count",
     "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_debug_fix_count",
-    "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_regions",
+    "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_batch_host_multi", "jpegb200_encode_batch_host_fmt", "jpegb200_unpack", "jpegb200_encode_regions",
     "jpegb200_stage_dct", "jpegb200_stage_huffman", "jpegb200_stage_write", "jpegb200_debug_build_tables",
     "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode", "jpegb200_compare_encode_batch",
 ]
@@ -84,6 +84,9 @@ def load_library() -> C.CDLL:
     L.jpegb200_launch_count.restype = C.c_uint64
     L.jpegb200_encode_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_size_t, vp, C.c_size_t, vp, vp]
     L.jpegb200_encode_batch_host.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]
+    L.jpegb200_encode_batch_host_fmt.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]
+    L.jpegb200_unpack.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.jpegb200_encode_batch_host_multi.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp]
     L.jpegb200_encode_regions.argtypes = [vp, vp, C.c_int, C.c_int, ip, C.c_int, vp, C.c_size_t, vp, vp]
     L.jpegb200_stage_dct.argtypes = [vp, u8p] + [C.c_int] * 6 + [i16p] * 3
     L.jpegb200_stage_huffman.argtypes = [vp] + [i16p] * 3 + [C.c_int, C.c_int, vp, vp]
@@ -282,6 +285,20 @@ class Encoder:
 
     def encode_batch_host_ptr(self, h_bgr: int, n: int, w: int, h: int, h_out: int, slot: int, h_sizes: int):
         self._check(self.lib.jpegb200_encode_batch_host(self.ctx, h_bgr, n, w, h, h_out, slot, h_sizes))
+
+    def encode_frames_fmt(self, packed: np.ndarray, fmt: int, w: int, h: int, slot: int | None = None) -> list[bytes]:
+        """(N, h*w*bpp) packed frames (fmt 1 = RGB565, 2 = GRAYSCALE; include/jpegb200.h) -> list of JFIF byte strings."""
+        packed = np.ascontiguousarray(packed, np.uint8)
+        N = packed.shape[0]
+        slot = slot or (w * h * 3 // 2 + 65536)
+        out = np.empty((N, slot), np.uint8)
+        sizes = np.zeros(N, np.uint32)
+        self._check(self.lib.jpegb200_encode_batch_host_fmt(self.ctx, C.c_void_p(packed.ctypes.data), fmt, N, w, h, C.c_void_p(out.ctypes.data), slot,
+                                                            C.c_void_p(sizes.ctypes.data)))
+        return [out[i, : sizes[i]].tobytes() for i in range(N)]
+
+    def unpack_ptr(self, d_src: int, fmt: int, n: int, w: int, h: int, d_bgr: int, stream: int = 0):
+        self._check(self.lib.jpegb200_unpack(self.ctx, C.c_void_p(d_src), fmt, n, w, h, C.c_void_p(d_bgr), C.c_void_p(stream)))
 
     def encode_frames(self, frames: np.ndarray, slot: int | None = None) -> list[bytes]:
         """Convenience: list of JFIF byte strings for a (N, H, W, 3) BGR array."""

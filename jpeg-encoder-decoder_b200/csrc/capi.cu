@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -71,7 +73,7 @@ struct Lane {
                                       // get the SM slots the other lanes' k_pixels_to_tokens CTAs free as they retire
   cudaEvent_t done = nullptr, sizes_ready = nullptr, pass1_done = nullptr, pass2_done = nullptr;
   DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base, fixtok;
-  DevBuf in, out, sizes;      // host-path staging on the device
+  DevBuf in, in_packed, out, sizes;      // host-path staging on the device (in_packed: frames in a packed camera format)
   PinBuf h_jobs, h_sizes;
   JbWs ws{};
   // host path bookkeeping of the wave in flight
@@ -131,7 +133,7 @@ struct Lane {
     return cudaSuccess;
   }
   void release() {
-    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &tok2, &tchunk_bits, &tchunk_base, &fixtok, &in, &out, &sizes})
+    for (DevBuf* b : {&jobs, &state_hist, &coef, &mask, &dcraw, &chunk_hist, &chunk_bits, &chunk_base, &huff, &enc, &scratch, &tile_ff, &fix, &tok, &runs, &run_base, &tok2, &tchunk_bits, &tchunk_base, &fixtok, &in, &in_packed, &out, &sizes})
       b->release();
     h_jobs.release();
     h_sizes.release();
@@ -495,11 +497,17 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
 }
 
 int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int w, int h, uint8_t* h_out, size_t slot, uint32_t* h_sizes) {
+  return jpegb200_encode_batch_host_fmt(c, h_bgr, JPEGB200_FMT_BGR888, n, w, h, h_out, slot, h_sizes);
+}
+
+int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fmt, int n, int w, int h, uint8_t* h_out, size_t slot, uint32_t* h_sizes) {
   if (!c || !h_bgr || !h_out || !h_sizes) return fail("null argument");
+  if (fmt != JPEGB200_FMT_BGR888 && fmt != JPEGB200_FMT_RGB565 && fmt != JPEGB200_FMT_GRAYSCALE) return fail("unknown input format %d", fmt);
   if (n <= 0) return 0;
   if (check_dims(w, h)) return -1;
   CK(cudaSetDevice(c->device));
   const size_t frame = (size_t)3 * w * h;
+  const size_t src_frame = fmt == JPEGB200_FMT_BGR888 ? frame : fmt == JPEGB200_FMT_RGB565 ? (size_t)2 * w * h : (size_t)w * h;
   const size_t dslot = (slot + 15) & ~(size_t)15;
   const JobDims jd = job_dims(w, h, slot);
   const int G = c->frames_per_wave;
@@ -517,6 +525,7 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     Lane& l = c->lanes[i];
     CK(l.ensure(wd));
     CK(l.in.ensure(g * frame));
+    if (fmt != JPEGB200_FMT_BGR888) CK(l.in_packed.ensure(g * src_frame));
     CK(l.out.ensure(g * dslot));
     CK(l.sizes.ensure(g * sizeof(uint32_t)));
     CK(l.h_sizes.ensure(g * sizeof(uint32_t)));
@@ -540,7 +549,13 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
     Lane& l = c->lanes[k % nl];
     if (retire(l)) return -1;
     const int first = k * G, cnt = std::min(G, n - first);
-    CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
+    if (fmt == JPEGB200_FMT_BGR888) {
+      CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
+    } else {                    // 2 or 1 byte per pixel over PCIe, unpacked on the device (k_formats.cu)
+      CK(cudaMemcpyAsync(l.in_packed.p, h_bgr + (size_t)first * src_frame, (size_t)cnt * src_frame, cudaMemcpyHostToDevice, l.stream));
+      jb_launch_unpack((const uint8_t*)l.in_packed.p, fmt, (size_t)cnt * w * h, (uint8_t*)l.in.p, l.stream);
+      c->launches++;
+    }
     k_fill_jobs<<<(cnt + 127) / 128, 128, 0, l.stream>>>(l.ws.jobs, cnt, (const uint8_t*)l.in.p, frame, w, h, (uint8_t*)l.out.p, dslot, jd);
     c->launches++;
     if (run_chain(c, l, cnt, w, h, jd.blocks, jd.chunks, FROM_PIXELS, false, false, (uint32_t*)l.sizes.p, true, tokens ? jd.runs : 0, jd.tchunks)) return -1;
@@ -551,6 +566,45 @@ int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int
   }
   for (int i = 0; i < nl; i++) if (retire(c->lanes[i])) return -1;
   for (int i = 0; i < nl; i++) CK(cudaStreamSynchronize(c->lanes[i].stream));
+  return 0;
+}
+
+int jpegb200_unpack(jpegb200_ctx* c, const uint8_t* d_src, int fmt, int n, int w, int h, uint8_t* d_bgr, void* stream) {
+  if (!c || !d_src || !d_bgr) return fail("null argument");
+  if (fmt != JPEGB200_FMT_RGB565 && fmt != JPEGB200_FMT_GRAYSCALE) return fail("unknown packed format %d", fmt);
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  if (((uintptr_t)d_src | (uintptr_t)d_bgr) & 7) return fail("d_src and d_bgr must be 8-byte aligned");
+  CK(cudaSetDevice(c->device));
+  jb_launch_unpack(d_src, fmt, (size_t)n * w * h, d_bgr, (cudaStream_t)stream);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// Batch-of-frames sharding over several contexts (one per GPU; SURVEY.md 8e: frames are independent, a frame is never split,
+// no collective): contiguous ranges of ceil(n / nctx) frames, one host thread per context for the duration of the call.
+int jpegb200_encode_batch_host_multi(jpegb200_ctx** ctxs, int nctx, const uint8_t* h_bgr, int n, int w, int h, uint8_t* h_out, size_t slot,
+                                     uint32_t* h_sizes) {
+  if (!ctxs || nctx <= 0 || !h_bgr || !h_out || !h_sizes) return fail("null argument");
+  for (int i = 0; i < nctx; i++) if (!ctxs[i]) return fail("null context %d", i);
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  const size_t frame = (size_t)3 * w * h;
+  const int per = (n + nctx - 1) / nctx;
+  std::vector<int> rc(nctx, 0);
+  std::vector<std::string> err(nctx);
+  std::vector<std::thread> th;
+  for (int i = 0; i < nctx; i++) {
+    const int first = i * per, cnt = std::min(per, n - first);
+    if (cnt <= 0) break;
+    th.emplace_back([=, &rc, &err]() {
+      rc[i] = jpegb200_encode_batch_host(ctxs[i], h_bgr + (size_t)first * frame, cnt, w, h, h_out + (size_t)first * slot, slot, h_sizes + first);
+      if (rc[i]) err[i] = jpegb200_last_error();       // the message is thread-local: carry it back to the caller's thread
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int i = 0; i < nctx; i++) if (rc[i]) return fail("context %d: %s", i, err[i].c_str());
   return 0;
 }
 

@@ -41,7 +41,8 @@ struct JbJob {
   uint32_t scratch_cap; // words available there
   uint8_t* out;         // destination slot of the finished JFIF stream
   uint32_t out_cap;     // bytes available there
-  uint32_t src_bytes;   // bytes readable from src (bounds the over-fetch of the aligned loader)
+  uint32_t src_bytes;   // extent of the frame at src (bookkeeping only: the bulk loader of unaligned crops reads whole 16-byte
+                        // granules and never leaves the granules that hold the frame's first and last byte)
   uint32_t tok_off;     // token path: first token of this job's pool inside ws.tok and ws.tok2 (capacity: JB_ROUND_TOKENS per tile and round)
   uint32_t run_off;     // token path: first run record of this job (Y runs, then Cb, then Cr)
   uint32_t tchunk_off;  // token path: first token chunk of this job in ws.tchunk_bits / ws.tchunk_base
@@ -205,6 +206,9 @@ void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
 void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st);
+
+// input formats (k_formats.cu): fmt 1 = RGB565, 2 = GRAYSCALE -> B,G,R
+bool jb_launch_unpack(const uint8_t* d_src, int fmt, size_t npix, uint8_t* d_bgr, cudaStream_t st);
 
 // comparator (brain.c)
 void jb_launch_subsample(const uint8_t* d_bgr, int w, int h, uint8_t* d_sub, int nframes, size_t frame_stride, cudaStream_t st);

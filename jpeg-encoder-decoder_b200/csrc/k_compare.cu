@@ -321,7 +321,10 @@ bool jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs, int* d
   size_t smem = 2 * (size_t)(w / 8 + 1) * sizeof(Run);
   if (smem > 200 * 1024) return false;
   if (smem > 40 * 1024) {
-    static size_t opted = 0;
+    static size_t opted_all[64] = {};                        // per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& opted = opted_all[dev & 63];
     if (smem > opted) { if (cudaFuncSetAttribute(k_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false; opted = smem; }
   }
   k_regions<<<nframes, 32, smem, st>>>(d_bits, w, h, d_outs, d_n);

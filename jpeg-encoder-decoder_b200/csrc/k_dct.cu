@@ -508,12 +508,15 @@ void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t
 }
 
 void jb_launch_dct_fast(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, cudaStream_t st) {
-  static int ctas_per_sm[2] = {0, 0}, sms = 0;
+  static int ctas_all[64][2] = {}, sms_all[64] = {};       // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  int* ctas_per_sm = ctas_all[dev];
+  int& sms = sms_all[dev];
   const int v = rows_aligned ? 1 : 0;
   auto kern = rows_aligned ? k_bgr_to_coef_fast<true> : k_bgr_to_coef_fast<false>;
   if (!ctas_per_sm[v]) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FastSmem));
     int n = 0;

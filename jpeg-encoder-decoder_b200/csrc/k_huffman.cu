@@ -146,6 +146,12 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
   __syncwarp();
 
   // The rest is short and strictly sequential: lane 0 replays it, the warp copies results out.
+  // Out of contract (unreachable from pixels, only through jpegb200_debug_build_tables): (a) a histogram without any used
+  // symbol - the reference's scan for the longest used length (encoder.c:255-257) then runs off code_len_freq[] into
+  // next[256] and its code loop (:283-300) runs off sym_sorted[]; (b) all 256 symbols used - encoder.c:277 then reads
+  // sym_sorted[256], i.e. sym_code_len[0], and zeroes the length of the symbol with that number.  The encoder's
+  // histograms always hold a DC category and an EOB, and its walker emits at most 162 of the 256 AC symbols; the kernel
+  // stays inside its arrays for both cases instead of replaying the overruns (tests exclude them).
   __shared__ int s_clf[TAB_WARPS][32];
   __shared__ int s_sorted[TAB_WARPS][256];
   __shared__ int s_slen[TAB_WARPS][256];

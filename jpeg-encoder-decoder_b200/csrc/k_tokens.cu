@@ -577,14 +577,18 @@ void jb_init_grey_tokens(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
 // tiles_per_warp = 0: persistent grid (one CTA per SM slot, each warp walks its share of the wave); n > 0: short-lived CTAs of
 // n tiles per warp, so that the high-priority kernels of other lanes get SM slots as CTAs retire (multi-lane batches).
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st, bool strided) {
-  static int ctas_per_sm[2] = {0, 0}, sms = 0;
+  // function attributes are per device: a process that drives several GPUs (jpegb200_encode_batch_host_multi) opts in on each
+  static int ctas_all[64][2] = {}, sms_all[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  int* ctas_per_sm = ctas_all[dev];
+  int& sms = sms_all[dev];
   const int v = rows_aligned ? 1 : 0;
   auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
   const int warps = rows_aligned ? TkWarps<true>::value : TkWarps<false>::value;
   const int smem = rows_aligned ? (int)sizeof(TkSmemT<true>) * warps : (int)sizeof(TkSmemT<false>) * warps;
   if (!ctas_per_sm[v]) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     int n = 0;

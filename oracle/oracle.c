@@ -548,3 +548,31 @@ double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, in
   free(jpg); free(sub); free(saved);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* --------------------------------------------------------------------------
+ * Input side.  The reference fills `raw` with fmt2rgb888() of espressif/esp32-camera 2.0.3
+ * (main/main.c:134; dependency pinned in dependencies.lock:2-8, source NOT vendored in the reference tree).  Restated
+ * from that component's published conversions/to_bmp.c are its two byte-shuffling branches; PARITY UNPINNED against the
+ * dependency itself (it cannot be built or fetched here) - pinned only by the known-answer vectors in tests/test_oracle.py
+ * that were worked out by hand from the published source.
+ *   fmt 1 = PIXFORMAT_RGB565 (pairs hb, lb), fmt 2 = PIXFORMAT_GRAYSCALE; output order B, G, R.
+ * ------------------------------------------------------------------------ */
+int orc_fmt2rgb888(const uint8_t *src, size_t src_len, int fmt, uint8_t *bgr) {
+  if (fmt == 1) {
+    for (size_t i = 0; i < src_len / 2; i++) {
+      uint8_t hb = *src++, lb = *src++;
+      *bgr++ = (uint8_t)((lb & 0x1F) << 3);
+      *bgr++ = (uint8_t)((hb & 0x07) << 5 | (lb & 0xE0) >> 3);
+      *bgr++ = (uint8_t)(hb & 0xF8);
+    }
+    return 1;
+  }
+  if (fmt == 2) {
+    for (size_t i = 0; i < src_len; i++) {
+      uint8_t b = *src++;
+      *bgr++ = b; *bgr++ = b; *bgr++ = b;
+    }
+    return 1;
+  }
+  return 0;
+}

@@ -93,6 +93,7 @@ class Oracle(_Base):
         L.orc_diff_mask.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_time_encode.restype = C.c_double
+        L.orc_fmt2rgb888.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.orc_time_loop.restype = C.c_double
 
@@ -145,6 +146,13 @@ class Oracle(_Base):
         s = self.lib.orc_time_encode(_u8(frames), N, H * W * 3, W, H, reps, C.byref(nb))
         return s, nb.value
 
+
+    def fmt2rgb888(self, packed: np.ndarray, fmt: int, npix: int) -> np.ndarray:
+        """fmt 1 = RGB565 (hb, lb pairs), 2 = GRAYSCALE -> (npix, 3) B,G,R bytes."""
+        packed = np.ascontiguousarray(packed, np.uint8).reshape(-1)
+        out = np.zeros((npix, 3), np.uint8)
+        assert self.lib.orc_fmt2rgb888(_u8(packed), packed.size, fmt, _u8(out)) == 1
+        return out
 
     def time_loop(self, frames):
         """app_main's loop over frames[1:] with frames[0] as the seed.  Returns (seconds, regions encoded, jpeg bytes)."""

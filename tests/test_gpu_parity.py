@@ -410,6 +410,40 @@ def test_compare_encode_batch_vs_oracle(enc, oracle, frames):
     assert any(j is not None for row in jpgs for j in row)
 
 
+def test_packed_input_formats(enc, oracle):
+    """Input side (jpegb200_encode_batch_host_fmt / jpegb200_unpack): RGB565 and GRAYSCALE frames are unpacked on the device
+    exactly like the oracle's restatement of fmt2rgb888 (esp32-camera 2.0.3), and the encoded bytes are the reference
+    encoder's bytes for the unpacked B,G,R frame."""
+    import torch
+    rng = np.random.default_rng(77)
+    w, h, n = 176, 144, 5
+    for fmt, bpp in ((1, 2), (2, 1)):
+        packed = rng.integers(0, 256, (n, h * w * bpp), dtype=np.uint8)
+        if fmt == 1:                                              # a smooth frame as well: more than noise statistics
+            yy, xx = np.mgrid[0:h, 0:w]
+            v565 = (((xx >> 1) & 31) << 11 | ((yy >> 1) & 63) << 5 | ((xx + yy) >> 3) & 31).astype(np.uint16)
+            packed[0] = np.stack([(v565 >> 8).astype(np.uint8), (v565 & 255).astype(np.uint8)], axis=-1).reshape(-1)
+        want_bgr = [oracle.fmt2rgb888(packed[i], fmt, w * h).reshape(h, w, 3) for i in range(n)]
+        d_src = torch.from_numpy(packed).cuda()
+        d_bgr = torch.zeros((n, h, w, 3), dtype=torch.uint8, device="cuda")
+        enc.unpack_ptr(d_src.data_ptr(), fmt, n, w, h, d_bgr.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_bgr.cpu().numpy(), np.stack(want_bgr)), fmt
+        jp = enc.encode_frames_fmt(packed, fmt, w, h)
+        for i in range(n):
+            assert jp[i] == oracle.encode(want_bgr[i])["jpg"].tobytes(), (fmt, i)
+
+
+def test_multi_context_c_caller():
+    """tools/multi_ctx_test (plain C against include/jpegb200.h): a host batch sharded over two contexts by
+    jpegb200_encode_batch_host_multi gives the bytes of the single-context call."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "multi_ctx_test")
+    assert os.path.exists(exe), "tools/multi_ctx_test is built by __graft_entry__.build()"
+    r = subprocess.run([exe, "11", "320", "240"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "multi_ctx_test ok" in r.stdout, (r.stdout, r.stderr)
+
+
 def test_subsample_ppm_file(api, frames, tmp_path, golden):
     p = str(tmp_path / "sub.ppm")
     api.subsample(frames.sample_bgr("640"), path=p)

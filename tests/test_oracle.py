@@ -196,3 +196,17 @@ def test_oracle_vs_ref_subsample_and_enlarge(oracle, ref):
         x0, y0 = int(rng.integers(0, W // 4)), int(rng.integers(0, H // 4))
         x1, y1 = int(rng.integers(x0, W // 4)), int(rng.integers(y0, H // 4))
         assert oracle.enlarge_adjust((x0, y0, x1, y1), W, H) == ref.enlarge_adjust((x0, y0, x1, y1), W, H)
+
+
+def test_fmt2rgb888_known_answers(oracle):
+    """Input side: the RGB565 / GRAYSCALE branches of fmt2rgb888 (esp32-camera 2.0.3, conversions/to_bmp.c; the reference calls
+    it at main/main.c:134).  The dependency is not in the reference tree: these vectors were worked out by hand from its
+    published source -  b = (lb & 0x1F) << 3, g = (hb & 0x07) << 5 | (lb & 0xE0) >> 3, r = hb & 0xF8, written B, G, R."""
+    kat = {  # (hb, lb) -> (B, G, R)
+        (0x00, 0x00): (0, 0, 0), (0xFF, 0xFF): (0xF8, 0xFC, 0xF8), (0xF8, 0x00): (0, 0, 0xF8), (0x07, 0xE0): (0, 0xFC, 0),
+        (0x00, 0x1F): (0xF8, 0, 0), (0x12, 0x34): (0xA0, 0x44, 0x10), (0xA5, 0x5A): (0xD0, 0xA8, 0xA0), (0x80, 0x01): (0x08, 0, 0x80)}
+    src = np.array([v for k in kat for v in k], np.uint8)
+    got = oracle.fmt2rgb888(src, 1, len(kat))
+    assert [tuple(int(x) for x in row) for row in got] == list(kat.values())
+    g = np.arange(256, dtype=np.uint8)
+    assert np.array_equal(oracle.fmt2rgb888(g, 2, 256), np.repeat(g[:, None], 3, axis=1))

@@ -335,6 +335,29 @@ def main():
         e2e = {"value": world * n * FRAME_MPIX / (dt / a.steps), "unit": "Mpix/s", "h2d_bytes_per_step": world * n * W * H * 3,
                "d2h_bytes_per_step": world * (jpeg_bytes + 4 * n), "ms_per_step": 1000 * dt / a.steps,
                "api": "jpegb200_encode_batch_host (pinned host buffers)", "frames_per_wave": a.e2e_frames_per_wave, "lanes": a.e2e_lanes}
+        if rank == 0 and world == 1 and not a.no_sub:
+            # the same frames as the camera's packed RGB565 (2 bytes per pixel over PCIe, unpacked on the device: SURVEY.md 8f rank 3)
+            b_, g_, r_ = d_in[..., 0], d_in[..., 1], d_in[..., 2]
+            h565 = torch.empty((n, H, W, 2), dtype=torch.uint8, pin_memory=True)
+            h565.copy_(torch.stack([(r_ & 0xF8) | (g_ >> 5), ((g_ << 3) & 0xE0) | (b_ >> 3)], dim=-1))
+            del b_, g_, r_
+
+            def pstep():
+                enc._check(enc.lib.jpegb200_encode_batch_host_fmt(enc.ctx, ctypes.c_void_p(h565.data_ptr()), 1, n, W, H, ctypes.c_void_p(h_out.data_ptr()), slot,
+                                                                  ctypes.c_void_p(h_sizes.data_ptr())))
+
+            for _ in range(2):
+                pstep()
+            assert (h_sizes.numpy() > 0).all()
+            t0 = time.perf_counter()
+            for _ in range(a.steps):
+                pstep()
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - t0) / a.steps
+            e2e["packed_rgb565"] = {"value": n * FRAME_MPIX / dtp, "unit": "Mpix/s", "h2d_bytes_per_step": n * W * H * 2,
+                                    "d2h_bytes_per_step": int(h_sizes.numpy().astype(np.int64).sum()) + 4 * n, "ms_per_step": 1000 * dtp,
+                                    "api": "jpegb200_encode_batch_host_fmt(JPEGB200_FMT_RGB565): the same frames as the camera's packed RGB565, unpacked on the device"}
+            del h565
 
     # ---- sub-records (N = 1 only): the other workloads BASELINE.json names, each measured like `value` but with fewer steps
     sub_records = []

@@ -120,6 +120,46 @@ template <bool ALIGNED>
 __device__ __noinline__ void tk_replay_patch(TkSmemT<ALIGNED>& sm, const TkShift& sh, int half, int mcu, int pr, int pc) {
   uint32_t cb[4] = {0, 0, 0, 0}, cr[4] = {0, 0, 0, 0};
   const int slot = half * 32 + mcu * 2 + pc;
+  if (ALIGNED) {
+    // Grey content (night / IR frames, the `ramp` class) lists every patch: an all-grey patch is recognised on the packed
+    // words (every byte equals its right neighbour, the neighbours of other pixels masked out) and takes its 16 results
+    // from the grey-level table, 8 table loads per row instead of 8 general replays.
+    uint32_t w[2][6], differ = 0;
+#pragma unroll
+    for (int dr = 0; dr < 2; dr++) {
+      const uint2* src = reinterpret_cast<const uint2*>(&sm.raw[2 * pr + dr][mcu * 12 + 6 * pc]);
+#pragma unroll
+      for (int k = 0; k < 3; k++) { const uint2 v = src[k]; w[dr][2 * k] = v.x; w[dr][2 * k + 1] = v.y; }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const uint32_t nxt = k < 5 ? w[dr][k + 1] : 0u;
+        const uint32_t t = w[dr][k] ^ __funnelshift_r(w[dr][k], nxt, 8);           // byte i ^ byte i + 1
+        differ |= t & (k % 3 == 0 ? 0xFF00FFFFu : k % 3 == 1 ? 0xFFFF00FFu : 0x00FFFF00u);   // bytes 3p + 2 pair different pixels
+      }
+    }
+    if (differ == 0) {
+#pragma unroll
+      for (int dr = 0; dr < 2; dr++) {
+        uint32_t e[8];
+#pragma unroll
+        for (int hq = 0; hq < 2; hq++) {
+          const uint32_t a = w[dr][3 * hq], b = w[dr][3 * hq + 1], c = w[dr][3 * hq + 2];
+          e[4 * hq + 0] = g_grey[a & 0xFFu];
+          e[4 * hq + 1] = g_grey[a >> 24];
+          e[4 * hq + 2] = g_grey[(b >> 16) & 0xFFu];
+          e[4 * hq + 3] = g_grey[(c >> 8) & 0xFFu];
+        }
+        uint32_t* ydst = &sm.smp[slot * 16 + ((pr ^ (slot >> 1)) & 3) * 4 + dr * 2];
+        *reinterpret_cast<uint2*>(ydst) = make_uint2(pack4(e[0], e[1], e[2], e[3]), pack4(e[4], e[5], e[6], e[7]));
+#pragma unroll
+        for (int c = 0; c < 8; c++) { cb[c >> 1] += (e[c] >> 8) & 0xFFu; cr[c >> 1] += e[c] >> 16; }
+      }
+      const int crow = half * 4 + pr, cw = (((crow >> 1) ^ (mcu >> 1)) & 3) * 4 + (crow & 1) * 2 + pc;
+      sm.smp[(64 + mcu) * 16 + cw] = pack4(cb[0] >> 2, cb[1] >> 2, cb[2] >> 2, cb[3] >> 2);
+      sm.smp[(80 + mcu) * 16 + cw] = pack4(cr[0] >> 2, cr[1] >> 2, cr[2] >> 2, cr[3] >> 2);
+      return;
+    }
+  }
 #pragma unroll 1
   for (int dr = 0; dr < 2; dr++) {
     const int r = 2 * pr + dr;                   // row inside the half = sample row of the luma block

@@ -94,20 +94,31 @@ __device__ void enlarge_adjust(Box* a, int fw, int fh) {     // brain.c:244-261
   if (a->y < 0) a->y = 0;
 }
 
-// One thread per frame (blockIdx.x = frame).  Dynamic shared memory: 2 run lists of (fw/8 + 1) entries.
-__global__ void k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int* __restrict__ outs_g, int* __restrict__ n_g) {
+// One warp per frame (blockIdx.x = frame): the replay itself is one thread's work (every step depends on the one before), the
+// other lanes only stage the frame's bit rows, RG_ROWS at a time, into shared memory, so that the sequential walk reads
+// them at shared-memory latency (with the rows in global memory the kernel spent 730 us per 1920x1280 frame waiting for
+// one word after the other).  Dynamic shared memory: 2 run lists of (fw/8 + 1) entries, then RG_ROWS rows of bit words.
+constexpr int RG_ROWS = 32;
+__global__ void __launch_bounds__(32) k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int* __restrict__ outs_g, int* __restrict__ n_g) {
   extern __shared__ Run s_runs[];
   __shared__ Box outs[JB_MAX_REGIONS];
-  if (threadIdx.x != 0) return;
+  const int lane = threadIdx.x;
   const int sw = fw >> 2, sh = fh >> 2, wpr = (sw + 31) >> 5, cap = fw / 8 + 1;
   bits += (size_t)blockIdx.x * wpr * sh;
   outs_g += (size_t)blockIdx.x * 4 * JB_MAX_REGIONS;
   n_g += blockIdx.x;
   Run* rows[2] = {s_runs, s_runs + cap};
-  for (int i = 0; i < JB_MAX_REGIONS; i++) outs[i] = Box{-1, -1, -1, -1};
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_runs + 2 * cap);
+  for (int i = lane; i < JB_MAX_REGIONS; i += 32) outs[i] = Box{-1, -1, -1, -1};
   int which = 0, nout = 0, ncur = 0, nprev = 0, result = -1;
 
-  for (int r = 0; r < sh && result < 0; r++) {
+  for (int r0 = 0; r0 < sh; r0 += RG_ROWS) {
+   const int nrows = min(RG_ROWS, sh - r0);
+   __syncwarp();
+   for (int k = lane; k < nrows * wpr; k += 32) s_bits[k] = bits[(size_t)r0 * wpr + k];
+   __syncwarp();
+   if (lane == 0)
+   for (int r = r0; r < r0 + nrows && result < 0; r++) {
     Run* cur = rows[which];
     Run* prev = rows[which ^ 1];
     // link the runs of the row that just ended against the row before it (brain.c:123-183)
@@ -154,7 +165,7 @@ __global__ void k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int
     cur = rows[which];
     // runs of row r from its bit words; a run still open at the right edge is dropped (brain.c:196-208)
     bool open = false;
-    const uint32_t* rb = bits + (size_t)r * wpr;
+    const uint32_t* rb = s_bits + (size_t)(r - r0) * wpr;
     for (int wi = 0; wi < wpr; wi++) {
       uint32_t word = rb[wi];
       const int base = wi << 5;
@@ -176,7 +187,10 @@ __global__ void k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int
         }
       }
     }
+   }
+   if (__shfl_sync(0xFFFFFFFFu, result, 0) >= 0) break;      // the > 99-box overflow ends the walk (brain.c:158-170)
   }
+  if (lane != 0) return;
 
   if (result < 0) {
     for (int i = 0; i < nout; i++) enlarge_adjust(&outs[i], fw, fh);
@@ -318,7 +332,7 @@ void jb_launch_diff_mask(const uint8_t* d_sub, const uint8_t* d_saved, int sw, i
 }
 // Returns false when the frame is too wide for the run lists to fit in shared memory (the caller reports it).
 bool jb_launch_regions(const uint32_t* d_bits, int w, int h, int* d_outs, int* d_n, int nframes, cudaStream_t st) {
-  size_t smem = 2 * (size_t)(w / 8 + 1) * sizeof(Run);
+  size_t smem = 2 * (size_t)(w / 8 + 1) * sizeof(Run) + (size_t)RG_ROWS * ((w / 4 + 31) / 32) * sizeof(uint32_t);
   if (smem > 200 * 1024) return false;
   if (smem > 40 * 1024) {
     static size_t opted_all[64] = {};                        // per device

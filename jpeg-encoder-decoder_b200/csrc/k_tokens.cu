@@ -36,6 +36,9 @@ namespace {
 #ifndef TK_SKIP_CLOSED
 #define TK_SKIP_CLOSED 1  // token walk: a lane that starts inside a block finds its first coefficient by binary descent, not by stepping
 #endif
+#ifndef TK_SYNC_EVERY
+#define TK_SYNC_EVERY 1   // the per-tile barrier (TK_SYNC = 1) every n-th tile only
+#endif
 #ifndef TK_ABLATE
 #define TK_ABLATE 0       // timing experiments only (wrong output): 1 = no token walk, 2 = no tie replay, 4 = no exact replay
 #endif
@@ -357,7 +360,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
     int tn = t_end;
 #pragma unroll 1
     for (int step = 0; step < 3; step++) {          // step 0: rows 0-7 + round 0 ; step 1: rows 8-15 + round 1 ; step 2: round 2
-      phase_sync(step == 0 ? 1 : 2);
+      if (step || (it % TK_SYNC_EVERY) == 0) phase_sync(step == 0 ? 1 : 2);
       if (step < 2) {
         if (active) {
           mbar_wait(&sm.full, parity);

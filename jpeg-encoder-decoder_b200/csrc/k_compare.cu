@@ -102,6 +102,7 @@ constexpr int RG_ROWS = 32;
 __global__ void __launch_bounds__(32) k_regions(const uint32_t* __restrict__ bits, int fw, int fh, int* __restrict__ outs_g, int* __restrict__ n_g) {
   extern __shared__ Run s_runs[];
   __shared__ Box outs[JB_MAX_REGIONS];
+  __shared__ uint32_t s_nz[RG_ROWS];                        // per staged row: which of its words hold a set bit
   const int lane = threadIdx.x;
   const int sw = fw >> 2, sh = fh >> 2, wpr = (sw + 31) >> 5, cap = fw / 8 + 1;
   bits += (size_t)blockIdx.x * wpr * sh;
@@ -116,6 +117,12 @@ __global__ void __launch_bounds__(32) k_regions(const uint32_t* __restrict__ bit
    const int nrows = min(RG_ROWS, sh - r0);
    __syncwarp();
    for (int k = lane; k < nrows * wpr; k += 32) s_bits[k] = bits[(size_t)r0 * wpr + k];
+   __syncwarp();
+   {                                                         // lane = row of the chunk; rows wider than 32 words are not skipped through
+     uint32_t nz = 0;
+     if (lane < nrows) for (int wi = 0; wi < wpr; wi++) nz |= (s_bits[lane * wpr + wi] != 0u ? 1u : 0u) << (wi & 31);
+     s_nz[lane] = wpr <= 32 ? nz : 0xFFFFFFFFu;
+   }
    __syncwarp();
    if (lane == 0)
    for (int r = r0; r < r0 + nrows && result < 0; r++) {
@@ -166,7 +173,15 @@ __global__ void __launch_bounds__(32) k_regions(const uint32_t* __restrict__ bit
     // runs of row r from its bit words; a run still open at the right edge is dropped (brain.c:196-208)
     bool open = false;
     const uint32_t* rb = s_bits + (size_t)(r - r0) * wpr;
+    uint32_t nzw = s_nz[r - r0];
     for (int wi = 0; wi < wpr; wi++) {
+      if (!open) {                                           // an empty word with no run open changes nothing: jump to the next
+        if (wpr <= 32) {                                     // word that holds a set bit (a word right after an open run is
+          nzw &= ~((1u << wi) - 1u);                         // visited even when empty: its first clear bit closes the run)
+          if (!nzw) break;
+          wi = __ffs(nzw) - 1;
+        } else if (!((nzw >> (wi & 31)) & 1u)) continue;
+      }
       uint32_t word = rb[wi];
       const int base = wi << 5;
       int pos = 0;                                           // bits below pos are consumed

@@ -38,13 +38,17 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t* total) 
 // run r of the job -> scan (0 Y, 1 Cb, 2 Cr); scans 1 and 2 share the chroma tables
 __device__ __forceinline__ int run_scan(uint32_t r, uint32_t nrc) { return r < 2u * nrc ? 0 : (r < 3u * nrc ? 1 : 2); }
 
-// enc[t][i]: code << 5 | length of table index i (0..255 AC symbols, 256..271 DC categories, 0 above: void tokens) of table
-// set t (0 luma, 1 chroma)
+// enc[t][i]: the resolved form of table index i (0..255 AC symbols, 256..271 DC categories, 0 above: void tokens) of table set
+// t (0 luma, 1 chroma): a token's category is a function of its index (AC: i & 15, DC: i - 256), so the shift that makes room
+// for the magnitude bits is applied here, once per CTA, instead of once per token:
+//   enc = code << (category + 5) | (code length + category)        resolved token = enc | magnitude bits << 5
 __device__ __forceinline__ void load_enc(const JbWs& ws, uint32_t job, uint32_t (*enc)[512]) {
   const uint32_t* g = ws.enc + (size_t)job * 4 * 256;
   for (int k = threadIdx.x; k < 2 * 512; k += blockDim.x) {
     const int t = k >> 9, i = k & 511;
-    enc[t][i] = i < 256 ? g[(2 * t + 1) * 256 + i] : (i < 272 ? g[(2 * t) * 256 + (i - 256)] : 0u);
+    const uint32_t e = i < 256 ? g[(2 * t + 1) * 256 + i] : (i < 272 ? g[(2 * t) * 256 + (i - 256)] : 0u);
+    const uint32_t cat = i < 256 ? (uint32_t)(i & 15) : (uint32_t)(i - 256);
+    enc[t][i] = e ? ((e >> 5) << (cat + 5)) | ((e & 31u) + cat) : 0u;
   }
 }
 
@@ -133,10 +137,10 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
         const uint32_t k = k0 + 32 * j + lane;
         if (k < run.ntok) {
           const uint32_t t = t8[j];
-          const uint32_t ent = e[(t >> 15) & 0x1FF], cat = (t >> 11) & 15u, z = t >> 24;
-          const uint32_t clen = (ent & 31u) + cat;                                  // <= 27 bits: code + magnitude bits
+          const uint32_t ent = e[(t >> 15) & 0x1FF], z = t >> 24;
+          const uint32_t clen = ent & 31u;                                          // <= 27 bits: code + magnitude bits
           // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
-          tok2[d0 + k] = z ? (t << 5) | 31u : ((((ent >> 5) << cat) | (t & 0x7FFu)) << 5) | clen;
+          tok2[d0 + k] = z ? (t << 5) | 31u : ent | ((t & 0x7FFu) << 5);
           const uint32_t len = clen + z * zrl_len;
           if ((d0 + k) / JB_TCHUNK == ca) la += len; else lb += len;
         }

@@ -56,7 +56,10 @@ namespace {
 constexpr int TK_WARPS_ALIGNED = TK_WARPS_PER_CTA;   // workers per CTA
 constexpr int TK_WARPS_UNALIGNED = 8;                // the wider staging rows of the unaligned loader leave room for 8
 template <bool ALIGNED> struct TkWarps { static constexpr int value = ALIGNED ? TK_WARPS_ALIGNED : TK_WARPS_UNALIGNED; };
-constexpr int TK_WINDOW = 384;          // a round with at most this many tokens is staged in shared memory (the round's dead sample
+#ifndef TK_WINDOW_TOKENS
+#define TK_WINDOW_TOKENS 384
+#endif
+constexpr int TK_WINDOW = TK_WINDOW_TOKENS;          // a round with at most this many tokens is staged in shared memory (the round's dead sample
                                         // slots: 1.5 KB of tokens + 0.5 KB of per-block walk state) and flushed with coalesced stores;
                                         // busier rounds store their tokens straight to global memory
 constexpr uint32_t FULL = 0xFFFFFFFFu;

@@ -392,28 +392,44 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int
 
 // The lane's column (i = lane & 7) of the 8x8 samples of block `blk` of a job, recomputed from the pixels with the exact
 // colour path (encoder.c:129-138); returns the component (0 luma, 1 chroma).
+// All loads of a batch are issued before the first conversion: ycc_pixel branches (grey table, tie replay through a call),
+// and a load placed behind it waits for the one before — 96 dependent round trips to memory per chroma block made
+// k_fix_tokens a 47 us kernel (r2).
 __device__ __forceinline__ int fix_block_samples(const JbJob& job, uint32_t blk, int i, uint32_t (&px)[8]) {
   const uint32_t nby = jb_nby(job.w, job.h), nbc = jb_nbc(job.w, job.h);
   const int comp = blk < nby ? 0 : 1;
   if (comp == 0) {
     const uint32_t bw = job.w / 8, by = blk / bw, bx = blk - by * bw;
+    uint32_t raw[8][3];
 #pragma unroll
     for (int t = 0; t < 8; t++) {
       const uint8_t* p = job.src + (size_t)(job.y + by * 8 + t) * job.pitch + 3u * (uint32_t)(job.x + bx * 8 + i);
-      px[t] = ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) & 0xFF;
+#pragma unroll
+      for (int c = 0; c < 3; c++) raw[t][c] = __ldg(p + c);
     }
+#pragma unroll
+    for (int t = 0; t < 8; t++) px[t] = ycc_pixel(raw[t][0], raw[t][1], raw[t][2]) & 0xFF;
   } else {
     const int ch = blk < nby + nbc ? 0 : 1;
     const uint32_t cblk = blk - nby - (ch ? nbc : 0), bw = job.w / 16, by = cblk / bw, bx = cblk - by * bw;
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-      uint32_t s = 0;
+    for (int half = 0; half < 2; half++) {            // two batches of 4 sample rows = 8 pixel rows x 2 pixels x 3 bytes
+      uint32_t raw[4][4][3];
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const uint8_t* p = job.src + (size_t)(job.y + (by * 8 + t) * 2 + (q >> 1)) * job.pitch + 3u * (uint32_t)(job.x + (bx * 8 + i) * 2 + (q & 1));
-        s += (ycc_pixel(__ldg(p), __ldg(p + 1), __ldg(p + 2)) >> (ch ? 16 : 8)) & 0xFF;
+      for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint8_t* p = job.src + (size_t)(job.y + (by * 8 + half * 4 + t) * 2 + (q >> 1)) * job.pitch + 3u * (uint32_t)(job.x + (bx * 8 + i) * 2 + (q & 1));
+#pragma unroll
+          for (int c = 0; c < 3; c++) raw[t][q][c] = __ldg(p + c);
+        }
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) sum += (ycc_pixel(raw[t][q][0], raw[t][q][1], raw[t][q][2]) >> (ch ? 16 : 8)) & 0xFF;
+        px[half * 4 + t] = sum >> 2;
       }
-      px[t] = s >> 2;
     }
   }
   return comp;

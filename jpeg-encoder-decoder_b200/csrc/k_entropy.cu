@@ -11,7 +11,7 @@
 //                  encoder.c:434-502), a CTA scan gives its bit offset, then it appends the bits MSB-first into a
 //                  shared-memory image of the chunk, which is then stored as big-endian words
 //                  (the two boundary words with atomicOr).
-//   k_count_ff     per 4 KiB tile of packed scan bytes: number of 0xFF bytes (each needs a stuffed
+//   k_count_ff     per 4 KiB tile of packed scan bytes (one warp): number of 0xFF bytes (each needs a stuffed
 //                  0x00, encoder.c:405-408).
 //   k_layout       per job: prefix of the tile counts, all marker segments (SOI/APP0, 2xDQT, 4xDHT,
 //                  SOF0, 3xSOS, EOI; encoder.c:504-644), the pad byte of each scan (fill_last_byte,
@@ -225,36 +225,55 @@ __global__ void __launch_bounds__(JB_CHUNK_BLOCKS) k_pack(JbWs ws, int dc_from_r
 }
 
 // ---------------------------------------------------------------------------------------------
+// 0x80 in every byte of w that equals 0xFF (exact per byte: no carries cross a byte)
+__device__ __forceinline__ uint32_t ff_flags(uint32_t w) {
+  const uint32_t x = ~w;
+  const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;             // bit 7 of a byte: its low 7 bits are not all zero
+  return ~(t | x) & 0x80808080u;
+}
+// FF flags of 16 bytes of which the first `valid` count
 __device__ __forceinline__ uint32_t count_ff16(uint4 v, uint32_t valid /*bytes, 0..16*/) {
-  uint32_t w[4] = {v.x, v.y, v.z, v.w};
-  uint32_t n = 0;
+  uint32_t f[4] = {ff_flags(v.x), ff_flags(v.y), ff_flags(v.z), ff_flags(v.w)};
+  if (valid < 16u) {
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    uint32_t m = __vcmpeq4(w[i], 0xFFFFFFFFu);                 // 0xFF per matching byte
-    int vb = (int)valid - 4 * i;                                // valid bytes in this word
-    if (vb <= 0) m = 0; else if (vb < 4) m &= (1u << (8 * vb)) - 1u;
-    n += __popc(m) >> 3;
+    for (int i = 0; i < 4; i++) {
+      const int vb = (int)valid - 4 * i;                        // valid bytes in this word
+      if (vb <= 0) f[i] = 0; else if (vb < 4) f[i] &= (1u << (8 * vb)) - 1u;
+    }
   }
-  return n;
+  return (uint32_t)(__popc(f[0]) + __popc(f[1]) + __popc(f[2]) + __popc(f[3]));
 }
 
+// One warp per 4 KiB tile (8 x 16 bytes per lane, one warp reduction, no barrier).
 __global__ void __launch_bounds__(256) k_count_ff(JbWs ws) {
-  __shared__ uint32_t wsum[9];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
   if (st->error) return;
-  for (int s = 0; s < 3; s++) {
-    const uint32_t nfull = st->seg_bits[s] >> 3;
-    const uint32_t ntiles = (nfull + JB_STUFF_TILE - 1) / JB_STUFF_TILE;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + st->seg_word[s]);
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const uint32_t off = t * JB_STUFF_TILE + threadIdx.x * 16;
-      uint32_t cnt = 0;
-      if (off < nfull) cnt = count_ff16(*reinterpret_cast<const uint4*>(src + off), min(16u, nfull - off));
-      uint32_t total;
-      cta_exclusive_scan(cnt, wsum, &total);
-      if (threadIdx.x == 0) ws.tile_ff[job.tile_off + s * job.tiles_per_seg + t] = total;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the tiles of the three scans form one list, so that a warp's work does not wait for the scans before it
+  uint32_t nfull3[3], nt[3], word3[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) { nfull3[s] = st->seg_bits[s] >> 3; nt[s] = (nfull3[s] + JB_STUFF_TILE - 1) / JB_STUFF_TILE; word3[s] = st->seg_word[s]; }
+  const uint32_t total_tiles = nt[0] + nt[1] + nt[2];
+  for (uint32_t f = blockIdx.x * 8u + warp; f < total_tiles; f += gridDim.x * 8u) {
+    const int s = f < nt[0] ? 0 : (f < nt[0] + nt[1] ? 1 : 2);
+    const uint32_t t = f - (s == 0 ? 0u : s == 1 ? nt[0] : nt[0] + nt[1]);
+    const uint32_t nfull = s == 0 ? nfull3[0] : s == 1 ? nfull3[1] : nfull3[2];
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + (s == 0 ? word3[0] : s == 1 ? word3[1] : word3[2]));
+    uint4 v[JB_STUFF_TILE / 512];                      // all loads first: one round trip to memory per tile
+#pragma unroll
+    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
+      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
+      v[j] = __ldg(reinterpret_cast<const uint4*>(src + (off < nfull ? off : 0u)));
     }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
+      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
+      cnt += count_ff16(v[j], off < nfull ? min(16u, nfull - off) : 0u);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) ws.tile_ff[job.tile_off + s * job.tiles_per_seg + t] = cnt;
   }
 }
 
@@ -352,58 +371,94 @@ __global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*p
 }
 
 // ---------------------------------------------------------------------------------------------
-// One 4 KiB tile of scan bytes per CTA step: the stuffed bytes are assembled in shared memory (byte stores are cheap there)
-// and leave as aligned 32-bit words; only the partial words at the two ends of the tile's output range are written
-// byte by byte, because the neighbouring tiles own the other bytes of those words.
+// One 4 KiB tile of scan bytes per CTA step.  The stuffed tile is assembled in shared memory at the byte phase of its
+// place in the file, so that it leaves as aligned 16-byte stores.  A thread whose 16 bytes hold no 0xFF (15 in 16) shifts
+// them to their phase in registers and stores words (the two partial words at its ends are OR-ed: the neighbours own the
+// other bytes); the others are spread byte by byte, 16 lanes of the warp per thread, leaving the zeroed byte behind
+// every 0xFF.  Only the 16-byte groups at the two ends of the tile's output range are written byte by byte, because the
+// neighbouring tiles own the rest of those groups.
 __global__ void __launch_bounds__(256) k_stuff(JbWs ws) {
-  __shared__ uint32_t wsum[9];
-  __shared__ uint32_t so[(2 * JB_STUFF_TILE + 16) / 4];
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  __shared__ __align__(16) uint32_t wsum[8];
+  __shared__ __align__(16) uint32_t so[(2 * JB_STUFF_TILE + 96) / 4];   // output byte k of the tile at byte 16 + mis + k
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
   if (st->error) return;
-  uint8_t* sob = reinterpret_cast<uint8_t*>(so);
-  for (int s = 0; s < 3; s++) {
-    const uint32_t nfull = st->seg_bits[s] >> 3;
-    const uint32_t ntiles = (nfull + JB_STUFF_TILE - 1) / JB_STUFF_TILE;
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + st->seg_word[s]);
-    uint8_t* dst = job.out + st->seg_out[s];
-    const uint32_t* tf = ws.tile_ff + job.tile_off + s * job.tiles_per_seg;
-    for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const uint32_t off = t * JB_STUFF_TILE + threadIdx.x * 16;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the tiles of the three scans form one list (a CTA's next tile does not wait for the scans before it)
+  uint32_t nfull3[3], nt[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) { nfull3[s] = st->seg_bits[s] >> 3; nt[s] = (nfull3[s] + JB_STUFF_TILE - 1) / JB_STUFF_TILE; }
+  const uint32_t total_tiles = nt[0] + nt[1] + nt[2];
+  {
+    for (uint32_t f = blockIdx.x; f < total_tiles; f += gridDim.x) {
+      const int s = f < nt[0] ? 0 : (f < nt[0] + nt[1] ? 1 : 2);
+      const uint32_t t = f - (s == 0 ? 0u : s == 1 ? nt[0] : nt[0] + nt[1]);
+      const uint32_t nfull = s == 0 ? nfull3[0] : s == 1 ? nfull3[1] : nfull3[2];
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + st->seg_word[s]);
+      uint8_t* dst = job.out + st->seg_out[s];
+      const uint32_t* tf = ws.tile_ff + job.tile_off + s * job.tiles_per_seg;
+      const uint32_t off = t * JB_STUFF_TILE + tid * 16;
       uint4 v = make_uint4(0, 0, 0, 0);
       uint32_t valid = 0;
-      if (off < nfull) { v = *reinterpret_cast<const uint4*>(src + off); valid = min(16u, nfull - off); }
+      if (off < nfull) { v = __ldg(reinterpret_cast<const uint4*>(src + off)); valid = min(16u, nfull - off); }
       const uint32_t cnt = count_ff16(v, valid);
-      uint32_t total;
-      const uint32_t ex = cta_exclusive_scan(cnt, wsum, &total);       // its barriers also protect `so` against the previous tile
-      uint8_t* g = dst + (size_t)t * JB_STUFF_TILE + tf[t];             // first output byte of the tile
-      const uint32_t mis = (uint32_t)(uintptr_t)g & 3u;
-      const uint32_t nbytes = min((uint32_t)JB_STUFF_TILE, nfull - t * JB_STUFF_TILE) + total;
-      // shared byte position of output byte k of the tile: 4 + k
-      uint8_t* o = sob + 4 + threadIdx.x * 16 + ex;
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t inc = cnt;
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        if ((uint32_t)i < valid) {
-          const uint8_t by = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-          *o++ = by;
-          if (by == 0xFF) *o++ = 0;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= (uint32_t)o) inc += n;
+      }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();                                                  // also: the previous tile has left `so`
+      uint32_t ex = inc - cnt, total = 0;
+      {
+        const uint4 a = *reinterpret_cast<const uint4*>(wsum), b = *reinterpret_cast<const uint4*>(wsum + 4);
+        const uint32_t w8[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) { total += w8[i]; ex += (uint32_t)i < warp ? w8[i] : 0u; }
+      }
+      uint8_t* g = dst + (size_t)t * JB_STUFF_TILE + tf[t];             // first output byte of the tile
+      const uint32_t mis = (uint32_t)(uintptr_t)g & 15u;
+      const uint32_t nbytes = min((uint32_t)JB_STUFF_TILE, nfull - t * JB_STUFF_TILE) + total;
+      const uint32_t ngroups = (mis + nbytes + 15u) >> 4;               // 16-byte groups of the file that hold bytes of the tile
+      for (uint32_t j = tid; j < ngroups + 2u; j += 256) reinterpret_cast<uint4*>(so)[j] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+      const uint32_t o = 16u + mis + tid * 16u + ex;                    // where this thread's first byte goes
+      if (valid == 16u && cnt == 0u) {
+        const uint32_t a = 8u * (o & 3u), wi = o >> 2;
+        atomicOr(so + wi, v.x << a);
+        so[wi + 1] = __funnelshift_l(v.x, v.y, a);
+        so[wi + 2] = __funnelshift_l(v.y, v.z, a);
+        so[wi + 3] = __funnelshift_l(v.z, v.w, a);
+        if (a) atomicOr(so + wi + 4, __funnelshift_l(v.w, 0u, a));
+      }
+      for (uint32_t sb = __ballot_sync(FULL, valid != 0u && !(valid == 16u && cnt == 0u)); sb; sb &= sb - 1u) {
+        const int L = __ffs(sb) - 1;
+        const uint32_t x0 = __shfl_sync(FULL, v.x, L), x1 = __shfl_sync(FULL, v.y, L), x2 = __shfl_sync(FULL, v.z, L), x3 = __shfl_sync(FULL, v.w, L);
+        const uint32_t oL = __shfl_sync(FULL, o, L), vL = __shfl_sync(FULL, valid, L);
+        const uint32_t q = lane & 15u;
+        const uint32_t wq = q < 8u ? (q < 4u ? x0 : x1) : (q < 12u ? x2 : x3);
+        const uint32_t by = (wq >> (8u * (q & 3u))) & 0xFFu;
+        const bool live = lane < 16u && q < vL;
+        const uint32_t ffm = __ballot_sync(FULL, live && by == 0xFFu);
+        if (live) {
+          const uint32_t p = oL + q + (uint32_t)__popc(ffm & ((1u << q) - 1u));
+          atomicOr(so + (p >> 2), by << (8u * (p & 3u)));
         }
       }
       __syncthreads();
-      // aligned word j of the output covers tile bytes [4j - mis, 4j - mis + 4)
-      const uint32_t nw = (mis + nbytes + 3) >> 2;
-      uint32_t* ga = reinterpret_cast<uint32_t*>(g - mis);
-      for (uint32_t j = threadIdx.x; j < nw; j += 256) {
-        const uint32_t b0 = 4 + 4 * j - mis;                            // shared byte position of the word's first byte (>= 1)
-        const uint32_t lo = so[b0 >> 2], hi = so[(b0 >> 2) + 1];
-        const uint32_t word = __funnelshift_r(lo, hi, 8 * (b0 & 3));
-        const int first = (int)(4 * j) - (int)mis, last = first + 3;    // tile byte indices covered by this word
-        if (first >= 0 && last < (int)nbytes) ga[j] = word;
+      // group j of the file = shared group j + 1
+      uint4* ga = reinterpret_cast<uint4*>(g - mis);
+      for (uint32_t j = tid; j < ngroups; j += 256) {
+        const uint4 x = reinterpret_cast<const uint4*>(so)[j + 1];
+        const int first = (int)(16u * j) - (int)mis;                    // tile byte index of the group's first byte
+        if (first >= 0 && first + 16 <= (int)nbytes) ga[j] = x;
         else {
+          const uint32_t w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-          for (int q = 0; q < 4; q++)
-            if (first + q >= 0 && first + q < (int)nbytes) (g - mis)[4 * j + q] = (uint8_t)(word >> (8 * q));
+          for (int q = 0; q < 16; q++)
+            if (first + q >= 0 && first + q < (int)nbytes) reinterpret_cast<uint8_t*>(ga + j)[q] = (uint8_t)(w[q >> 2] >> (8 * (q & 3)));
         }
       }
     }
@@ -420,7 +475,7 @@ void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_
   k_pack<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
 }
 void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st) {
-  k_count_ff<<<dim3(ctas_per_job, njobs), 256, 0, st>>>(ws);
+  k_count_ff<<<dim3((ctas_per_job + 3) / 4, njobs), 256, 0, st>>>(ws);     // a warp per tile: a quarter of k_stuff's CTAs covers the same tiles
 }
 void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st) { k_layout<<<njobs, 256, 0, st>>>(ws, sizes_out); }
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st) {

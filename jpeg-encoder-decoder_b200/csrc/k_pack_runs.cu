@@ -210,6 +210,37 @@ __device__ __forceinline__ void or_bits_s(uint32_t* img, uint32_t pos, uint32_t 
   if ((uint32_t)v) atomicOr(img + wi + 1, (uint32_t)v);
 }
 
+// Concatenate the lane's 8 code words (MSB first) behind the sbit & 31 bits that precede them in their first word, in a
+// W-word register accumulator, and store the words into the bit image: the first and the last word are shared with the
+// neighbouring lanes (OR), the others are the lane's own.  W = 9 holds any 8 tokens (8 x 27 + 31 bits).
+template <int W>
+__device__ __forceinline__ void concat_store(uint32_t* stage, const uint32_t (&word)[PR_TOK], const uint32_t (&len)[PR_TOK], uint32_t sbit, uint32_t nbits) {
+  uint32_t A[W];
+#pragma unroll
+  for (int q = 0; q < W; q++) A[q] = 0;
+  uint32_t tot = sbit & 31;
+#pragma unroll
+  for (int j = 0; j < PR_TOK; j++) {
+#pragma unroll
+    for (int q = 0; q < W - 1; q++) A[q] = __funnelshift_l(A[q + 1], A[q], len[j]);
+    A[W - 1] = (A[W - 1] << len[j]) | (len[j] ? word[j] : 0u);
+    tot += len[j];
+  }
+  const uint32_t pad = (32u - (tot & 31u)) & 31u;
+#pragma unroll
+  for (int q = 0; q < W - 1; q++) A[q] = __funnelshift_l(A[q + 1], A[q], pad);
+  A[W - 1] <<= pad;
+  const int nw = nbits ? (int)((tot + pad) >> 5) : 0;
+  uint32_t* dst = stage + (sbit >> 5) - (W - nw);
+#pragma unroll
+  for (int q = 0; q < W; q++) {
+    if (q >= W - nw) {
+      if (q == W - nw || q == W - 1) atomicOr(dst + q, A[q]);
+      else dst[q] = A[q];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
@@ -263,31 +294,12 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
     for (uint32_t k = lane; k < nwr + 1; k += 32) stage[k] = 0;
     __syncwarp();
     const uint32_t sbit = phase + ex;
+    // the lanes' bits rarely exceed four words (5 bits per token on photographic content): the short accumulator shifts
+    // 3 words per token instead of 8
+    const bool wide = __any_sync(FULL, (sbit & 31u) + nbits > 128u);
     if (zr == 0) {
-      uint32_t A[9];
-#pragma unroll
-      for (int q = 0; q < 9; q++) A[q] = 0;
-      uint32_t tot = sbit & 31;
-#pragma unroll
-      for (int j = 0; j < PR_TOK; j++) {
-#pragma unroll
-        for (int q = 0; q < 8; q++) A[q] = __funnelshift_l(A[q + 1], A[q], len[j]);
-        A[8] = (A[8] << len[j]) | (len[j] ? word[j] : 0u);
-        tot += len[j];
-      }
-      const uint32_t pad = (32u - (tot & 31u)) & 31u;
-#pragma unroll
-      for (int q = 0; q < 8; q++) A[q] = __funnelshift_l(A[q + 1], A[q], pad);
-      A[8] <<= pad;
-      const int nw = nbits ? (int)((tot + pad) >> 5) : 0;
-      uint32_t* dst = stage + (sbit >> 5) - (9 - nw);
-#pragma unroll
-      for (int q = 0; q < 9; q++) {
-        if (q >= 9 - nw) {
-          if (q == 9 - nw || q == 8) atomicOr(dst + q, A[q]);
-          else dst[q] = A[q];
-        }
-      }
+      if (wide) concat_store<9>(stage, word, len, sbit, nbits);
+      else concat_store<4>(stage, word, len, sbit, nbits);
     } else {
       uint32_t pos = sbit;
 #pragma unroll

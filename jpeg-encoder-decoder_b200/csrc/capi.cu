@@ -258,14 +258,11 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     { StageTimer t(c, st, ST_FIX); jb_launch_fix_tokens(ws, st); }
     CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
     { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }
-    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }
-    { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
-    { StageTimer t(c, st, ST_RUNBITS); jb_launch_compact_tokens(ws, njobs, max_runs, st); }
-    { StageTimer t(c, st, ST_SCAN); jb_launch_scan_tchunks(ws, njobs, st); }
+    { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }      // + packed tables
+    { StageTimer t(c, st, ST_RUNBITS); jb_launch_compact_tokens(ws, njobs, max_runs, st); }                                      // + chunk scan (last CTA of a job)
     { StageTimer t(c, st, ST_PACK); jb_launch_pack_tchunks(ws, njobs, max_tchunks, st); }
     const uint32_t tail_ctas = njobs >= 16 ? 24 : 64;       // CTAs per job of the byte-stuffing kernels
-    { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, st); }
-    { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
+    { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, d_sizes, st); }                                // + layout (last CTA of a job)
     { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, tail_ctas, st); }
     if (c->split_streams && c->overlap_waves) {
       CK(cudaEventRecord(l.pass2_done, st));
@@ -290,11 +287,10 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }
     if (stop_after_tables) { CK(cudaGetLastError()); return 0; }
   }
-  { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }
+  if (from == FROM_PLANES_WRITE) { StageTimer t(c, st, ST_TABLES); jb_launch_pack_tables(ws, njobs, st); }     // caller-provided huff_codes
   { StageTimer t(c, st, ST_SCAN); jb_launch_scan(ws, njobs, max_chunks, st); c->launches++; }
   { StageTimer t(c, st, ST_PACK); jb_launch_pack(ws, njobs, max_chunks, dc_from_raw, st); }
-  { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, st); }
-  { StageTimer t(c, st, ST_LAYOUT); jb_launch_layout(ws, njobs, d_sizes, st); }
+  { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, 8, d_sizes, st); }
   { StageTimer t(c, st, ST_STUFF); jb_launch_stuff(ws, njobs, 8, st); }
   CK(cudaGetLastError());
   return 0;

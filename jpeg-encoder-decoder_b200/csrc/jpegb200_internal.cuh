@@ -59,6 +59,8 @@ struct JbJobState {
   uint32_t tok_total[3];     // token path: tokens per scan
   uint32_t tok_start[3];     // token path: first token of each scan inside the job's part of ws.tok2 (multiple of JB_TCHUNK)
   uint32_t tok_cursor;       // token path: tokens handed out so far in the job's part of ws.tok (rounds claim their space atomically)
+  uint32_t ctas_compacted;   // token path: CTAs of k_compact_tokens that are done with the job (the last one scans the chunks)
+  uint32_t ctas_counted;     // CTAs of k_count_ff that are done with the job (the last one lays the file out)
 };
 
 enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4 };
@@ -192,8 +194,7 @@ void jb_launch_build_huffman(const JbWs& ws, int njobs, bool wide_keys, cudaStre
 void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_scan(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t st);
 void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st);
-void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
-void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st);
+void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, uint32_t* sizes_out, cudaStream_t st);     // + layout
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st);
 
 // grey-level table of the colour replay (dct_core.cuh): one copy per translation unit, filled once per context
@@ -204,7 +205,6 @@ void jb_init_grey_dct(cudaStream_t st);
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st, bool strided = false);
 void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st);
-void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st);
 void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st);
 
 // input formats (k_formats.cu): fmt 1 = RGB565, 2 = GRAYSCALE -> B,G,R

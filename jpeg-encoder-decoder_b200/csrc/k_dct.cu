@@ -390,6 +390,15 @@ __global__ void __launch_bounds__(FT_THREADS, 5) k_bgr_to_coef_fast(JbWs ws, int
   }
 }
 
+// 1 / (4 q) with the bracket's safety factor for both quantisers (natural order), filled at context creation: the
+// reciprocal and the int -> double conversion (I2F.F64, MUFU.RCP64H + Newton) were 6 % of k_fix_tokens' stall samples, paid by
+// each of its 1184 CTAs.
+__device__ double g_rq[128];
+__global__ void k_init_rq() {
+  const int tid = threadIdx.x, comp = tid >> 6;
+  g_rq[tid] = __dmul_rn(__drcp_rn((double)c_quant[comp][tid & 63]), 0x1.00000004p-2);
+}
+
 // The lane's column (i = lane & 7) of the 8x8 samples of block `blk` of a job, recomputed from the pixels with the exact
 // colour path (encoder.c:129-138); returns the component (0 luma, 1 chroma).
 // All loads of a batch are issued before the first conversion: ycc_pixel branches (grey table, tie replay through a call),
@@ -441,12 +450,12 @@ __global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
   __shared__ int16_t zz[4][4 * 64];
   __shared__ double rqs[2][8][10];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
+  {                                   // the bracket's reciprocals: computed once per context (k_init_rq), one load here
     const int comp = tid >> 6, r = (tid >> 3) & 7, u = tid & 7;
-    rqs[comp][r][u] = __dmul_rn(__drcp_rn((double)c_quant[comp][r * 8 + u]), 0x1.00000004p-2);
+    rqs[comp][r][u] = g_rq[tid];
   }
-  __syncthreads();
   const uint32_t count = *ws.fix_count;
+  __syncthreads();
   const int b = lane >> 3, i = lane & 7;
   const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
   for (uint32_t base = (blockIdx.x * 4 + warp) * 4; base < count; base += gridDim.x * 16) {
@@ -471,17 +480,20 @@ __global__ void __launch_bounds__(128) k_fix_blocks(JbWs ws) {
 // Token path: the blocks k_pixels_to_tokens could not decide.  It reserved their token slots (DC written, the rest void);
 // here the literal chain gives the block, one lane writes its AC tokens and EOB over the void slots and adds the symbols
 // to the job's histograms.  8 lanes per block, 4 blocks per warp.
-__global__ void __launch_bounds__(128) k_fix_tokens(JbWs ws) {
+#ifndef JB_FIX_MIN_CTAS
+#define JB_FIX_MIN_CTAS 6      // 85 registers: r2 measured 1 (164 registers) 251.9, 4: 257.4, 6: 258.4 Gpix/s for the headline batch
+#endif
+__global__ void __launch_bounds__(128, JB_FIX_MIN_CTAS) k_fix_tokens(JbWs ws) {
   __shared__ double tr[4][4 * TR_STRIDE];
   __shared__ int16_t zz[4][4 * 64];
   __shared__ double rqs[2][8][10];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  {
+  {                                   // the bracket's reciprocals: computed once per context (k_init_rq), one load here
     const int comp = tid >> 6, r = (tid >> 3) & 7, u = tid & 7;
-    rqs[comp][r][u] = __dmul_rn(__drcp_rn((double)c_quant[comp][r * 8 + u]), 0x1.00000004p-2);
+    rqs[comp][r][u] = g_rq[tid];
   }
-  __syncthreads();
   const uint32_t count = *ws.fix_count;
+  __syncthreads();
   const int b = lane >> 3, i = lane & 7;
   const uint2 izzrow = reinterpret_cast<const uint2*>(c_izz)[i];
   for (uint32_t base = (blockIdx.x * 4 + warp) * 4; base < count; base += gridDim.x * 16) {
@@ -492,23 +504,27 @@ __global__ void __launch_bounds__(128) k_fix_tokens(JbWs ws) {
     const int comp = fix_block_samples(job, e.y, i, px);
     uint64_t mask;
     block_dct(px, comp, rqs[comp][i], izzrow, tr[warp], zz[warp], lane, &mask);
-    if (live && i == 0) {
+    // AC tokens: lane i of the block's 8 takes zig-zag positions 8i .. 8i + 7; run and slot of a coefficient follow from the
+    // mask bits below it (r2: one lane walked the whole block, 37 % of the kernel's instructions with 4 of 32 lanes active)
+    const uint32_t mlo = __shfl_sync(0xFFFFFFFFu, (uint32_t)mask, lane & ~7), mhi = __shfl_sync(0xFFFFFFFFu, (uint32_t)(mask >> 32), lane & ~7);
+    const uint64_t m = ((uint64_t)mhi << 32) | mlo;
+    if (live) {
       const int16_t* blk = zz[warp] + b * 64;
       int* hist_ac = ws.hist + (size_t)e.x * 4 * 257 + (comp ? 3 * 257 : 257);
       uint32_t* out = ws.tok + e.z + 1;                                // slot 0 holds the DC token
-      int prev1 = 1;
-      for (uint64_t m = mask; m; m &= m - 1) {
-        const int p = __ffsll((long long)m) - 1;
+      for (uint32_t byte = (uint32_t)(m >> (8 * i)) & 0xFFu; byte; byte &= byte - 1) {
+        const int p = 8 * i + __ffs(byte) - 1;
+        const uint64_t below = m & ((1ull << p) - 1ull);
+        const int prev1 = below ? 64 - __clzll((long long)below) : 1;  // position after the previous non-zero coefficient
         const int v = blk[p];
         const int run = p - prev1;
-        prev1 = p + 1;
         const int cat = 32 - __clz(abs(v));
         const int sym = ((run & 15) << 4) | cat, zrl = run >> 4;
         atomicAdd(&hist_ac[sym], 1);
         if (zrl) atomicAdd(&hist_ac[0xF0], zrl);
-        *out++ = jb_token(v, cat, sym, zrl);
+        out[__popcll(below)] = jb_token(v, cat, sym, zrl);
       }
-      if (!(mask >> 63)) { atomicAdd(&hist_ac[0], 1); *out++ = 0; }   // EOB
+      if (i == 0 && !(m >> 63)) { atomicAdd(&hist_ac[0], 1); out[__popcll(m)] = 0; }   // EOB
     }
     __syncwarp();
   }
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(128) k_fix_tokens(JbWs ws) {
 
 }  // namespace
 
-void jb_init_grey_dct(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
+void jb_init_grey_dct(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); k_init_rq<<<1, 128, 0, st>>>(); }
 
 void jb_launch_dct(const JbWs& ws, int njobs, int max_w, int max_h, cudaStream_t st) {
   int tiles = ((max_w + TILE_W - 1) / TILE_W) * (max_h / 16);

@@ -13,7 +13,7 @@
 //                  (the two boundary words with atomicOr).
 //   k_count_ff     per 4 KiB tile of packed scan bytes (one warp): number of 0xFF bytes (each needs a stuffed
 //                  0x00, encoder.c:405-408).
-//   k_layout       per job: prefix of the tile counts, all marker segments (SOI/APP0, 2xDQT, 4xDHT,
+//   layout_job     per job (last CTA of k_count_ff): prefix of the tile counts, all marker segments (SOI/APP0, 2xDQT, 4xDHT,
 //                  SOF0, 3xSOS, EOI; encoder.c:504-644), the pad byte of each scan (fill_last_byte,
 //                  encoder.c:425-432: always one byte, never stuffed) and the total size.
 //   k_stuff        per tile: copies scan bytes to their final position, inserting 0x00 after 0xFF.
@@ -21,8 +21,11 @@
 #include "tables.cuh"
 #include "walk.cuh"
 
-namespace {
+#ifndef JB_FUSE_LAYOUT
+#define JB_FUSE_LAYOUT 1
+#endif
 
+namespace {
 
 // Resolve (chunk index inside the job) -> segment and chunk inside the segment.
 __device__ __forceinline__ bool locate_chunk(const JbJob& job, uint32_t c, int* s, uint32_t* cs) {
@@ -244,50 +247,17 @@ __device__ __forceinline__ uint32_t count_ff16(uint4 v, uint32_t valid /*bytes, 
   return (uint32_t)(__popc(f[0]) + __popc(f[1]) + __popc(f[2]) + __popc(f[3]));
 }
 
-// One warp per 4 KiB tile (8 x 16 bytes per lane, one warp reduction, no barrier).
-__global__ void __launch_bounds__(256) k_count_ff(JbWs ws) {
-  const JbJob job = ws.jobs[blockIdx.y];
-  const JbJobState* st = ws.state + blockIdx.y;
-  if (st->error) return;
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // the tiles of the three scans form one list, so that a warp's work does not wait for the scans before it
-  uint32_t nfull3[3], nt[3], word3[3];
-#pragma unroll
-  for (int s = 0; s < 3; s++) { nfull3[s] = st->seg_bits[s] >> 3; nt[s] = (nfull3[s] + JB_STUFF_TILE - 1) / JB_STUFF_TILE; word3[s] = st->seg_word[s]; }
-  const uint32_t total_tiles = nt[0] + nt[1] + nt[2];
-  for (uint32_t f = blockIdx.x * 8u + warp; f < total_tiles; f += gridDim.x * 8u) {
-    const int s = f < nt[0] ? 0 : (f < nt[0] + nt[1] ? 1 : 2);
-    const uint32_t t = f - (s == 0 ? 0u : s == 1 ? nt[0] : nt[0] + nt[1]);
-    const uint32_t nfull = s == 0 ? nfull3[0] : s == 1 ? nfull3[1] : nfull3[2];
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + (s == 0 ? word3[0] : s == 1 ? word3[1] : word3[2]));
-    uint4 v[JB_STUFF_TILE / 512];                      // all loads first: one round trip to memory per tile
-#pragma unroll
-    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
-      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
-      v[j] = __ldg(reinterpret_cast<const uint4*>(src + (off < nfull ? off : 0u)));
-    }
-    uint32_t cnt = 0;
-#pragma unroll
-    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
-      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
-      cnt += count_ff16(v[j], off < nfull ? min(16u, nfull - off) : 0u);
-    }
-    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-    if (lane == 0) ws.tile_ff[job.tile_off + s * job.tiles_per_seg + t] = cnt;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 __constant__ unsigned char c_soi_app0[20] = {0xFF, 0xD8, 0xFF, 0xE0, 0x00, 0x10, 'J', 'F', 'I', 'F', 0x00, 0x01, 0x01, 0x00, 0x00, 0x48, 0x00, 0x48, 0x00, 0x00};
 
-__global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*per job, may be null*/) {
+// Per job, once its tiles are counted (256 threads; runs in the CTA of k_count_ff that finishes the job last).
+__device__ __forceinline__ void layout_job(const JbWs& ws, const uint32_t jobid, const JbJob& job, uint32_t* sizes_out /*per job, may be null*/) {
   __shared__ uint32_t wsum[9];
   __shared__ uint32_t s_ff[3], s_dht_off[4], s_dht_n[4], s_sof, s_seg_out[3], s_size, s_err;
-  const JbJob job = ws.jobs[blockIdx.x];
-  JbJobState* st = ws.state + blockIdx.x;
+  JbJobState* st = ws.state + jobid;
   const int tid = threadIdx.x;
   if (st->error) {
-    if (tid == 0) { st->size = 0; if (sizes_out) sizes_out[blockIdx.x] = 0; }
+    if (tid == 0) { st->size = 0; if (sizes_out) sizes_out[jobid] = 0; }
     return;
   }
   // prefix of the 0xFF counts of each scan's tiles
@@ -298,14 +268,14 @@ __global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*p
     uint32_t carry = 0;
     for (uint32_t base = 0; base < ntiles; base += 256) {
       uint32_t k = base + tid;
-      uint32_t v = k < ntiles ? tf[k] : 0, total;
+      uint32_t v = k < ntiles ? __ldcg(tf + k) : 0, total;          // written by the job's other CTAs: read at L2
       uint32_t ex = cta_exclusive_scan(v, wsum, &total);
       if (k < ntiles) tf[k] = carry + ex;
       carry += total;
     }
     if (tid == 0) s_ff[s] = carry;
   }
-  const JbHuff* hc = ws.huff + (size_t)blockIdx.x * 4;
+  const JbHuff* hc = ws.huff + (size_t)jobid * 4;
   if (tid == 0) {
     uint32_t off = 20 + 69 + 69;
     for (int t = 0; t < 4; t++) {
@@ -329,7 +299,7 @@ __global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*p
     for (int s = 0; s < 3; s++) { st->seg_out[s] = s_seg_out[s]; st->seg_ff[s] = s_ff[s]; }
     if (s_err) atomicOr(&st->error, (uint32_t)JB_ERR_SLOT);
     st->size = s_err ? 0 : off;
-    if (sizes_out) sizes_out[blockIdx.x] = s_err ? 0 : off;
+    if (sizes_out) sizes_out[jobid] = s_err ? 0 : off;
   }
   __syncthreads();
   if (s_err) return;
@@ -369,6 +339,53 @@ __global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out /*p
   }
   if (tid == 64) { out[s_size - 2] = 0xFF; out[s_size - 1] = 0xD9; }            // encoder.c:637-641
 }
+
+// One warp per 4 KiB tile (8 x 16 bytes per lane, one warp reduction, no barrier).  The CTA that finishes a job last lays its file out.
+__global__ void __launch_bounds__(256) k_count_ff(JbWs ws, uint32_t* sizes_out) {
+  const JbJob job = ws.jobs[blockIdx.y];
+  JbJobState* st = ws.state + blockIdx.y;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the tiles of the three scans form one list, so that a warp's work does not wait for the scans before it
+  uint32_t nfull3[3], nt[3], word3[3];
+#pragma unroll
+  for (int s = 0; s < 3; s++) { nfull3[s] = st->seg_bits[s] >> 3; nt[s] = (nfull3[s] + JB_STUFF_TILE - 1) / JB_STUFF_TILE; word3[s] = st->seg_word[s]; }
+  const uint32_t total_tiles = st->error ? 0u : nt[0] + nt[1] + nt[2];
+  for (uint32_t f = blockIdx.x * 8u + warp; f < total_tiles; f += gridDim.x * 8u) {
+    const int s = f < nt[0] ? 0 : (f < nt[0] + nt[1] ? 1 : 2);
+    const uint32_t t = f - (s == 0 ? 0u : s == 1 ? nt[0] : nt[0] + nt[1]);
+    const uint32_t nfull = s == 0 ? nfull3[0] : s == 1 ? nfull3[1] : nfull3[2];
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(ws.scratch + job.scratch_off + (s == 0 ? word3[0] : s == 1 ? word3[1] : word3[2]));
+    uint4 v[JB_STUFF_TILE / 512];                      // all loads first: one round trip to memory per tile
+#pragma unroll
+    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
+      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
+      v[j] = __ldg(reinterpret_cast<const uint4*>(src + (off < nfull ? off : 0u)));
+    }
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int j = 0; j < JB_STUFF_TILE / 512; j++) {
+      const uint32_t off = t * JB_STUFF_TILE + ((uint32_t)j * 32u + lane) * 16u;
+      cnt += count_ff16(v[j], off < nfull ? min(16u, nfull - off) : 0u);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if (lane == 0) ws.tile_ff[job.tile_off + s * job.tiles_per_seg + t] = cnt;
+  }
+#if JB_FUSE_LAYOUT
+  __shared__ uint32_t s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&st->ctas_counted, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  layout_job(ws, blockIdx.y, job, sizes_out);
+#endif
+}
+#if !JB_FUSE_LAYOUT
+__global__ void __launch_bounds__(256) k_layout(JbWs ws, uint32_t* sizes_out) { layout_job(ws, blockIdx.x, ws.jobs[blockIdx.x], sizes_out); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // One 4 KiB tile of scan bytes per CTA step.  The stuffed tile is assembled in shared memory at the byte phase of its
@@ -474,10 +491,12 @@ void jb_launch_scan(const JbWs& ws, int njobs, uint32_t max_chunks, cudaStream_t
 void jb_launch_pack(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, cudaStream_t st) {
   k_pack<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw);
 }
-void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st) {
-  k_count_ff<<<dim3((ctas_per_job + 3) / 4, njobs), 256, 0, st>>>(ws);     // a warp per tile: a quarter of k_stuff's CTAs covers the same tiles
+void jb_launch_count_ff(const JbWs& ws, int njobs, uint32_t ctas_per_job, uint32_t* sizes_out, cudaStream_t st) {
+  k_count_ff<<<dim3((ctas_per_job + 3) / 4, njobs), 256, 0, st>>>(ws, sizes_out);     // a warp per tile: a quarter of k_stuff's CTAs covers the same tiles
+#if !JB_FUSE_LAYOUT
+  k_layout<<<njobs, 256, 0, st>>>(ws, sizes_out);
+#endif
 }
-void jb_launch_layout(const JbWs& ws, int njobs, uint32_t* sizes_out, cudaStream_t st) { k_layout<<<njobs, 256, 0, st>>>(ws, sizes_out); }
 void jb_launch_stuff(const JbWs& ws, int njobs, uint32_t ctas_per_job, cudaStream_t st) {
   k_stuff<<<dim3(ctas_per_job, njobs), 256, 0, st>>>(ws);
 }

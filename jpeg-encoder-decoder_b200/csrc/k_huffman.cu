@@ -62,9 +62,17 @@ struct TabSmem {
   int next[257];
   int tail[257];
   int grp[257 + 31];     // representative (chain head) of each symbol
+  int clf[32];           // code_len_freq
+  int sorted[256], slen[256], code[256];
 };
 
-constexpr int TAB_WARPS = 4;
+// Warps (= tables) per CTA.  r2 measured 16 (a quarter of the CTAs, so that a multi-lane batch leaves more SMs to the other
+// lanes' k_pixels_to_tokens): 53 us against 32 us per 64-job wave, and a slower step - the merge loop is issue-dense and four
+// warps per scheduler slow each other down more than the freed SMs are worth.
+#ifndef JB_TAB_WARPS
+#define JB_TAB_WARPS 4
+#endif
+constexpr int TAB_WARPS = JB_TAB_WARPS;
 
 // warp-wide minimum: one REDUX for 32-bit keys, a shuffle tree for 64-bit keys
 __device__ __forceinline__ unsigned warp_min(unsigned v) { return __reduce_min_sync(0xFFFFFFFFu, v); }
@@ -80,7 +88,8 @@ __device__ __forceinline__ unsigned long long warp_min(unsigned long long v) {
 // KeyT = unsigned when every frequency is below 2^23 (crops up to 2^23 pixels), else unsigned long long.
 template <typename KeyT>
 __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int ntables) {
-  __shared__ TabSmem sm_all[TAB_WARPS];
+  extern __shared__ __align__(16) unsigned char tab_smem_raw[];
+  TabSmem* sm_all = reinterpret_cast<TabSmem*>(tab_smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * TAB_WARPS + warp;
   if (t >= ntables) return;
@@ -152,14 +161,10 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
   // sym_sorted[256], i.e. sym_code_len[0], and zeroes the length of the symbol with that number.  The encoder's
   // histograms always hold a DC category and an EOB, and its walker emits at most 162 of the 256 AC symbols; the kernel
   // stays inside its arrays for both cases instead of replaying the overruns (tests exclude them).
-  __shared__ int s_clf[TAB_WARPS][32];
-  __shared__ int s_sorted[TAB_WARPS][256];
-  __shared__ int s_slen[TAB_WARPS][256];
-  __shared__ int s_code[TAB_WARPS][256];
-  int* clf = s_clf[warp];
-  int* sorted = s_sorted[warp];
-  int* slen = s_slen[warp];
-  int* code = s_code[warp];
+  int* clf = sm.clf;
+  int* sorted = sm.sorted;
+  int* slen = sm.slen;
+  int* code = sm.code;
   for (int k = lane; k < 256; k += 32) { sorted[k] = -1; slen[k] = 0; code[k] = -1; }
   clf[lane] = 0;
   __syncwarp();
@@ -214,6 +219,9 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
     hc->sym_sorted[k] = sorted[k];
     hc->sym_code_len[k] = slen[k];
     hc->sym_code[k] = code[k];
+    // the entropy kernels' packed form (what k_pack_tables derives from a huff_code)
+    const int l = slen[k];
+    ws.enc[(size_t)t * 256 + k] = (l > 0 && l <= 16) ? ((uint32_t)code[k] << 5) | (uint32_t)l : 0u;
   }
 }
 
@@ -235,10 +243,21 @@ __global__ void k_pack_tables(JbWs ws, int ntables) {
 void jb_launch_symbol_stats(const JbWs& ws, int njobs, uint32_t max_chunks, int dc_from_raw, int store_dc_diff, cudaStream_t st) {
   k_symbol_stats<<<dim3(max_chunks, njobs), JB_CHUNK_BLOCKS, 0, st>>>(ws, dc_from_raw, store_dc_diff);
 }
+// Also writes the packed tables (ws.enc): k_pack_tables is needed only for caller-provided huff_codes.
 void jb_launch_build_huffman(const JbWs& ws, int njobs, bool wide_keys, cudaStream_t st) {
+  static bool opted[64][2] = {};          // function attributes are per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  const int smem = (int)sizeof(TabSmem) * TAB_WARPS;
+  if (!opted[dev][wide_keys ? 1 : 0]) {
+    if (wide_keys) cudaFuncSetAttribute(k_build_huffman<unsigned long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    else cudaFuncSetAttribute(k_build_huffman<unsigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    opted[dev][wide_keys ? 1 : 0] = true;
+  }
   int nt = njobs * 4;
-  if (wide_keys) k_build_huffman<unsigned long long><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
-  else k_build_huffman<unsigned><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, 0, st>>>(ws, nt);
+  if (wide_keys) k_build_huffman<unsigned long long><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, smem, st>>>(ws, nt);
+  else k_build_huffman<unsigned><<<(nt + TAB_WARPS - 1) / TAB_WARPS, TAB_WARPS * 32, smem, st>>>(ws, nt);
 }
 void jb_launch_pack_tables(const JbWs& ws, int njobs, cudaStream_t st) {
   k_pack_tables<<<njobs * 4, 256, 0, st>>>(ws, njobs * 4);

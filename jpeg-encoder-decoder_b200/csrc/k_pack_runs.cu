@@ -3,10 +3,10 @@
 //   k_runs_prepare    per job: the first DC token of every run (encoder.c:168-177 predicts across the whole plane, a run only
 //                     knows its own blocks) with its histogram entry; exclusive prefix of the runs' token counts inside each
 //                     scan = where each run goes in scan order
-//   k_compact_tokens  per run (one warp): copies the run's tokens into scan order (ws.tok2) and adds their code bits
+//   k_compact_tokens  per batch of 16 consecutive runs (one warp): copies the runs' tokens into scan order (ws.tok2) and adds their code bits
 //                     (code length + magnitude bits [+ ZRL codes]) to the totals of the token chunks they land in
-//   k_scan_tchunks    per job: exclusive prefix of the chunk bits inside each of the three scans, scan placement in the
-//                     job's scratch area, clearing of the words that two chunks share
+//                     The CTA that finishes a job last then scans (scan_tchunks): exclusive prefix of the chunk bits inside
+//                     each of the three scans, scan placement in the job's scratch area, clearing of the words two chunks share
 //   k_pack_tchunks    per chunk of 256 tokens (one warp): 8 consecutive tokens per lane are concatenated in registers, a warp
 //                     scan gives the bit offsets, the chunk's bits are assembled in shared memory and flushed as big-endian
 //                     words (the first and the last word of a chunk are OR-ed into place)
@@ -18,6 +18,9 @@ namespace {
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 constexpr int PR_WARPS = 8;                 // warps per CTA
+#ifndef JB_FUSE_SCAN
+#define JB_FUSE_SCAN 0
+#endif
 constexpr int PR_TOK = JB_TCHUNK / 32;      // tokens per lane
 static_assert(PR_TOK == 8, "the register concatenation below is written for 8 tokens per lane");
 // a token is at most 3 ZRL codes + one code + 11 magnitude bits = 75 bits
@@ -96,71 +99,10 @@ __global__ void __launch_bounds__(256) k_runs_prepare(JbWs ws) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
-  __shared__ uint32_t enc[2][512];
-  const JbJob job = ws.jobs[blockIdx.y];
-  const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
-  load_enc(ws, blockIdx.y, enc);
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* tok2 = ws.tok2 + job.tok_off;
-  uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
-  // the record of the next run is fetched while the current one is copied (one dependent global load less per run)
-  const uint32_t stride = gridDim.x * PR_WARPS;
-  uint32_t r = blockIdx.x * PR_WARPS + warp;
-  uint4 rec = make_uint4(0, 0, 0, 0);
-  uint32_t dnext = 0;
-  if (r < nr) { rec = __ldg(reinterpret_cast<const uint4*>(ws.runs + job.run_off + r)); dnext = __ldg(ws.run_base + job.run_off + r); }
-  for (; r < nr; r += stride) {
-    JbRun run;
-    run.tok = rec.x; run.ntok = rec.y; run.dc = rec.z; run.pad = rec.w;
-    const uint32_t d0 = dnext;
-    if (r + stride < nr) { rec = __ldg(reinterpret_cast<const uint4*>(ws.runs + job.run_off + r + stride)); dnext = __ldg(ws.run_base + job.run_off + r + stride); }
-    const uint32_t* e = enc[run_scan(r, nrc) ? 1 : 0];
-    const uint32_t zrl_len = e[0xF0] & 31u;
-    const uint32_t* tok = ws.tok + run.tok;
-    for (uint32_t k0 = 0; k0 < run.ntok; k0 += 256) {       // up to 8 independent loads per lane in flight
-      const int nj = (int)min(8u, (run.ntok - k0 + 31u) >> 5);      // warp-uniform: short runs (chroma) skip the empty slices
-      uint32_t t8[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint32_t k = k0 + 32 * j + lane;
-        t8[j] = 0u;
-        if (j < nj && k < run.ntok) t8[j] = __ldg(tok + k);
-      }
-      // the 256 tokens of this step land in at most two chunks
-      const uint32_t ca = (d0 + k0) / JB_TCHUNK;
-      uint32_t la = 0, lb = 0;
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        if (j >= nj) break;                                           // uniform
-        const uint32_t k = k0 + 32 * j + lane;
-        if (k < run.ntok) {
-          const uint32_t t = t8[j];
-          const uint32_t ent = e[(t >> 15) & 0x1FF], z = t >> 24;
-          const uint32_t clen = ent & 31u;                                          // <= 27 bits: code + magnitude bits
-          // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
-          tok2[d0 + k] = z ? (t << 5) | 31u : ent | ((t & 0x7FFu) << 5);
-          const uint32_t len = clen + z * zrl_len;
-          if ((d0 + k) / JB_TCHUNK == ca) la += len; else lb += len;
-        }
-      }
-      la = __reduce_add_sync(FULL, la);
-      lb = __reduce_add_sync(FULL, lb);
-      if (lane == 0) {
-        if (la) atomicAdd(&cbits[ca], la);
-        if (lb) atomicAdd(&cbits[ca + 1], lb);
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
-  __shared__ uint32_t wsum[9];
-  __shared__ uint32_t s_word[4];
-  const JbJob job = ws.jobs[blockIdx.x];
-  JbJobState* st = ws.state + blockIdx.x;
+// Per job, once all its runs are compacted: exclusive prefix of the chunk bits inside each scan, placement of the scans in
+// the job's scratch area, clearing of the words two chunks share.  Runs in the CTA that finishes the job's compaction last.
+__device__ __forceinline__ void scan_tchunks(const JbWs& ws, uint32_t jobid, const JbJob& job, uint32_t* wsum /*[9]*/, uint32_t* s_word /*[4]*/) {
+  JbJobState* st = ws.state + jobid;
   const uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
   uint32_t* cbase = ws.tchunk_base + job.tchunk_off;
   uint32_t seg_bits[3];
@@ -169,7 +111,7 @@ __global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
     uint32_t carry = 0;
     for (uint32_t b = 0; b < n; b += 256) {
       const uint32_t k = b + threadIdx.x;
-      uint32_t v = k < n ? cbits[c0 + k] : 0, total;
+      uint32_t v = k < n ? __ldcg(cbits + c0 + k) : 0, total;            // accumulated by atomics of other CTAs: read at L2
       const uint32_t ex = cta_exclusive_scan(v, wsum, &total);
       if (k < n) cbase[c0 + k] = carry + ex;
       carry += total;
@@ -200,6 +142,116 @@ __global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
   }
 }
 
+// A warp takes a *batch* of CP_BATCH consecutive runs of one scan: their records arrive with one load per lane and reach the
+// run loop by shuffles, their destinations are contiguous in scan order, and the code bits of the tokens are kept per lane for
+// the current token chunk and the next one and leave with one warp reduction per chunk (r2: one warp per run paid 40
+// warp-instructions of set-up per run and 70 per 256-token step, 61 % of the kernel, on 164 000 runs per 64-frame wave of which
+// half - the chroma runs - hold 38 tokens).
+#ifndef JB_CP_BATCH
+#define JB_CP_BATCH 16
+#endif
+#ifndef JB_CP_STEP
+#define JB_CP_STEP 4
+#endif
+constexpr int CP_BATCH = JB_CP_BATCH;      // runs per batch
+constexpr int CP_STEP = JB_CP_STEP;        // 32-token slices whose loads are in flight together
+__global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
+  __shared__ uint32_t enc[2][512];
+  const JbJob job = ws.jobs[blockIdx.y];
+  const uint32_t nrc = jb_runs_chroma(job.w, job.h);
+  load_enc(ws, blockIdx.y, enc);
+  __syncthreads();
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* tok2 = ws.tok2 + job.tok_off;
+  uint32_t* cbits = ws.tchunk_bits + job.tchunk_off;
+  const uint32_t nb_y = (2u * nrc + CP_BATCH - 1) / CP_BATCH, nb_c = (nrc + CP_BATCH - 1) / CP_BATCH, nbatch = nb_y + 2u * nb_c;
+  for (uint32_t b = blockIdx.x * PR_WARPS + warp; b < nbatch; b += gridDim.x * PR_WARPS) {
+    const int s = b < nb_y ? 0 : (b < nb_y + nb_c ? 1 : 2);
+    const uint32_t first = (b - (s == 0 ? 0u : s == 1 ? nb_y : nb_y + nb_c)) * CP_BATCH;
+    const uint32_t r0 = s == 0 ? 0u : (s == 1 ? 2u * nrc : 3u * nrc), ns = s == 0 ? 2u * nrc : nrc;
+    const uint32_t nvalid = min((uint32_t)CP_BATCH, ns - first);
+    uint32_t src_l = 0, n_l = 0, d_l = 0;
+    if (lane < nvalid) {
+      const uint2 rec = __ldg(reinterpret_cast<const uint2*>(ws.runs + job.run_off + r0 + first + lane));     // first token, tokens
+      src_l = rec.x; n_l = rec.y;
+      d_l = __ldg(ws.run_base + job.run_off + r0 + first + lane);
+    }
+    const uint32_t* e = enc[s ? 1 : 0];
+    const uint32_t zrl_len = e[0xF0] & 31u;
+    // code bits of the tokens that land in chunk cA (accA) and cA + 1 (accB), per lane
+    uint32_t cA = __shfl_sync(FULL, d_l, 0) / JB_TCHUNK, accA = 0, accB = 0;
+    // (run, step) pairs in one loop, software-pipelined: the loads of the next step - of this run or of the next one - are in
+    // flight while the current step is resolved and stored
+    uint32_t r = 0, k0 = 0;
+    uint32_t src = __shfl_sync(FULL, src_l, 0), n = __shfl_sync(FULL, n_l, 0), d = __shfl_sync(FULL, d_l, 0);
+    uint32_t t[CP_STEP];
+#pragma unroll
+    for (int j = 0; j < CP_STEP; j++) t[j] = 32u * j + lane < n ? __ldg(ws.tok + src + lane + 32 * j) : JB_TOKEN_VOID;
+    while (r < nvalid) {
+      uint32_t r2 = r, k2 = k0 + 32 * CP_STEP, src2 = src, n2 = n, d2 = d;
+      if (k2 >= n) {
+        r2 = r + 1; k2 = 0;
+        src2 = __shfl_sync(FULL, src_l, r2 & 31); n2 = __shfl_sync(FULL, n_l, r2 & 31); d2 = __shfl_sync(FULL, d_l, r2 & 31);
+        if (r2 >= nvalid) n2 = 0;
+      }
+      uint32_t tn[CP_STEP];
+#pragma unroll
+      for (int j = 0; j < CP_STEP; j++) tn[j] = k2 + 32u * j + lane < n2 ? __ldg(ws.tok + src2 + k2 + lane + 32 * j) : JB_TOKEN_VOID;
+      if (k0 < n) {
+        const uint32_t cs = (d + k0) / JB_TCHUNK;       // destinations are contiguous: the chunk of a step's first token is cA or cA + 1
+        if (cs != cA) {
+          accA = __reduce_add_sync(FULL, accA);
+          if (lane == 0 && accA) atomicAdd(&cbits[cA], accA);
+          accA = accB; accB = 0; cA = cs;
+        }
+        const uint32_t rem = n - k0;                    // tokens of the run from k0 on
+        uint32_t* dp = tok2 + d + k0 + lane;
+#pragma unroll
+        for (int j = 0; j < CP_STEP; j++) {
+          if (32u * j >= rem) break;                    // warp-uniform
+          const uint32_t tk = t[j], ent = e[(tk >> 15) & 0x1FFu], z = tk >> 24;
+          // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
+          if (32u * j + lane < rem) dp[32 * j] = z ? (tk << 5) | 31u : ent | ((tk & 0x7FFu) << 5);
+          const uint32_t len = (ent & 31u) + z * zrl_len;                               // a void token: no bits
+          const bool in_b = (d + k0 + 32u * j + lane) / JB_TCHUNK != cA;                // a step spans at most two chunks
+          accA += in_b ? 0u : len;
+          accB += in_b ? len : 0u;
+        }
+      }
+      r = r2; k0 = k2; src = src2; n = n2; d = d2;
+#pragma unroll
+      for (int j = 0; j < CP_STEP; j++) t[j] = tn[j];
+    }
+    accA = __reduce_add_sync(FULL, accA);
+    accB = __reduce_add_sync(FULL, accB);
+    if (lane == 0) {
+      if (accA) atomicAdd(&cbits[cA], accA);
+      if (accB) atomicAdd(&cbits[cA + 1], accB);
+    }
+  }
+#if JB_FUSE_SCAN
+  // the CTA that finishes the job last scans its chunks (one launch and one thin kernel less per wave)
+  __shared__ uint32_t s_wsum[9], s_word[4], s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(&ws.state[blockIdx.y].ctas_compacted, 1u) == gridDim.x - 1u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  scan_tchunks(ws, blockIdx.y, job, s_wsum, s_word);
+#endif
+}
+
+#if !JB_FUSE_SCAN
+__global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
+  __shared__ uint32_t s_wsum[9], s_word[4];
+  scan_tchunks(ws, blockIdx.x, ws.jobs[blockIdx.x], s_wsum, s_word);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // OR `len` (<= 32) bits into the MSB-first bit image at bit position pos (rare path: lanes whose tokens carry ZRLs).
 __device__ __forceinline__ void or_bits_s(uint32_t* img, uint32_t pos, uint32_t bits, uint32_t len) {
@@ -329,9 +381,11 @@ static uint32_t item_ctas(int njobs, uint32_t max_items) {
 }
 void jb_launch_runs_prepare(const JbWs& ws, int njobs, cudaStream_t st) { k_runs_prepare<<<njobs, 256, 0, st>>>(ws); }
 void jb_launch_compact_tokens(const JbWs& ws, int njobs, uint32_t max_runs, cudaStream_t st) {
-  k_compact_tokens<<<dim3(item_ctas(njobs, max_runs), njobs), PR_WARPS * 32, 0, st>>>(ws);
+  k_compact_tokens<<<dim3(item_ctas(njobs, (max_runs + CP_BATCH - 1) / CP_BATCH + 3), njobs), PR_WARPS * 32, 0, st>>>(ws);
+#if !JB_FUSE_SCAN
+  k_scan_tchunks<<<njobs, 256, 0, st>>>(ws);
+#endif
 }
-void jb_launch_scan_tchunks(const JbWs& ws, int njobs, cudaStream_t st) { k_scan_tchunks<<<njobs, 256, 0, st>>>(ws); }
 void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cudaStream_t st) {
   k_pack_tchunks<<<dim3(item_ctas(njobs, max_tchunks), njobs), PR_WARPS * 32, 0, st>>>(ws);
 }

@@ -178,19 +178,38 @@ __global__ void __launch_bounds__(TAB_WARPS * 32) k_build_huffman(JbWs ws, int n
     }
     if (overflow) atomicOr(&state->error, (uint32_t)JB_ERR_CODELEN);
   }
-  // sym_sorted (encoder.c:262-268): symbols 0..255 ordered by (pre-limit length, symbol); ballots give each symbol its rank
+  // sym_sorted (encoder.c:262-268): symbols 0..255 ordered by (pre-limit length, symbol).  Rank of symbol k = lane + 32 j:
+  // symbols of shorter lengths + symbols of its own length in earlier slots j + those in lower lanes of its slot
+  // (MATCH.ANY groups the lanes of a slot by length).  r2: a ballot per (length 1..31, slot) was 52 % of the kernel's time.
   {
-    int n = 0;
-    for (int l = 1; l < 32; l++) {
+    int* cnt = sm.tail;                 // dead after the merge loop: [0..31] symbols seen so far per length, [32..63] first rank per length
+    cnt[lane] = 0;
+    __syncwarp();
+    int within[8], lens[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const int k = lane + 32 * j;
-        const bool hit = sm.len[k] == l;
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) sorted[n + __popc(bal & ((1u << lane) - 1u))] = k;
-        n += __popc(bal);
-      }
+    for (int j = 0; j < 8; j++) {
+      int l = sm.len[lane + 32 * j];
+      if (l > 31) l = 0;                 // never equal to a length the reference's loop visits: not sorted
+      lens[j] = l;
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, l);
+      const int seen = cnt[l];
+      within[j] = seen + __popc(peers & ((1u << lane) - 1u));
+      __syncwarp();
+      if (l && lane == __ffs(peers) - 1) cnt[l] = seen + __popc(peers);
+      __syncwarp();
     }
+    const int c = lane ? cnt[lane] : 0;
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    cnt[32 + lane] = inc - c;
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (lens[j]) sorted[cnt[32 + lens[j]] + within[j]] = lane + 32 * j;
   }
   __syncwarp();
   if (lane == 0) {

@@ -210,3 +210,37 @@ def test_fmt2rgb888_known_answers(oracle):
     assert [tuple(int(x) for x in row) for row in got] == list(kat.values())
     g = np.arange(256, dtype=np.uint8)
     assert np.array_equal(oracle.fmt2rgb888(g, 2, 256), np.repeat(g[:, None], 3, axis=1))
+
+
+# ---- second oracle: the upstream encoder utils/original.c --------------------------------------
+UPSTREAM = os.path.join(ROOT, "oracle", "_ref", "upstream_original")
+
+
+def _run_upstream(tmp_path, rgb):
+    """utils/original.c is a program: <ppm> <quality> -> ./out.jpg, and it needs ./hisParts/ for its stage dumps."""
+    import subprocess
+    (tmp_path / "hisParts").mkdir(exist_ok=True)
+    h, w, _ = rgb.shape
+    (tmp_path / "in.ppm").write_bytes(b"P6\n%d %d\n255\n" % (w, h) + rgb.tobytes())
+    subprocess.run([UPSTREAM, "in.ppm", "50"], cwd=tmp_path, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=120)
+    return (tmp_path / "out.jpg").read_bytes()
+
+
+@pytest.mark.skipif(not os.path.exists(UPSTREAM), reason="oracle/_ref/upstream_original not built (needs /root/reference)")
+@pytest.mark.parametrize("key,src", [("sample_64x64_bgr", "64"), ("sample_640x640_bgr", "640"), ("sample_640x640_diffs_bgr", "640_diffs")])
+def test_upstream_original_agrees_on_samples(tmp_path, frames, golden, oracle, key, src):
+    """The upstream program reads the PPM as R,G,B; the reference reads the same bytes as B,G,R (encoder.c:132-135): the
+    reference's output for the byte-reversed frame (the *_bgr fixtures) must be the upstream's output for the file."""
+    jpg = _run_upstream(tmp_path, frames.sample_rgb(src))
+    assert sha(jpg) == golden["encode"][key]["sha256"]
+    assert jpg == oracle.encode(frames.sample_bgr(src))["jpg"].tobytes()
+
+
+@pytest.mark.skipif(not os.path.exists(UPSTREAM), reason="oracle/_ref/upstream_original not built (needs /root/reference)")
+def test_upstream_original_agrees_on_random_images(tmp_path, oracle):
+    rng = np.random.default_rng(11)
+    for (h, w) in [(16, 16), (32, 48), (64, 16), (48, 80)]:
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if h == 32:
+            rgb[:] = rgb[:, :, :1]                      # grey: every pixel on an integer boundary of the colour chain
+        assert _run_upstream(tmp_path, rgb) == oracle.encode(np.ascontiguousarray(rgb[:, :, ::-1]))["jpg"].tobytes(), (h, w)

@@ -255,6 +255,9 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
       CK(cudaStreamWaitEvent(l.stream_hi, l.pass1_done, 0));
       st = l.stream_hi;
     }
+    static int ablate = -1;               // development knob (timing experiments, wrong output): JPEGB200_ABLATE_PASS2=1 stops after pass 1
+    if (ablate < 0) { const char* e = getenv("JPEGB200_ABLATE_PASS2"); ablate = e ? atoi(e) : 0; }
+    if (ablate == 1) { CK(cudaGetLastError()); return 0; }
     { StageTimer t(c, st, ST_FIX); jb_launch_fix_tokens(ws, st); }
     CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
     { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }

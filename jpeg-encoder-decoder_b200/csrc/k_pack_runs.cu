@@ -293,10 +293,7 @@ __device__ __forceinline__ void concat_store(uint32_t* stage, const uint32_t (&w
   }
 }
 
-#ifndef JB_PACK_MIN_CTAS
-#define JB_PACK_MIN_CTAS 1
-#endif
-__global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunks(JbWs ws) {
+__global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;
@@ -305,39 +302,24 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunk
   for (int s = 0; s < 3; s++) { nchunk[s] = (st->tok_total[s] + JB_TCHUNK - 1) / JB_TCHUNK; total_chunks += nchunk[s]; }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* stage = stage_all[warp];
-  // The scans' placement and totals, once per CTA; a chunk's tokens, bit offset and bit total are fetched one chunk ahead
-  // (r2: a fifth of the kernel's warp-stall samples sat on these loads).
-  uint32_t tstart[3], ttotal[3], sword[3];
-#pragma unroll
-  for (int s = 0; s < 3; s++) { tstart[s] = st->tok_start[s] / JB_TCHUNK; ttotal[s] = st->tok_total[s]; sword[s] = st->seg_word[s]; }
-  struct Chunk { uint4 a, b; uint32_t base_bits, total, ntok; int s; };
-  auto fetch = [&](uint32_t f) {
-    Chunk ch;
-    ch.a = make_uint4(0, 0, 0, 0); ch.b = ch.a; ch.base_bits = 0; ch.total = 0; ch.ntok = 0; ch.s = 0;
-    if (f >= total_chunks) return ch;
-    ch.s = f < nchunk[0] ? 0 : (f < nchunk[0] + nchunk[1] ? 1 : 2);
-    const uint32_t c = f - (ch.s == 0 ? 0u : ch.s == 1 ? nchunk[0] : nchunk[0] + nchunk[1]);
-    const uint32_t cg = (ch.s == 0 ? tstart[0] : ch.s == 1 ? tstart[1] : tstart[2]) + c;      // chunk id inside the job
-    ch.ntok = min((uint32_t)JB_TCHUNK, (ch.s == 0 ? ttotal[0] : ch.s == 1 ? ttotal[1] : ttotal[2]) - c * JB_TCHUNK);
-    ch.base_bits = __ldg(ws.tchunk_base + job.tchunk_off + cg);
-    ch.total = __ldg(ws.tchunk_bits + job.tchunk_off + cg);
-    const uint4* tp = reinterpret_cast<const uint4*>(ws.tok2 + job.tok_off + (size_t)cg * JB_TCHUNK) + 2 * lane;
-    if (lane * PR_TOK < ch.ntok) ch.a = __ldg(tp);
-    if (lane * PR_TOK + 4 < ch.ntok) ch.b = __ldg(tp + 1);
-    return ch;
-  };
-  const uint32_t fstride = gridDim.x * PR_WARPS;
-  Chunk nxt = fetch(blockIdx.x * PR_WARPS + warp);
-  for (uint32_t f = blockIdx.x * PR_WARPS + warp; f < total_chunks; f += fstride) {
-    const Chunk cur = nxt;
-    nxt = fetch(f + fstride);
-    const int s = cur.s;
-    const uint32_t ntok = cur.ntok, base_bits = cur.base_bits, total = cur.total;
+  for (uint32_t f = blockIdx.x * PR_WARPS + warp; f < total_chunks; f += gridDim.x * PR_WARPS) {
+    const int s = f < nchunk[0] ? 0 : (f < nchunk[0] + nchunk[1] ? 1 : 2);
+    const uint32_t c = f - (s == 0 ? 0u : s == 1 ? nchunk[0] : nchunk[0] + nchunk[1]);
+    const uint32_t cg = st->tok_start[s] / JB_TCHUNK + c;                      // chunk id inside the job
+    const uint32_t ntok = min((uint32_t)JB_TCHUNK, st->tok_total[s] - c * JB_TCHUNK);
+    const uint32_t base_bits = ws.tchunk_base[job.tchunk_off + cg], total = ws.tchunk_bits[job.tchunk_off + cg];
     const uint32_t phase = base_bits & 31;
-    uint32_t* gw = ws.scratch + job.scratch_off + (s == 0 ? sword[0] : s == 1 ? sword[1] : sword[2]) + (base_bits >> 5);   // word that holds the chunk's first bit
+    uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the chunk's first bit
     const bool first_shared = phase != 0 || total < 32;
     const uint32_t last_word = (phase + total - 1) >> 5;
-    const uint32_t t8[PR_TOK] = {cur.a.x, cur.a.y, cur.a.z, cur.a.w, cur.b.x, cur.b.y, cur.b.z, cur.b.w};
+    const uint4* tp = reinterpret_cast<const uint4*>(ws.tok2 + job.tok_off + (size_t)cg * JB_TCHUNK) + 2 * lane;
+    uint32_t t8[PR_TOK];
+    {
+      uint4 a = make_uint4(0, 0, 0, 0), b = a;
+      if (lane * PR_TOK < ntok) a = __ldg(tp);
+      if (lane * PR_TOK + 4 < ntok) b = __ldg(tp + 1);
+      t8[0] = a.x; t8[1] = a.y; t8[2] = a.z; t8[3] = a.w; t8[4] = b.x; t8[5] = b.y; t8[6] = b.z; t8[7] = b.w;
+    }
     // resolved tokens (k_compact_tokens): code word << 5 | length; length 31 escapes to a raw token that carries ZRLs
     const uint32_t* enc_ac = ws.enc + ((size_t)blockIdx.y * 4 + (s ? 3 : 1)) * 256;
     uint32_t word[PR_TOK], len[PR_TOK], zr = 0, nbits = 0, zrl_code = 0, zrl_len = 0;

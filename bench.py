@@ -418,6 +418,59 @@ def main():
         sub_records.append(device_record("ramp", 1920, 1280, 128, "config 4, class 'ramp': 128 x 1920x1280 (R=G=B=(x+y+f)&255: every pixel on an exact-integer colour boundary)"))
         sub_records.append(device_record("natural", 3840, 2160, 256, "config 5: 256 x 3840x2160 natural"))
 
+        # decoding side: 256 device-resident streams of 1920x1280 natural -> B,G,R frames; checked against the
+        # CPU statement of the same arithmetic (oracle/oracle_decode.c), which is also the CPU arm of this record
+        def decode_record(nfr=256, sw_=1920, sh_=1280):
+            x = torch.empty((nfr, sh_, sw_, 3), dtype=torch.uint8, device=dev)
+            tile_ = torch.from_numpy(fr.tile_bgr(sw_, sh_)).to(dev)
+            for i in range(nfr):
+                dx, dy = fr.natural_shift(i, sw_, sh_)
+                x[i] = torch.roll(tile_, shifts=(dy, dx), dims=(0, 1))
+            o = torch.zeros((nfr, SLOT), dtype=torch.uint8, device=dev)
+            z = torch.zeros(nfr, dtype=torch.int32, device=dev)
+            enc.encode_batch_ptr(x.data_ptr(), nfr, sw_, sh_, sw_ * sh_ * 3, o.data_ptr(), SLOT, z.data_ptr(), stream.cuda_stream)
+            torch.cuda.synchronize()
+            back = torch.zeros_like(x)
+            status = torch.full((nfr,), 7, dtype=torch.int32, device=dev)
+
+            def st_():
+                enc.decode_batch_ptr(o.data_ptr(), SLOT, z.data_ptr(), nfr, sw_, sh_, back.data_ptr(), sw_ * sh_ * 3, 0, status.data_ptr(), stream.cuda_stream)
+
+            for _ in range(2):
+                st_()
+            torch.cuda.synchronize()
+            assert not status.any().item(), "a stream did not decode"
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            ea.record(stream)
+            for _ in range(reps):
+                st_()
+            eb.record(stream)
+            torch.cuda.synchronize()
+            msr = ea.elapsed_time(eb) / reps
+            import cpu_checkers
+            orc = cpu_checkers.Oracle()
+            zs = z.cpu().numpy().astype(np.uint32)
+            checked = []
+            for i in (0, nfr - 1):                                   # bit-exact against the CPU statement
+                want = orc.decode(o[i, :int(zs[i])].cpu().numpy().tobytes(), sw_, sh_)
+                assert want["rc"] == 0 and np.array_equal(want["bgr"], back[i].cpu().numpy()), ("decode differs from the oracle decoder", i)
+                checked.append(i)
+            sample = o[:2].cpu().numpy()
+            cpu_s = orc.time_decode(np.ascontiguousarray(sample), zs[:2], sw_, sh_)
+            err = back[:8].float() - x[:8].float()
+            rec = {"workload": f"decoding side: {nfr} device-resident streams of {sw_}x{sh_} natural -> B,G,R frames (jpegb200_decode_batch)",
+                   "metric": f"Mpix/s JPEG decode ({sw_}x{sh_} 4:2:0 batch)", "value": nfr * sw_ * sh_ / 1e6 / (msr / 1e3), "unit": "Mpix/s", "frames": nfr, "steps": reps,
+                   "warmup": 2, "ms_per_step": msr, "frames_equal_to_oracle_decoder": checked,
+                   "psnr_db_vs_input": float(10 * torch.log10(255.0 ** 2 / (err ** 2).mean())),
+                   "cpu_baseline": {"value": 2 * sw_ * sh_ / 1e6 / cpu_s, "unit": "Mpix/s", "cores": 1, "kind": "port",
+                                    "sample": "2 streams, oracle/oracle_decode.c single thread (the reference has no working decoder: pixel arithmetic restated from its stubs)"}}
+            del x, o, z, back
+            torch.cuda.empty_cache()
+            return rec
+
+        sub_records.append(decode_record())
+
         # config 3: the comparator loop (main.c:137-162) through jpegb200_compare_encode_batch with HOST frames: H2D of the frames,
         # subsample + compare + device-built region jobs + encode, D2H of the streams, all inside the timed region
         for (lw, lh, nf) in ((640, 640, 65), (1920, 1280, 33)):

@@ -82,6 +82,26 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx *ctx, const uint8_t *h_src, int 
 /* Device-resident form: n packed frames at d_src -> B,G,R frames at d_bgr (3*w*h bytes each), on `stream`. */
 int jpegb200_unpack(jpegb200_ctx *ctx, const uint8_t *d_src, int fmt, int n, int w, int h, uint8_t *d_bgr, void *stream);
 
+/* ---- decoding side ---------------------------------------------------------
+ * The streams write_jpg / jpegb200_encode_batch produce (baseline, 8 bit, 4:2:0, three single-component scans, per-image
+ * Huffman tables; encoder.c:549-644) back to coefficient planes and B,G,R frames.  The reference has only stubs for this
+ * direction (utils/func_tester.c:1261-1319); the arithmetic they fix (toRgb's constants, 2 x 2 replicated chroma, de-quantise
+ * + inverse of the encoder's transform with its cosine table, DC = running sum) is what is computed, in FP64 in a fixed
+ * order.  Entropy decoding is serial per scan; the batch supplies the parallelism (one thread per scan).
+ *   d_streams   stream i at d_streams + i*slot, d_sizes[i] bytes (the layout jpegb200_encode_batch leaves); d_streams and slot
+ *               multiples of 16
+ *   d_bgr       frame i at d_bgr + i*frame_stride (multiple of 4), rows w*3 bytes apart; NULL = planes only
+ *   d_planes    optional, n x (w*h*3/2) int16: Y, Cb, Cr of every frame in the encoder's plane layout (zig-zag blocks in
+ *               raster order, DC differenced as rgb_to_dct leaves it, encoder.c:158-178); NULL = internal scratch
+ *   d_status    optional, n int32: 0 or a negative JPEGB200_DEC_* code per stream (a bad stream never stops the batch)
+ * Asynchronous with respect to the host, ordered on `stream`. */
+enum { JPEGB200_DEC_NOT_JPEG = -1, JPEGB200_DEC_BAD_MARKER = -2, JPEGB200_DEC_TRUNCATED = -3, JPEGB200_DEC_UNSUPPORTED = -4, JPEGB200_DEC_BAD_CODE = -5 };
+int jpegb200_decode_batch(jpegb200_ctx *ctx, const uint8_t *d_streams, size_t slot, const uint32_t *d_sizes, int n, int w, int h,
+                          uint8_t *d_bgr, size_t frame_stride, int16_t *d_planes, int32_t *d_status, void *stream);
+/* Same work with HOST buffers (synchronous); h_planes and h_status may be NULL. */
+int jpegb200_decode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_streams, size_t slot, const uint32_t *h_sizes, int n, int w, int h,
+                               uint8_t *h_bgr, int16_t *h_planes, int32_t *h_status);
+
 /* Multi-GPU form of the same call (batch-of-frames sharding, no collective, a frame is never split):
  * `ctxs` holds one context per GPU (jpegb200_create(&ctxs[i], i)); context i encodes the contiguous range of
  * ceil(n / nctx) frames starting at i * ceil(n / nctx) with its own host thread for the duration of the call, reading

@@ -99,6 +99,8 @@ def load_library() -> C.CDLL:
     L.jpegb200_compare_encode.argtypes = [vp, u8p, C.c_int, C.c_int, C.c_int, ip, u8p, C.c_size_t, u32p, u8p]
     L.jpegb200_compare_encode_batch.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, ip, ip, u32p, C.POINTER(C.c_uint64), vp, C.c_size_t]
     # the reference's own entry points (include/encoder.h, include/brain.h)
+    L.jpegb200_decode_batch.argtypes = [vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp]
+    L.jpegb200_decode_batch_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.jpegb200_set_dims.argtypes = [C.c_int, C.c_int]
     L.jpegb200_set_dims.restype = None
     L.rgb_to_dct.argtypes = [u8p, i16p, i16p, i16p, Area]
@@ -308,6 +310,28 @@ class Encoder:
         if (sizes == 0).any():
             raise JpegB200Error("an output did not fit its slot")
         return [out[i, : sizes[i]].tobytes() for i in range(N)]
+
+    # ---- decoding side (include/jpegb200.h: jpegb200_decode_batch*) ----
+    def decode_batch_ptr(self, d_streams: int, slot: int, d_sizes: int, n: int, w: int, h: int, d_bgr: int, frame_stride: int, d_planes: int = 0,
+                         d_status: int = 0, stream: int = 0):
+        self._check(self.lib.jpegb200_decode_batch(self.ctx, d_streams, slot, d_sizes, n, w, h, d_bgr or None, frame_stride, d_planes or None, d_status or None,
+                                                   stream or None))
+
+    def decode_streams(self, jpgs: list, w: int, h: int, planes: bool = False):
+        """jpgs: byte strings of w x h streams.  Returns (bgr (N,h,w,3) uint8, status (N,) int32[, planes (N, w*h*3/2) int16])."""
+        n = len(jpgs)
+        slot = (max(len(j) for j in jpgs) + 15) & ~15
+        buf = np.zeros((n, slot), np.uint8)
+        sizes = np.zeros(n, np.uint32)
+        for i, j in enumerate(jpgs):
+            buf[i, :len(j)] = np.frombuffer(bytes(j), np.uint8)
+            sizes[i] = len(j)
+        bgr = np.zeros((n, h, w, 3), np.uint8)
+        status = np.zeros(n, np.int32)
+        pl = np.zeros((n, w * h * 3 // 2), np.int16) if planes else None
+        self._check(self.lib.jpegb200_decode_batch_host(self.ctx, buf.ctypes.data, slot, sizes.ctypes.data, n, w, h, bgr.ctypes.data,
+                                                        pl.ctypes.data if planes else None, status.ctypes.data))
+        return (bgr, status, pl) if planes else (bgr, status)
 
     def build_tables(self, freqs: np.ndarray) -> list[dict]:
         """Test hook: device table builder on (T, 257) int32 histograms."""

@@ -192,6 +192,8 @@ struct jpegb200_ctx {
   // comparator state
   DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_saved_in, cmp_bits, cmp_outs, cmp_rout, cmp_misc, cmp_arena;
   PinBuf cmp_host;
+  // decoding side: per-stream descriptors, scratch planes / absolute DCs / samples, staging of the host variant
+  DevBuf dec_frames, dec_planes, dec_dcabs, dec_samples, dec_in, dec_sizes, dec_out, dec_planes_out;
   bool have_saved = false;
   int saved_w = 0, saved_h = 0;
 };
@@ -384,6 +386,7 @@ void jpegb200_destroy(jpegb200_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& l : c->lanes) l.release();
   for (DevBuf* b : {&c->cmp_frame, &c->cmp_sub, &c->cmp_saved, &c->cmp_saved_in, &c->cmp_bits, &c->cmp_outs, &c->cmp_rout, &c->cmp_misc, &c->cmp_arena}) b->release();
+  for (DevBuf* b : {&c->dec_frames, &c->dec_planes, &c->dec_dcabs, &c->dec_samples, &c->dec_in, &c->dec_sizes, &c->dec_out, &c->dec_planes_out}) b->release();
   c->cmp_host.release();
   if (c->fork) cudaEventDestroy(c->fork);
   delete c;
@@ -578,6 +581,74 @@ int jpegb200_unpack(jpegb200_ctx* c, const uint8_t* d_src, int fmt, int n, int w
   jb_launch_unpack(d_src, fmt, (size_t)n * w * h, d_bgr, (cudaStream_t)stream);
   c->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- decoding side ---------------------------------------------------------------------------------
+int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot, const uint32_t* d_sizes, int n, int w, int h, uint8_t* d_bgr, size_t frame_stride,
+                          int16_t* d_planes, int32_t* d_status, void* stream) {
+  if (!c || !d_streams || !d_sizes) return fail("null argument");
+  if (!d_bgr && !d_planes) return fail("nothing to produce: d_bgr and d_planes are both null");
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  if (w > 65535 || h > 65535) return fail("a baseline frame header holds 16-bit dimensions");
+  if (d_bgr && ((frame_stride & 3) || frame_stride < (size_t)3 * w * h || ((uintptr_t)d_bgr & 3))) return fail("d_bgr must be 4-byte aligned, frame_stride a multiple of 4 and >= 3*w*h");
+  if (d_planes && ((uintptr_t)d_planes & 1)) return fail("d_planes must be 2-byte aligned");
+  if (((uintptr_t)d_streams | slot) & 15) return fail("d_streams and slot must be multiples of 16 (the scans are fetched in aligned 16-byte groups)");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)w * h;
+  // the scratch buffers are reused by the next call: a caller that uses several streams orders the calls itself
+  cudaError_t e;
+  if ((e = c->dec_frames.ensure((size_t)n * jb_dec_frame_bytes())) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  if ((e = c->dec_dcabs.ensure((size_t)n * (npix / 64 * 3 / 2) * sizeof(int16_t))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  if (!d_planes) {
+    if ((e = c->dec_planes.ensure((size_t)n * (npix + npix / 2) * sizeof(int16_t))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+    d_planes = (int16_t*)c->dec_planes.p;
+  }
+  if (d_bgr && (e = c->dec_samples.ensure((size_t)n * (npix + npix / 2))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  jb_launch_decode(d_streams, slot, d_sizes, n, w, h, c->dec_frames.p, d_planes, (int16_t*)c->dec_dcabs.p, (uint8_t*)c->dec_samples.p, d_bgr, frame_stride, d_status, st);
+  c->launches += d_bgr ? 4 : 2;
+  if (d_status) c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int jpegb200_decode_batch_host(jpegb200_ctx* c, const uint8_t* h_streams, size_t slot, const uint32_t* h_sizes, int n, int w, int h, uint8_t* h_bgr, int16_t* h_planes,
+                               int32_t* h_status) {
+  if (!c || !h_streams || !h_sizes) return fail("null argument");
+  if (!h_bgr && !h_planes) return fail("nothing to produce: h_bgr and h_planes are both null");
+  if (n <= 0) return 0;
+  if (check_dims(w, h)) return -1;
+  CK(cudaSetDevice(c->device));
+  const size_t npix = (size_t)w * h, frame = 3 * npix, planes = (npix + npix / 2) * sizeof(int16_t);
+  cudaError_t e;
+  if (slot & 15) return fail("slot must be a multiple of 16");
+  if ((e = c->dec_in.ensure((size_t)n * slot)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  if ((e = c->dec_sizes.ensure((size_t)n * 8)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  if (h_bgr && (e = c->dec_out.ensure((size_t)n * frame)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  if (h_planes && (e = c->dec_planes_out.ensure((size_t)n * planes)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+  cudaStream_t st = c->lanes[0].stream;
+  uint32_t* d_sizes = (uint32_t*)c->dec_sizes.p;
+  int32_t* d_status = (int32_t*)(d_sizes + n);
+  CK(cudaMemcpyAsync(d_sizes, h_sizes, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+  // only the bytes of each stream cross the link, not the slots
+  size_t run0 = 0;
+  for (int i = 0; i < n; i++) {
+    if (h_sizes[i] > slot) return fail("stream %d is larger than its slot", i);
+    if (i + 1 == n || h_sizes[i] != slot) {            // copy [run0 .. i]: full slots in front, then the bytes of stream i
+      const size_t bytes = (size_t)(i - run0) * slot + h_sizes[i];
+      if (bytes) CK(cudaMemcpyAsync((uint8_t*)c->dec_in.p + run0 * slot, h_streams + run0 * slot, bytes, cudaMemcpyHostToDevice, st));
+      run0 = (size_t)i + 1;
+    }
+  }
+  if (jpegb200_decode_batch(c, (const uint8_t*)c->dec_in.p, slot, d_sizes, n, w, h, h_bgr ? (uint8_t*)c->dec_out.p : nullptr, frame,
+                            h_planes ? (int16_t*)c->dec_planes_out.p : nullptr, d_status, st))
+    return -1;
+  if (h_bgr) CK(cudaMemcpyAsync(h_bgr, c->dec_out.p, (size_t)n * frame, cudaMemcpyDeviceToHost, st));
+  if (h_planes) CK(cudaMemcpyAsync(h_planes, c->dec_planes_out.p, (size_t)n * planes, cudaMemcpyDeviceToHost, st));
+  if (h_status) CK(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   return 0;
 }
 

@@ -46,5 +46,13 @@ double orc_time_encode(const uint8_t *frames, int nframes, size_t frame_stride, 
 int orc_fmt2rgb888(const uint8_t *src, size_t src_len, int fmt, uint8_t *bgr);     /* esp32-camera 2.0.3 to_bmp.c, RGB565 / GRAYSCALE branches */
 double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int *regions_out, size_t *bytes_out);
 
+/* decoder for write_jpg's streams (oracle_decode.c; entropy side pinned, pixel side restated from the stubs at
+ * utils/func_tester.c:1261-1319 - "parity unpinned", see the file header).  Planes / bgr may be NULL.  *w, *h: on entry the
+ * dimensions the caller sized its buffers for (0 = any), on return the stream's.  Returns 0 or ORC_DEC_*. */
+enum { ORC_DEC_NOT_JPEG = -1, ORC_DEC_BAD_MARKER = -2, ORC_DEC_TRUNCATED = -3, ORC_DEC_UNSUPPORTED = -4, ORC_DEC_BAD_CODE = -5 };
+int orc_decode(const uint8_t *jpg, size_t n, int *w, int *h, int16_t *Y, int16_t *Cb, int16_t *Cr, uint8_t *bgr);
+void orc_idct_block(const int16_t *zz, int dc, const int *quant_natural, uint8_t *out, int stride);
+double orc_time_decode(const uint8_t *jpgs, const uint32_t *sizes, size_t slot, int nframes, int reps, uint8_t *bgr_scratch);
+
 extern const uint64_t orc_cos_bits[64];
 extern const int orc_quant_luma[64], orc_quant_chroma[64], orc_zigzag[64];

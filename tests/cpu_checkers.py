@@ -96,6 +96,25 @@ class Oracle(_Base):
         L.orc_fmt2rgb888.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.orc_time_loop.restype = C.c_double
+        L.orc_decode.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.POINTER(C.c_int16)] * 3 + [C.POINTER(C.c_uint8)]
+        L.orc_time_decode.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_uint8)]
+        L.orc_time_decode.restype = C.c_double
+
+    def decode(self, jpg, w, h):
+        """jpg: bytes / uint8 array of one stream of w x h pixels.  Returns dict(rc, w, h, Y, Cb, Cr, bgr)."""
+        jpg = np.ascontiguousarray(np.frombuffer(bytes(jpg), np.uint8))
+        n = w * h
+        Y, Cb, Cr = np.zeros(n, np.int16), np.zeros(n // 4, np.int16), np.zeros(n // 4, np.int16)
+        bgr = np.zeros((h, w, 3), np.uint8)
+        ww, hh = C.c_int(w), C.c_int(h)
+        rc = self.lib.orc_decode(_u8(jpg), jpg.size, C.byref(ww), C.byref(hh), _i16(Y), _i16(Cb), _i16(Cr), _u8(bgr))
+        return dict(rc=rc, w=ww.value, h=hh.value, Y=Y, Cb=Cb, Cr=Cr, bgr=bgr)
+
+    def time_decode(self, jpgs, sizes, w, h, reps=1):
+        """jpgs: (N, slot) uint8, sizes: (N,) uint32.  Returns seconds."""
+        scratch = np.zeros(w * h * 3, np.uint8)
+        sizes = np.ascontiguousarray(sizes, np.uint32)
+        return self.lib.orc_time_decode(_u8(jpgs), sizes.ctypes.data_as(C.POINTER(C.c_uint32)), jpgs.shape[1], jpgs.shape[0], reps, _u8(scratch))
 
     def encode(self, bgr, area=None):
         H, W, _ = bgr.shape

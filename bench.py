@@ -418,9 +418,9 @@ def main():
         sub_records.append(device_record("ramp", 1920, 1280, 128, "config 4, class 'ramp': 128 x 1920x1280 (R=G=B=(x+y+f)&255: every pixel on an exact-integer colour boundary)"))
         sub_records.append(device_record("natural", 3840, 2160, 256, "config 5: 256 x 3840x2160 natural"))
 
-        # decoding side: 256 device-resident streams of 1920x1280 natural -> B,G,R frames; checked against the
+        # decoding side: 1024 device-resident streams of 1920x1280 natural -> B,G,R frames; checked against the
         # CPU statement of the same arithmetic (oracle/oracle_decode.c), which is also the CPU arm of this record
-        def decode_record(nfr=256, sw_=1920, sh_=1280):
+        def decode_record(nfr=1024, sw_=1920, sh_=1280):
             x = torch.empty((nfr, sh_, sw_, 3), dtype=torch.uint8, device=dev)
             tile_ = torch.from_numpy(fr.tile_bgr(sw_, sh_)).to(dev)
             for i in range(nfr):

@@ -150,87 +150,132 @@ __global__ void __launch_bounds__(256) k_dec_parse(const uint8_t* __restrict__ s
 
 // Bit reader of one scan: 0xFF 0x00 -> 0xFF; past the scan's last byte it supplies 1-bits — fill_last_byte
 // (encoder.c:425-432) pads with ones and never stuffs, so a final 0xFF byte reads as the next marker's first byte.
-// The stream is fetched 16 aligned bytes at a time, one fetch ahead (a byte-wise reader spent 2000 clocks per symbol on
-// dependent loads); a word without an 0xFF byte (all but one in 64) enters the bit accumulator whole.
+// The stream is fetched in aligned 16-byte groups into a 64-byte ring per lane in shared memory; a word without an 0xFF
+// byte (all but one in 64) enters the bit buffer whole.  The fetches are issued by the whole warp at the same trips of
+// the symbol loop (prefetch) and land in the ring four trips later: a lane that fetched into registers whenever IT crossed
+// a group boundary made the whole warp wait for that load at the next lane's crossing (the scoreboard is per warp, and
+// some lane crosses on almost every trip): 700 clocks per trip.
+// The bit buffer is LEFT-ALIGNED in hi:lo (the next bit is bit 31 of hi): peeking is one shift, consuming a funnel shift.
 struct DecBits {
   const uint4* base;         // 16-byte aligned address at or before the scan's first byte
   uint32_t pos, end;         // byte offsets from base: next byte to consume, end of the scan
   uint32_t last;             // last 16-byte group (index from base) that lies inside the stream's slot: nothing beyond it is read
-  uint4 q, qn;               // the 16 bytes that hold pos, and the next 16
-  uint64_t acc;
-  int nacc;
+  uint32_t loaded;           // groups [0, loaded) have been fetched; group g sits in ring slot g & 3
+  uint32_t* ring;            // this lane's column: word w of slot s at ring[(4 s + w) * 32]
+  uint4 pre;                 // prefetched group on its way to the ring
+  bool pending;
+  uint32_t hi, lo;
+  int nacc;                  // valid bits in hi:lo
   __device__ __forceinline__ uint4 group(uint32_t k) const { return k <= last ? __ldg(base + k) : make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ void init(const uint8_t* stream, size_t slot, uint32_t start, uint32_t stop) {
+  __device__ __forceinline__ void put(uint4 v) {
+    uint32_t* d = ring + ((loaded & 3u) << 2) * 32u;
+    d[0] = v.x; d[32] = v.y; d[64] = v.z; d[96] = v.w;
+    loaded++;
+  }
+  __device__ __forceinline__ void init(const uint8_t* stream, size_t slot, uint32_t start, uint32_t stop, uint32_t* ring_column) {
     const uintptr_t a = (uintptr_t)(stream + start);
     base = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
     pos = (uint32_t)(a & 15);
     end = pos + (stop - start);
     last = (uint32_t)(((uintptr_t)(stream + slot) - (uintptr_t)base - 1) >> 4);     // slots are 16-byte aligned (checked by the C ABI)
-    q = group(0);
-    qn = group(1);
-    acc = 0;
+    ring = ring_column;
+    loaded = 0;
+    const uint4 g0 = group(0), g1 = group(1), g2 = group(2);
+    put(g0); put(g1); put(g2);
+    pending = false;
+    hi = lo = 0;
     nacc = 0;
   }
-  __device__ __forceinline__ uint32_t word_at(uint32_t p) const {        // the aligned word of q that holds byte offset p
-    const uint32_t k = (p >> 2) & 3u;
-    return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
+  // called by all lanes at the same trips: trip & 7 == 0 issues the fetch of the next group when fewer than 3 groups lie
+  // ahead of the reader (the ring holds 4), trip & 7 == 4 moves it into the ring
+  __device__ __forceinline__ void prefetch(uint32_t trip) {
+    if ((trip & 7u) == 0) {
+      pending = loaded - (pos >> 4) < 4u;
+      if (pending) pre = group(loaded);
+    } else if ((trip & 7u) == 4u && pending) {
+      if (loaded - (pos >> 4) < 4u) put(pre);        // (an emergency fetch may have filled the ring meanwhile)
+      pending = false;
+    }
   }
-  __device__ __forceinline__ void advance(uint32_t nbytes) {
-    const uint32_t before = pos >> 4;
-    pos += nbytes;
-    if ((pos >> 4) != before) { q = qn; qn = group((pos >> 4) + 1); }
+  __device__ __forceinline__ uint32_t word_at(uint32_t p) {                // the aligned word that holds byte offset p
+    while ((p >> 4) >= loaded) { pending = false; put(group(loaded)); }   // the reader overtook the prefetcher (dense data): fetch now
+    return ring[((((p >> 4) & 3u) << 2) | ((p >> 2) & 3u)) * 32u];
   }
-  __device__ __forceinline__ uint32_t byte_at_pos() const { return (word_at(pos) >> (8u * (pos & 3u))) & 0xFFu; }
-  __device__ __forceinline__ void refill() {
+  __device__ __forceinline__ uint32_t byte_at_pos() { return (word_at(pos) >> (8u * (pos & 3u))) & 0xFFu; }
+  // append n (8 or 32) bits, right-aligned in v, behind the nacc valid bits (nacc <= 32 on entry)
+  __device__ __forceinline__ void append(uint32_t v, int n) {
+    const unsigned long long x = (unsigned long long)v << (64 - n - nacc);
+    hi |= (uint32_t)(x >> 32);
+    lo |= (uint32_t)x;
+    nacc += n;
+  }
+  __device__ __forceinline__ void refill() {                              // afterwards more than 32 bits are valid
     while (nacc <= 32) {
       if ((pos & 3u) == 0 && pos + 4 <= end) {
         const uint32_t w = word_at(pos);
         const uint32_t x = ~w, t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
         if ((~(t | x) & 0x80808080u) == 0) {                                 // no 0xFF among the four bytes
-          acc = (acc << 32) | __byte_perm(w, 0, 0x0123);
-          nacc += 32;
-          advance(4);
+          append(__byte_perm(w, 0, 0x0123), 32);
+          pos += 4;
           continue;
         }
       }
       uint32_t b = 0xFF;
       if (pos < end) {
         b = byte_at_pos();
-        advance(1);
-        if (b == 0xFF && pos < end && byte_at_pos() == 0x00) advance(1);      // stuffed zero, encoder.c:405-408
+        pos++;
+        if (b == 0xFF && pos < end && byte_at_pos() == 0x00) pos++;          // stuffed zero, encoder.c:405-408
       }
-      acc = (acc << 8) | b;
-      nacc += 8;
+      append(b, 8);
     }
   }
-  __device__ __forceinline__ uint32_t peek(int n) const { return (uint32_t)(acc >> (nacc - n)) & ((1u << n) - 1u); }
-  __device__ __forceinline__ void skip(int n) { nacc -= n; }
+  __device__ __forceinline__ uint32_t peek(int n) const { return (hi >> 1) >> (31 - n); }      // n = 0 .. 32
+  __device__ __forceinline__ void skip(int n) {                                                // n = 0 .. 31
+    hi = __funnelshift_l(lo, hi, n);
+    lo <<= n;
+    nacc -= n;
+  }
 };
 
-__device__ __forceinline__ int dec_symbol(DecBits& r, const JbDecTab& t, const uint16_t* s_look /* this lane's column: entry i at s_look[32 i] */) {
-  const uint32_t lk = s_look[32u * r.peek(8)];
+// Per-warp decoding tables in shared memory, entry i of lane L at [...][i][L] (at most two lanes per bank).  Everything a
+// symbol may need is here: a warp of 32 scans sees a code longer than 8 bits on most trips, and its two dependent loads
+// from global memory (limits, then the symbol) were 1400 clocks per trip - the L1 lines of the tables do not survive the
+// 32 scattered coefficient stores of every trip.
+struct DecSmem {
+  uint16_t look[2][256][32];     // [0 DC, 1 AC][next 8 bits] -> (length << 8) | symbol, 0 = longer than 8 bits
+  uint32_t limit[2][8][32];      // lengths 9..16: see JbDecTab::limit16
+  int32_t off[2][8][32];         // lengths 9..16: JbDecTab::valoff
+  uint8_t val_ac[256][32];       // symbols of the AC table in code order
+  uint8_t val_dc[16][32];        // ... of the DC table (12 categories)
+  uint32_t ring[16][32];         // stream bytes on their way to the bit buffers: 4 groups of 16 bytes per lane
+};
+
+__device__ __forceinline__ int dec_symbol(DecBits& r, const DecSmem& sm, int ac, int lane) {
+  const uint32_t lk = sm.look[ac][r.hi >> 24][lane];
   if (lk) { r.skip((int)(lk >> 8)); return (int)(lk & 0xFFu); }
-  // longer than 8 bits (a few per cent of the symbols, but most trips of a warp of 32 scans see one): the length is 9 + the
-  // number of lengths 9..16 whose limit the 16-bit window reaches - no loop, the lanes that take this path take it together
-  const uint32_t c16 = r.peek(16);
-  int l = 9;
+  // longer than 8 bits: the length is 9 + the number of lengths 9..16 whose limit the 16-bit window reaches (no loop: the
+  // lanes that take this path take it together)
+  const uint32_t c16 = r.hi >> 16;
+  int l = 0;
 #pragma unroll
-  for (int j = 9; j <= 16; j++) l += c16 >= t.limit16[j] ? 1 : 0;
-  if (l > 16) return -1;
-  const int code = (int)(c16 >> (16 - l));
-  r.skip(l);
-  return t.val[(t.valoff[l] + code) & 255];
+  for (int j = 0; j < 8; j++) l += c16 >= sm.limit[ac][j][lane] ? 1 : 0;
+  if (l > 7) return -1;
+  const int code = (int)(c16 >> (7 - l));
+  r.skip(9 + l);
+  const int idx = sm.off[ac][l][lane] + code;
+  return ac ? sm.val_ac[idx & 255][lane] : sm.val_dc[idx & 15][lane];
 }
-__device__ __forceinline__ int dec_extend(int v, int n) { return n && v < (1 << (n - 1)) ? v - (1 << n) + 1 : v; }   // inverse of encoder.c:441-443
+// magnitude bits -> value (inverse of encoder.c:441-443); n = 0 gives 0
+__device__ __forceinline__ int dec_extend(uint32_t raw, int n) {
+  const uint32_t full = 1u << n;
+  return raw < (full >> 1) ? (int)raw - (int)full + 1 : (int)raw;
+}
 
 // planes of frame f: Y (w*h), Cb, Cr (w*h/4 each) int16, zeroed by the caller; dcabs: one int16 per block in the same order
-// The look-ahead tables live in shared memory, entry i of lane L at [i][L] (two lanes per bank at most): every symbol
-// scatters 32 two-byte stores over 32 frames, and read through L1 the tables were evicted as fast as they were loaded (r2:
-// 1400 clocks per symbol, whatever the instruction count).
 __global__ void __launch_bounds__(32) k_dec_scan(const uint8_t* __restrict__ streams, size_t slot, int nframes, int w, int h, JbDecFrame* frames,
                                                 int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
-  __shared__ uint16_t s_look[2][256][32];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ DecSmem sm;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x;
   if (t >= 3 * nframes) return;
   const int comp = t / nframes, f = t - comp * nframes;      // a warp decodes one component of 32 frames: similar lengths
   JbDecFrame& fr = frames[f];
@@ -241,17 +286,23 @@ __global__ void __launch_bounds__(32) k_dec_scan(const uint8_t* __restrict__ str
   int16_t* dca = dcabs + (size_t)f * (npix / 64 * 3 / 2) + (comp == 0 ? 0 : comp == 1 ? npix / 64 : npix / 64 + npix / 256);
   const JbDecTab& dc = fr.tab[0][fr.td[comp]];
   const JbDecTab& ac = fr.tab[1][fr.ta[comp]];
-  for (int i = 0; i < 256; i++) { s_look[0][i][threadIdx.x] = dc.look[i]; s_look[1][i][threadIdx.x] = ac.look[i]; }
+  for (int i = 0; i < 256; i++) { sm.look[0][i][lane] = dc.look[i]; sm.look[1][i][lane] = ac.look[i]; sm.val_ac[i][lane] = ac.val[i]; }
+  for (int i = 0; i < 16; i++) sm.val_dc[i][lane] = dc.val[i];
+  for (int j = 0; j < 8; j++) {
+    sm.limit[0][j][lane] = dc.limit16[9 + j]; sm.limit[1][j][lane] = ac.limit16[9 + j];
+    sm.off[0][j][lane] = dc.valoff[9 + j]; sm.off[1][j][lane] = ac.valoff[9 + j];
+  }
   DecBits r;
-  r.init(streams + (size_t)f * slot, slot, fr.scan_start[comp], fr.scan_end[comp]);
+  r.init(streams + (size_t)f * slot, slot, fr.scan_start[comp], fr.scan_end[comp], &sm.ring[0][lane]);
   // One symbol per trip, whatever block it belongs to: the 32 scans of a warp then advance at their own pace.  A loop over
   // blocks with an inner loop over the block's symbols re-converges after every block and runs at the pace of the busiest of
   // 32 blocks (measured: 4 x the time).
   int pred = 0, rc = 0, b = 0, k = 0;
   int16_t* blk = plane;
-  while (b < nblocks) {
+  for (uint32_t trip = 0; b < nblocks; trip++) {
+    r.prefetch(trip);
     r.refill();
-    const int sym = dec_symbol(r, k == 0 ? dc : ac, &s_look[k == 0 ? 0 : 1][0][threadIdx.x]);
+    const int sym = dec_symbol(r, sm, k == 0 ? 0 : 1, lane);
     if (sym < 0) { rc = JB_DEC_BAD_CODE; break; }
     // DC (k = 0: the symbol is the category, encoder.c:434-448) and AC (run << 4 | size, encoder.c:450-502) share one
     // predicated path: divergent branches here are paid by all 32 scans of the warp
@@ -259,7 +310,7 @@ __global__ void __launch_bounds__(32) k_dec_scan(const uint8_t* __restrict__ str
     const int run = is_dc ? 0 : sym >> 4, sz = is_dc ? sym : sym & 15;
     const bool special = !is_dc && sz == 0;         // ZRL (run 15) or EOB (run 0)
     if ((is_dc && sym > 15) || (special && run != 0 && run != 15)) { rc = JB_DEC_BAD_CODE; break; }
-    const int v = dec_extend((int)(sz ? r.peek(sz) : 0u), sz);
+    const int v = dec_extend(r.peek(sz), sz);
     r.skip(sz);
     const int kc = k + run;                         // position of the coefficient
     if (!special) {

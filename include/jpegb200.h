@@ -51,6 +51,7 @@ int jpegb200_get_timing(jpegb200_ctx *ctx, double *ms_total, uint64_t *launches)
 /* Per-stage sums; index: 0 pixels -> tokens (plane path: pixels -> coefficient planes), 1 plane masks, 2 symbol stats,
  * 3 huffman build, 4 table pack, 5 block bits, 6 scan, 7 pack, 8 count 0xFF, 9 layout, 10 stuff, 11 undecided blocks
  * (k_fix_tokens / k_fix_blocks), 12 run preparation (first DC of every run, token prefix), 13 token compaction.
+ * On the token path stage 3 includes the packed tables, 13 the chunk scan and 8 the layout (folded into those launches).
  * ms and n have 16 entries. */
 int jpegb200_get_stage_timing(jpegb200_ctx *ctx, double *ms, uint64_t *n);
 

@@ -8,11 +8,11 @@
 //   k_dec_parse    one CTA per stream: thread 0 reads the marker segments up to the first scan (quantisers, the four
 //                  Huffman tables with an 8-bit look-ahead table each, SOF0 / SOS checks), all threads then look for the
 //                  markers that end the scans
-//   k_dec_scan     one THREAD per scan: entropy decoding is a serial chain per scan (no restart intervals: every code's
-//                  position depends on all codes before it); the batch supplies the parallelism — threads of a warp decode
-//                  the same component of 32 different frames.  Writes the non-zero coefficients into zeroed planes (zig-zag
-//                  order, DC still a difference: exactly the planes rgb_to_dct leaves, encoder.c:158-178) and the absolute
-//                  DC of every block
+//   k_dec_scan     one WARP per scan: entropy decoding is a serial chain per scan (no restart intervals: every code's position
+//                  depends on all codes before it), so the lanes decode the 32 tokens that would start at the next 32 bit
+//                  positions and a warp-uniform walk follows the real chain through them.  Writes the planes block by block
+//                  (zig-zag order, DC still a difference: exactly the planes rgb_to_dct leaves, encoder.c:158-178) and the
+//                  absolute DC of every block
 //   k_dec_idct     8 threads per block: de-quantise, separable inverse transform in FP64 in a fixed order, samples
 //   k_dec_colour   one thread per 4 x 2 pixels: chroma replicated 2 x 2, toRgb in FP64, B,G,R bytes
 #include "jpegb200_internal.cuh"
@@ -148,180 +148,164 @@ __global__ void __launch_bounds__(256) k_dec_parse(const uint8_t* __restrict__ s
   }
 }
 
-// Bit reader of one scan: 0xFF 0x00 -> 0xFF; past the scan's last byte it supplies 1-bits — fill_last_byte
-// (encoder.c:425-432) pads with ones and never stuffs, so a final 0xFF byte reads as the next marker's first byte.
-// The stream is fetched in aligned 16-byte groups into a 64-byte ring per lane in shared memory; a word without an 0xFF
-// byte (all but one in 64) enters the bit buffer whole.  The fetches are issued by the whole warp at the same trips of
-// the symbol loop (prefetch) and land in the ring four trips later: a lane that fetched into registers whenever IT crossed
-// a group boundary made the whole warp wait for that load at the next lane's crossing (the scoreboard is per warp, and
-// some lane crosses on almost every trip): 700 clocks per trip.
-// The bit buffer is LEFT-ALIGNED in hi:lo (the next bit is bit 31 of hi): peeking is one shift, consuming a funnel shift.
-struct DecBits {
-  const uint4* base;         // 16-byte aligned address at or before the scan's first byte
-  uint32_t pos, end;         // byte offsets from base: next byte to consume, end of the scan
-  uint32_t last;             // last 16-byte group (index from base) that lies inside the stream's slot: nothing beyond it is read
-  uint32_t loaded;           // groups [0, loaded) have been fetched; group g sits in ring slot g & 3
-  uint32_t* ring;            // this lane's column: word w of slot s at ring[(4 s + w) * 32]
-  uint4 pre;                 // prefetched group on its way to the ring
-  bool pending;
-  uint32_t hi, lo;
-  int nacc;                  // valid bits in hi:lo
-  __device__ __forceinline__ uint4 group(uint32_t k) const { return k <= last ? __ldg(base + k) : make_uint4(0, 0, 0, 0); }
-  __device__ __forceinline__ void put(uint4 v) {
-    uint32_t* d = ring + ((loaded & 3u) << 2) * 32u;
-    d[0] = v.x; d[32] = v.y; d[64] = v.z; d[96] = v.w;
-    loaded++;
-  }
-  __device__ __forceinline__ void init(const uint8_t* stream, size_t slot, uint32_t start, uint32_t stop, uint32_t* ring_column) {
-    const uintptr_t a = (uintptr_t)(stream + start);
-    base = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    pos = (uint32_t)(a & 15);
-    end = pos + (stop - start);
-    last = (uint32_t)(((uintptr_t)(stream + slot) - (uintptr_t)base - 1) >> 4);     // slots are 16-byte aligned (checked by the C ABI)
-    ring = ring_column;
-    loaded = 0;
-    const uint4 g0 = group(0), g1 = group(1), g2 = group(2);
-    put(g0); put(g1); put(g2);
-    pending = false;
-    hi = lo = 0;
-    nacc = 0;
-  }
-  // called by all lanes at the same trips: trip & 7 == 0 issues the fetch of the next group when fewer than 3 groups lie
-  // ahead of the reader (the ring holds 4), trip & 7 == 4 moves it into the ring
-  __device__ __forceinline__ void prefetch(uint32_t trip) {
-    if ((trip & 7u) == 0) {
-      pending = loaded - (pos >> 4) < 4u;
-      if (pending) pre = group(loaded);
-    } else if ((trip & 7u) == 4u && pending) {
-      if (loaded - (pos >> 4) < 4u) put(pre);        // (an emergency fetch may have filled the ring meanwhile)
-      pending = false;
-    }
-  }
-  __device__ __forceinline__ uint32_t word_at(uint32_t p) {                // the aligned word that holds byte offset p
-    while ((p >> 4) >= loaded) { pending = false; put(group(loaded)); }   // the reader overtook the prefetcher (dense data): fetch now
-    return ring[((((p >> 4) & 3u) << 2) | ((p >> 2) & 3u)) * 32u];
-  }
-  __device__ __forceinline__ uint32_t byte_at_pos() { return (word_at(pos) >> (8u * (pos & 3u))) & 0xFFu; }
-  // append n (8 or 32) bits, right-aligned in v, behind the nacc valid bits (nacc <= 32 on entry)
-  __device__ __forceinline__ void append(uint32_t v, int n) {
-    const unsigned long long x = (unsigned long long)v << (64 - n - nacc);
-    hi |= (uint32_t)(x >> 32);
-    lo |= (uint32_t)x;
-    nacc += n;
-  }
-  __device__ __forceinline__ void refill() {                              // afterwards more than 32 bits are valid
-    while (nacc <= 32) {
-      if ((pos & 3u) == 0 && pos + 4 <= end) {
-        const uint32_t w = word_at(pos);
-        const uint32_t x = ~w, t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-        if ((~(t | x) & 0x80808080u) == 0) {                                 // no 0xFF among the four bytes
-          append(__byte_perm(w, 0, 0x0123), 32);
-          pos += 4;
-          continue;
-        }
-      }
-      uint32_t b = 0xFF;
-      if (pos < end) {
-        b = byte_at_pos();
-        pos++;
-        if (b == 0xFF && pos < end && byte_at_pos() == 0x00) pos++;          // stuffed zero, encoder.c:405-408
-      }
-      append(b, 8);
-    }
-  }
-  __device__ __forceinline__ uint32_t peek(int n) const { return (hi >> 1) >> (31 - n); }      // n = 0 .. 32
-  __device__ __forceinline__ void skip(int n) {                                                // n = 0 .. 31
-    hi = __funnelshift_l(lo, hi, n);
-    lo <<= n;
-    nacc -= n;
-  }
+// ---- entropy decoding: one WARP per scan -------------------------------------------------------------------------------------
+// A scan has no restart intervals: where a code starts depends on every code before it.  What the 32 lanes of a warp can do
+// in parallel is decode, for each of the next 32 bit positions, the token that WOULD start there (with the AC table and with
+// the DC table); a short warp-uniform walk then follows the real chain through those 32 results with one shuffle per token.
+// r2 history: one THREAD per scan (32 scans per warp) needed 158 warp-instructions per symbol at 5.9 clocks each and 140 ms
+// for any batch up to 1024 frames, whatever was done to its inner loop (profiles/r2b_summary.md section 4).
+//   clean stream  the scan's bytes without the stuffed zeros (0xFF 0x00 -> 0xFF, encoder.c:405-408), 128 raw bytes per refill:
+//                 every lane takes one word, a byte is dropped iff it is 0x00 behind a 0xFF, a warp scan places the rest in a
+//                 256-byte ring of big-endian words.  Past the scan's last byte the stream continues with 1-bits: fill_last_byte
+//                 (encoder.c:425-432) pads with ones and never stuffs, so a final 0xFF reads as the next marker's first byte.
+//   window        lane i looks at the 32 bits that start i bits behind the read position
+//   result        total bits | run << 6 | (size == 0) << 10 | invalid << 11 | value << 16, for the AC and for the DC reading
+//   walk          position 0 is a token start; the token there tells where the next one starts (all state warp-uniform)
+// The block under construction lives in shared memory and leaves as one 128-byte store (no zeroed planes needed).
+struct DecWarp {
+  uint16_t look[2][256];     // [0 DC, 1 AC][next 8 bits] -> (code length << 8) | symbol, 0 = longer than 8 bits
+  uint32_t limit[2][8];      // lengths 9..16: JbDecTab::limit16
+  int32_t off[2][8];         // lengths 9..16: JbDecTab::valoff
+  uint8_t val[2][256];       // symbols in code order
+  uint32_t ring[64];         // clean stream: bit b = bit 31 - (b & 31) of ring[(b >> 5) & 63]
+  uint32_t blk[32];          // the block under construction, 64 int16
 };
+constexpr int DS_WARPS = 4;
 
-// Per-warp decoding tables in shared memory, entry i of lane L at [...][i][L] (at most two lanes per bank).  Everything a
-// symbol may need is here: a warp of 32 scans sees a code longer than 8 bits on most trips, and its two dependent loads
-// from global memory (limits, then the symbol) were 1400 clocks per trip - the L1 lines of the tables do not survive the
-// 32 scattered coefficient stores of every trip.
-struct DecSmem {
-  uint16_t look[2][256][32];     // [0 DC, 1 AC][next 8 bits] -> (length << 8) | symbol, 0 = longer than 8 bits
-  uint32_t limit[2][8][32];      // lengths 9..16: see JbDecTab::limit16
-  int32_t off[2][8][32];         // lengths 9..16: JbDecTab::valoff
-  uint8_t val_ac[256][32];       // symbols of the AC table in code order
-  uint8_t val_dc[16][32];        // ... of the DC table (12 categories)
-  uint32_t ring[16][32];         // stream bytes on their way to the bit buffers: 4 groups of 16 bytes per lane
-};
-
-__device__ __forceinline__ int dec_symbol(DecBits& r, const DecSmem& sm, int ac, int lane) {
-  const uint32_t lk = sm.look[ac][r.hi >> 24][lane];
-  if (lk) { r.skip((int)(lk >> 8)); return (int)(lk & 0xFFu); }
-  // longer than 8 bits: the length is 9 + the number of lengths 9..16 whose limit the 16-bit window reaches (no loop: the
-  // lanes that take this path take it together)
-  const uint32_t c16 = r.hi >> 16;
-  int l = 0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) l += c16 >= sm.limit[ac][j][lane] ? 1 : 0;
-  if (l > 7) return -1;
-  const int code = (int)(c16 >> (7 - l));
-  r.skip(9 + l);
-  const int idx = sm.off[ac][l][lane] + code;
-  return ac ? sm.val_ac[idx & 255][lane] : sm.val_dc[idx & 15][lane];
-}
-// magnitude bits -> value (inverse of encoder.c:441-443); n = 0 gives 0
+// inverse of encoder.c:441-443: n magnitude bits -> value; n = 0 gives 0
 __device__ __forceinline__ int dec_extend(uint32_t raw, int n) {
   const uint32_t full = 1u << n;
   return raw < (full >> 1) ? (int)raw - (int)full + 1 : (int)raw;
 }
 
-// planes of frame f: Y (w*h), Cb, Cr (w*h/4 each) int16, zeroed by the caller; dcabs: one int16 per block in the same order
-__global__ void __launch_bounds__(32) k_dec_scan(const uint8_t* __restrict__ streams, size_t slot, int nframes, int w, int h, JbDecFrame* frames,
-                                                int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
-  __shared__ DecSmem sm;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x;
+// The token that starts at the top of `win`, read with table class c (0 DC: the symbol is the size; 1 AC: run << 4 | size).
+__device__ __forceinline__ uint32_t dec_token(const DecWarp& sm, int c, uint32_t win) {
+  const uint32_t lk = sm.look[c][win >> 24];
+  int len = (int)(lk >> 8), sym = (int)(lk & 0xFFu);
+  uint32_t bad = 0;
+  if (!lk) {                                    // longer than 8 bits: 9 + the number of lengths whose limit the window reaches
+    const uint32_t c16 = win >> 16;
+    int l = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) l += c16 >= sm.limit[c][j] ? 1 : 0;
+    bad = l > 7;
+    l = min(l, 7);
+    len = 9 + l;
+    sym = sm.val[c][(sm.off[c][l] + (int)(c16 >> (7 - l))) & 255];
+  }
+  const int sz = c ? sym & 15 : sym & 31, run = c ? sym >> 4 : 0;
+  bad |= (!c && sym > 15) || (c && sz == 0 && run != 0 && run != 15) || len + sz > 31;
+  const uint32_t raw = sz ? (win << len) >> (32 - sz) : 0u;
+  const int v = dec_extend(raw, sz & 15);
+  return (uint32_t)((len + sz) & 63) | ((uint32_t)run << 6) | ((sz == 0 ? 1u : 0u) << 10) | (bad << 11) | ((uint32_t)v << 16);
+}
+
+// planes of frame f: Y (w*h), Cb, Cr (w*h/4 each) int16; dcabs: one int16 per block in the same order
+__global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __restrict__ streams, size_t slot, int nframes, int w, int h, JbDecFrame* frames,
+                                                          int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  __shared__ DecWarp sm_all[DS_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * DS_WARPS + warp;                  // the Y scans (ten times the chroma scans' length) come first
   if (t >= 3 * nframes) return;
-  const int comp = t / nframes, f = t - comp * nframes;      // a warp decodes one component of 32 frames: similar lengths
+  const int comp = t / nframes, f = t - comp * nframes;
   JbDecFrame& fr = frames[f];
   if (fr.status) return;
+  DecWarp& sm = sm_all[warp];
   const size_t npix = (size_t)w * h;
   const int nblocks = (w / 8) * (h / 8) / (comp ? 4 : 1);
-  int16_t* plane = planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4);
+  uint32_t* plane32 = reinterpret_cast<uint32_t*>(planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4));
   int16_t* dca = dcabs + (size_t)f * (npix / 64 * 3 / 2) + (comp == 0 ? 0 : comp == 1 ? npix / 64 : npix / 64 + npix / 256);
-  const JbDecTab& dc = fr.tab[0][fr.td[comp]];
-  const JbDecTab& ac = fr.tab[1][fr.ta[comp]];
-  for (int i = 0; i < 256; i++) { sm.look[0][i][lane] = dc.look[i]; sm.look[1][i][lane] = ac.look[i]; sm.val_ac[i][lane] = ac.val[i]; }
-  for (int i = 0; i < 16; i++) sm.val_dc[i][lane] = dc.val[i];
-  for (int j = 0; j < 8; j++) {
-    sm.limit[0][j][lane] = dc.limit16[9 + j]; sm.limit[1][j][lane] = ac.limit16[9 + j];
-    sm.off[0][j][lane] = dc.valoff[9 + j]; sm.off[1][j][lane] = ac.valoff[9 + j];
+  {
+    const JbDecTab& dc = fr.tab[0][fr.td[comp]];
+    const JbDecTab& ac = fr.tab[1][fr.ta[comp]];
+    for (int i = lane; i < 256; i += 32) { sm.look[0][i] = dc.look[i]; sm.look[1][i] = ac.look[i]; sm.val[0][i] = dc.val[i]; sm.val[1][i] = ac.val[i]; }
+    if (lane < 8) { sm.limit[0][lane] = dc.limit16[9 + lane]; sm.limit[1][lane] = ac.limit16[9 + lane]; sm.off[0][lane] = dc.valoff[9 + lane]; sm.off[1][lane] = ac.valoff[9 + lane]; }
+    sm.blk[lane] = 0;
   }
-  DecBits r;
-  r.init(streams + (size_t)f * slot, slot, fr.scan_start[comp], fr.scan_end[comp], &sm.ring[0][lane]);
-  // One symbol per trip, whatever block it belongs to: the 32 scans of a warp then advance at their own pace.  A loop over
-  // blocks with an inner loop over the block's symbols re-converges after every block and runs at the pace of the busiest of
-  // 32 blocks (measured: 4 x the time).
-  int pred = 0, rc = 0, b = 0, k = 0;
-  int16_t* blk = plane;
-  for (uint32_t trip = 0; b < nblocks; trip++) {
-    r.prefetch(trip);
-    r.refill();
-    const int sym = dec_symbol(r, sm, k == 0 ? 0 : 1, lane);
-    if (sym < 0) { rc = JB_DEC_BAD_CODE; break; }
-    // DC (k = 0: the symbol is the category, encoder.c:434-448) and AC (run << 4 | size, encoder.c:450-502) share one
-    // predicated path: divergent branches here are paid by all 32 scans of the warp
-    const bool is_dc = k == 0;
-    const int run = is_dc ? 0 : sym >> 4, sz = is_dc ? sym : sym & 15;
-    const bool special = !is_dc && sz == 0;         // ZRL (run 15) or EOB (run 0)
-    if ((is_dc && sym > 15) || (special && run != 0 && run != 15)) { rc = JB_DEC_BAD_CODE; break; }
-    const int v = dec_extend(r.peek(sz), sz);
-    r.skip(sz);
-    const int kc = k + run;                         // position of the coefficient
-    if (!special) {
-      if (kc > 63) { rc = JB_DEC_BAD_CODE; break; }
-      blk[kc] = (int16_t)v;
+  // raw side: aligned words from the 16-byte aligned address at or before the scan's first byte
+  const uint8_t* stream = streams + (size_t)f * slot;
+  const uintptr_t a0 = (uintptr_t)(stream + fr.scan_start[comp]);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)15);
+  const uint32_t start = (uint32_t)(a0 & 15), stop = start + (fr.scan_end[comp] - fr.scan_start[comp]);    // byte offsets from base
+  const uint32_t limit = (uint32_t)((uintptr_t)(stream + slot) - (uintptr_t)base);                          // nothing beyond the slot is read
+  uint32_t rword = 0, prev_byte = 0;            // next raw word, last raw byte of the previous refill
+  uint32_t produced = 0;                        // clean bytes written so far
+  uint32_t bp = 0;                              // clean bits consumed so far
+  uint8_t* ring8 = reinterpret_cast<uint8_t*>(sm.ring);
+  __syncwarp();
+
+  int rc = 0, b = 0, k = 0, pred = 0;
+  while (b < nblocks) {
+    // ---- refill: the window below reads up to 96 bits behind bp ------------------------------------------------------
+    while (produced * 8u < bp + 104u) {
+      const uint32_t p0 = (rword + lane) * 4u;                                   // raw byte offset of this lane's word
+      uint32_t wv = p0 + 4u <= limit ? __ldg(base + rword + lane) : 0xFFFFFFFFu;
+      uint32_t by[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) by[j] = p0 + j < stop ? (wv >> (8 * j)) & 0xFFu : 0xFFu;       // past the end: 1-bits
+      uint32_t before = __shfl_up_sync(FULL, by[3], 1);
+      if (lane == 0) before = prev_byte;
+      uint32_t keep = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t pr = j ? by[j - 1] : before;
+        const bool stuffed = by[j] == 0x00u && pr == 0xFFu && p0 + j < stop;     // only real bytes of the scan are ever stuffing
+        keep |= (p0 + j >= start && !stuffed ? 1u : 0u) << j;
+      }
+      const uint32_t cnt = (uint32_t)__popc(keep);
+      uint32_t inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += n;
+      }
+      uint32_t dst = produced + inc - cnt;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if ((keep >> j) & 1u) { ring8[(dst & 255u) ^ 3u] = (uint8_t)by[j]; dst++; }
+      produced += __shfl_sync(FULL, inc, 31);
+      prev_byte = __shfl_sync(FULL, by[3], 31);
+      rword += 32;
+      __syncwarp();
     }
-    if (is_dc) { pred += v; dca[b] = (int16_t)pred; }
-    k = special ? (run == 15 ? k + 16 : 64) : kc + 1;
-    if (k >= 64) { b++; k = 0; blk += 64; }
+    // ---- the 32 candidate tokens ------------------------------------------------------------------------------------
+    const uint32_t wi = bp >> 5, o = (bp & 31u) + (uint32_t)lane;
+    const uint32_t w0 = sm.ring[wi & 63u], w1 = sm.ring[(wi + 1u) & 63u], w2 = sm.ring[(wi + 2u) & 63u];
+    const uint32_t win = o < 32u ? __funnelshift_l(w1, w0, o) : __funnelshift_l(w2, w1, o - 32u);
+    const uint32_t r_dc = dec_token(sm, 0, win), r_ac = dec_token(sm, 1, win);
+    // ---- walk (all state is warp-uniform) -----------------------------------------------------------------------------
+    uint32_t pos = 0;
+    while (pos < 32u && b < nblocks) {
+      const uint32_t R = __shfl_sync(FULL, k == 0 ? r_dc : r_ac, (int)pos);
+      if (R & 0x800u) { rc = JB_DEC_BAD_CODE; break; }
+      const int v = (int)R >> 16, run = (int)(R >> 6) & 15;
+      if (k == 0) {                                   // DC difference (encoder.c:434-448)
+        pred += v;
+        if (lane == 0) { reinterpret_cast<int16_t*>(sm.blk)[0] = (int16_t)v; dca[b] = (int16_t)pred; }
+        k = 1;
+      } else if (R & 0x400u) {                        // ZRL / EOB (encoder.c:470-476, :496-500)
+        k = run == 15 ? k + 16 : 64;
+      } else {
+        const int kc = k + run;
+        if (kc > 63) { rc = JB_DEC_BAD_CODE; break; }
+        if (lane == 0) reinterpret_cast<int16_t*>(sm.blk)[kc] = (int16_t)v;
+        k = kc + 1;
+      }
+      pos += R & 63u;
+      if (k >= 64) {                                  // the block is complete: one 128-byte store, and a clean slate
+        __syncwarp();
+        plane32[(size_t)b * 32 + lane] = sm.blk[lane];
+        sm.blk[lane] = 0;
+        __syncwarp();
+        b++;
+        k = 0;
+      }
+    }
+    if (rc) break;
+    bp += pos;
   }
-  if (rc) atomicCAS(&fr.status, 0, rc);
+  if (rc && lane == 0) atomicCAS(&fr.status, 0, rc);
 }
 
 // 8 threads per block, 16 blocks per CTA.  Block ids run over Y, Cb, Cr of one frame (blockIdx.y = frame).
@@ -428,15 +412,14 @@ __global__ void k_dec_status(const JbDecFrame* frames, int n, int32_t* status) {
 
 size_t jb_dec_frame_bytes() { return sizeof(JbDecFrame); }
 
-// d_frames: n x jb_dec_frame_bytes(); d_planes: n x (w*h*3/2) int16 (zeroed here); d_dcabs: n x (w*h/64*3/2) int16;
+// d_frames: n x jb_dec_frame_bytes(); d_planes: n x (w*h*3/2) int16; d_dcabs: n x (w*h/64*3/2) int16;
 // d_samples: n x (w*h*3/2) bytes; d_bgr may be null (planes only); d_status may be null.
 void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_sizes, int n, int w, int h, void* d_frames, int16_t* d_planes, int16_t* d_dcabs,
                       uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, cudaStream_t st) {
   JbDecFrame* fr = reinterpret_cast<JbDecFrame*>(d_frames);
   const size_t npix = (size_t)w * h;
-  cudaMemsetAsync(d_planes, 0, (size_t)n * (npix + npix / 2) * sizeof(int16_t), st);
   k_dec_parse<<<n, 256, 0, st>>>(d_streams, slot, d_sizes, w, h, fr);
-  k_dec_scan<<<(3 * n + 31) / 32, 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs);
+  k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs);
   if (d_bgr) {
     const uint32_t nb = (uint32_t)(npix / 64 * 3 / 2);
     k_dec_idct<<<dim3((nb + 15) / 16, n), 128, 0, st>>>(w, h, fr, d_planes, d_dcabs, d_samples);

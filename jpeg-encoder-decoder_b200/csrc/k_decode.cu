@@ -274,26 +274,25 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
     const uint32_t w0 = sm.ring[wi & 63u], w1 = sm.ring[(wi + 1u) & 63u], w2 = sm.ring[(wi + 2u) & 63u];
     const uint32_t win = o < 32u ? __funnelshift_l(w1, w0, o) : __funnelshift_l(w2, w1, o - 32u);
     const uint32_t r_dc = dec_token(sm, 0, win), r_ac = dec_token(sm, 1, win);
-    // ---- walk (all state is warp-uniform) -----------------------------------------------------------------------------
-    uint32_t pos = 0;
+    // ---- walk (all state is warp-uniform; no branch depends on the token except the end of a block) ----------------------
+    uint32_t pos = 0, bad = 0;
     while (pos < 32u && b < nblocks) {
-      const uint32_t R = __shfl_sync(FULL, k == 0 ? r_dc : r_ac, (int)pos);
-      if (R & 0x800u) { rc = JB_DEC_BAD_CODE; break; }
+      const uint32_t Rd = __shfl_sync(FULL, r_dc, (int)pos), Ra = __shfl_sync(FULL, r_ac, (int)pos);
+      const bool is_dc = k == 0;
+      const uint32_t R = is_dc ? Rd : Ra;
       const int v = (int)R >> 16, run = (int)(R >> 6) & 15;
-      if (k == 0) {                                   // DC difference (encoder.c:434-448)
+      const bool zero_size = (R & 0x400u) != 0;              // AC: ZRL / EOB (encoder.c:470-476, :496-500); DC: a zero difference
+      const int kc = is_dc ? 0 : k + run;                    // where the value goes
+      const bool store = is_dc || !zero_size;
+      bad |= (R & 0x800u) | (store && kc > 63 ? 0x800u : 0u);
+      if (lane == 0 && store) reinterpret_cast<int16_t*>(sm.blk)[kc & 63] = (int16_t)v;
+      if (is_dc) {                                           // encoder.c:434-448
         pred += v;
-        if (lane == 0) { reinterpret_cast<int16_t*>(sm.blk)[0] = (int16_t)v; dca[b] = (int16_t)pred; }
-        k = 1;
-      } else if (R & 0x400u) {                        // ZRL / EOB (encoder.c:470-476, :496-500)
-        k = run == 15 ? k + 16 : 64;
-      } else {
-        const int kc = k + run;
-        if (kc > 63) { rc = JB_DEC_BAD_CODE; break; }
-        if (lane == 0) reinterpret_cast<int16_t*>(sm.blk)[kc] = (int16_t)v;
-        k = kc + 1;
+        if (lane == 0) dca[b] = (int16_t)pred;
       }
+      k = store ? kc + 1 : (run == 15 ? k + 16 : 64);
       pos += R & 63u;
-      if (k >= 64) {                                  // the block is complete: one 128-byte store, and a clean slate
+      if (k >= 64) {                                         // the block is complete: one 128-byte store, and a clean slate
         __syncwarp();
         plane32[(size_t)b * 32 + lane] = sm.blk[lane];
         sm.blk[lane] = 0;
@@ -301,8 +300,10 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
         b++;
         k = 0;
       }
+      if ((R & 63u) == 0) bad |= 0x800u;                     // (cannot happen for a valid token: guards the loop against hostile tables)
+      if (bad) break;
     }
-    if (rc) break;
+    if (bad) { rc = JB_DEC_BAD_CODE; break; }
     bp += pos;
   }
   if (rc && lane == 0) atomicCAS(&fr.status, 0, rc);

@@ -293,6 +293,49 @@ __device__ __forceinline__ void concat_store(uint32_t* stage, const uint32_t (&w
   }
 }
 
+// The same with up to two ZRL codes (runs of 16 zeros, encoder.c:470-476) in front of a token: they form one more code word of
+// at most 32 bits.  About one token in 500 carries a ZRL, but two chunks in five hold one, and the OR-into-the-image path for
+// such a lane cost the whole warp some 300 instructions; here the warp pays 8 more appends only in those chunks.
+__device__ __forceinline__ void concat_store_z4(uint32_t* stage, const uint32_t (&word)[PR_TOK], const uint32_t (&len)[PR_TOK], uint32_t sbit, uint32_t nbits,
+                                                uint32_t zr, uint32_t zrl_code, uint32_t zrl_len) {
+  constexpr int W = 4;
+  uint32_t A[W] = {0, 0, 0, 0};
+  uint32_t tot = sbit & 31;
+  const uint32_t two = (zrl_code << (zrl_len & 31u)) | zrl_code;
+#pragma unroll
+  for (int j = 0; j < PR_TOK; j++) {
+    const uint32_t z = (zr >> (2 * j)) & 3u;
+    const uint32_t pl = z * zrl_len, pw = z == 2u ? two : zrl_code;     // z = 0: length 0, the word does not matter
+    if (pl == 32u) {                                                     // two 16-bit ZRL codes: a whole word moves up
+#pragma unroll
+      for (int q = 0; q < W - 1; q++) A[q] = A[q + 1];
+      A[W - 1] = pw;
+    } else {
+#pragma unroll
+      for (int q = 0; q < W - 1; q++) A[q] = __funnelshift_l(A[q + 1], A[q], pl);
+      A[W - 1] = (A[W - 1] << pl) | (pl ? pw : 0u);
+    }
+    tot += pl;
+#pragma unroll
+    for (int q = 0; q < W - 1; q++) A[q] = __funnelshift_l(A[q + 1], A[q], len[j]);
+    A[W - 1] = (A[W - 1] << len[j]) | (len[j] ? word[j] : 0u);
+    tot += len[j];
+  }
+  const uint32_t pad = (32u - (tot & 31u)) & 31u;
+#pragma unroll
+  for (int q = 0; q < W - 1; q++) A[q] = __funnelshift_l(A[q + 1], A[q], pad);
+  A[W - 1] <<= pad;
+  const int nw = nbits ? (int)((tot + pad) >> 5) : 0;
+  uint32_t* dst = stage + (sbit >> 5) - (W - nw);
+#pragma unroll
+  for (int q = 0; q < W; q++) {
+    if (q >= W - nw) {
+      if (q == W - nw || q == W - 1) atomicOr(dst + q, A[q]);
+      else dst[q] = A[q];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
@@ -349,9 +392,14 @@ __global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
     // the lanes' bits rarely exceed four words (5 bits per token on photographic content): the short accumulator shifts
     // 3 words per token instead of 8
     const bool wide = __any_sync(FULL, (sbit & 31u) + nbits > 128u);
-    if (zr == 0) {
-      if (wide) concat_store<9>(stage, word, len, sbit, nbits);
+    const bool zrls = __any_sync(FULL, zr != 0);
+    const bool zrl3 = __any_sync(FULL, ((zr & (zr >> 1)) & 0x5555u) != 0);      // a token behind 48 or more zeros: three ZRL codes
+    if (!wide && !zrl3) {
+      if (zrls) concat_store_z4(stage, word, len, sbit, nbits, zr, __shfl_sync(FULL, zrl_code, __ffs(__ballot_sync(FULL, zr != 0)) - 1),
+                                __shfl_sync(FULL, zrl_len, __ffs(__ballot_sync(FULL, zr != 0)) - 1));
       else concat_store<4>(stage, word, len, sbit, nbits);
+    } else if (zr == 0) {
+      concat_store<9>(stage, word, len, sbit, nbits);
     } else {
       uint32_t pos = sbit;
 #pragma unroll

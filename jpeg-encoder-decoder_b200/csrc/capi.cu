@@ -264,7 +264,7 @@ int run_chain(jpegb200_ctx* c, Lane& l, int njobs, int max_w, int max_h, uint32_
     CK(cudaMemsetAsync(l.tchunk_bits.p, 0, l.tchunk_bytes, st));
     { StageTimer t(c, st, ST_DCFIX); jb_launch_runs_prepare(ws, njobs, st); }
     { StageTimer t(c, st, ST_HUFF); jb_launch_build_huffman(ws, njobs, (size_t)max_w * max_h >= ((size_t)1 << 23), st); }      // + packed tables
-    { StageTimer t(c, st, ST_RUNBITS); jb_launch_compact_tokens(ws, njobs, max_runs, st); }                                      // + chunk scan (last CTA of a job)
+    { StageTimer t(c, st, ST_RUNBITS); jb_launch_compact_tokens(ws, njobs, max_runs, st); c->launches++; }                       // k_compact_tokens + k_scan_tchunks
     { StageTimer t(c, st, ST_PACK); jb_launch_pack_tchunks(ws, njobs, max_tchunks, st); }
     const uint32_t tail_ctas = njobs >= 16 ? 24 : 64;       // CTAs per job of the byte-stuffing kernels
     { StageTimer t(c, st, ST_COUNTFF); jb_launch_count_ff(ws, njobs, tail_ctas, d_sizes, st); }                                // + layout (last CTA of a job)

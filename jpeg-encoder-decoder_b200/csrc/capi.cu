@@ -593,7 +593,7 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
   if (check_dims(w, h)) return -1;
   if (w > 65535 || h > 65535) return fail("a baseline frame header holds 16-bit dimensions");
   if (d_bgr && ((frame_stride & 3) || frame_stride < (size_t)3 * w * h || ((uintptr_t)d_bgr & 3))) return fail("d_bgr must be 4-byte aligned, frame_stride a multiple of 4 and >= 3*w*h");
-  if (d_planes && ((uintptr_t)d_planes & 1)) return fail("d_planes must be 2-byte aligned");
+  if (d_planes && ((uintptr_t)d_planes & 3)) return fail("d_planes must be 4-byte aligned");
   if (((uintptr_t)d_streams | slot) & 15) return fail("d_streams and slot must be multiples of 16 (the scans are fetched in aligned 16-byte groups)");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = (cudaStream_t)stream;

@@ -51,6 +51,7 @@ double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, in
  * dimensions the caller sized its buffers for (0 = any), on return the stream's.  Returns 0 or ORC_DEC_*. */
 enum { ORC_DEC_NOT_JPEG = -1, ORC_DEC_BAD_MARKER = -2, ORC_DEC_TRUNCATED = -3, ORC_DEC_UNSUPPORTED = -4, ORC_DEC_BAD_CODE = -5 };
 int orc_decode(const uint8_t *jpg, size_t n, int *w, int *h, int16_t *Y, int16_t *Cb, int16_t *Cr, uint8_t *bgr);
+void orc_to_bgr(const uint8_t *Y, const uint8_t *Cb, const uint8_t *Cr, int n, uint8_t *bgr);      /* toRgb, func_tester.c:1266-1272 */
 void orc_idct_block(const int16_t *zz, int dc, const int *quant_natural, uint8_t *out, int stride);
 double orc_time_decode(const uint8_t *jpgs, const uint32_t *sizes, size_t slot, int nframes, int reps, uint8_t *bgr_scratch);
 

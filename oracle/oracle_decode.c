@@ -1,7 +1,10 @@
 /* TEST INFRASTRUCTURE ONLY — CPU decoder for the streams the reference's write_jpg produces (see oracle.h).
  *
- * PARITY UNPINNED for the pixel side: the reference has no working decoder.  utils/func_tester.c:1261-1319 holds stubs
- * (`decode` returns 0 at :1262-1264, `idct` ends in a TODO at :1285-1309); what they do fix is restated here:
+ * PARITY UNPINNED for the inverse transform and the up-sampling: the reference has no working decoder.
+ * utils/func_tester.c:1261-1319 holds stubs (`decode` returns 0 at :1262-1264, `idct` ends in a TODO at :1285-1309, `Upsampling`
+ * indexes the chroma row with y instead of y / 2).  The stubs that are complete functions - toRgb, fromZigZag, abs_dc - are
+ * compiled by oracle/Makefile (oracle/_ref/libstubs.so) and PIN their step (tests/test_decoder.py::
+ * test_decoder_steps_against_the_reference_stubs).  What the stubs fix is restated here:
  *   toRgb        :1266-1272   R = Y + 1.4 (Cr-128), G = Y - 0.343 (Cb-128) - 0.711 (Cr-128), B = Y + 1.765 (Cb-128), in double
  *   Upsampling   :1274-1277   every chroma sample is replicated 2 x 2 (nearest neighbour)
  *   idct         :1285-1309   de-quantise, then the separable inverse of encoder.c:87-108 with the same cosine table
@@ -143,6 +146,18 @@ void orc_idct_block(const int16_t *zz, int dc, const int *quant_natural, uint8_t
 
 static uint8_t clamp_trunc(double v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
 
+/* toRgb (utils/func_tester.c:1266-1272) for n pixels with full-resolution Y, Cb, Cr: the same three expressions, evaluated
+ * left to right in double; the stub stores the double into a uint8_t without a range check (undefined for values outside
+ * [0, 255]), here the value is clamped first.  Pinned against the stub itself for every in-range value (tests/test_decoder.py). */
+void orc_to_bgr(const uint8_t *Y, const uint8_t *Cb, const uint8_t *Cr, int n, uint8_t *bgr) {
+  for (int i = 0; i < n; i++) {
+    double y = Y[i], cb = (double)Cb[i] - 128, cr = (double)Cr[i] - 128;
+    bgr[3 * i + 2] = clamp_trunc(y + 1.4 * cr);
+    bgr[3 * i + 1] = clamp_trunc(y - 0.343 * cb - 0.711 * cr);
+    bgr[3 * i + 0] = clamp_trunc(y + 1.765 * cb);
+  }
+}
+
 int orc_decode(const uint8_t *jpg, size_t n, int *w_out, int *h_out, int16_t *Yp, int16_t *Cbp, int16_t *Crp, uint8_t *bgr) {
   if (n < 4 || jpg[0] != 0xFF || jpg[1] != 0xD8) return ORC_DEC_NOT_JPEG;
   int quant[2][64] = {{0}}, have_q[2] = {0, 0};
@@ -235,11 +250,7 @@ int orc_decode(const uint8_t *jpg, size_t n, int *w_out, int *h_out, int16_t *Yp
       }
       for (int y = 0; y < h; y++)
         for (int x = 0; x < w; x++) {
-          double Y = Ys[(size_t)y * w + x], cb = (double)Cbs[(size_t)(y / 2) * cw + x / 2] - 128, cr = (double)Crs[(size_t)(y / 2) * cw + x / 2] - 128;
-          uint8_t *o = bgr + ((size_t)y * w + x) * 3;
-          o[2] = clamp_trunc(Y + 1.4 * cr);
-          o[1] = clamp_trunc(Y - 0.343 * cb - 0.711 * cr);
-          o[0] = clamp_trunc(Y + 1.765 * cb);
+          orc_to_bgr(Ys + (size_t)y * w + x, Cbs + (size_t)(y / 2) * cw + x / 2, Crs + (size_t)(y / 2) * cw + x / 2, 1, bgr + ((size_t)y * w + x) * 3);
         }
       free(Ys); free(Cs);
     }

@@ -84,6 +84,60 @@ def test_oracle_decoder_rejects_damage(oracle, frames):
     assert oracle.decode(bytes(jpg), 64, 80)["rc"] < 0                             # not the dimensions the buffers were sized for
 
 
+STUBS = os.path.join(ROOT, "oracle", "_ref", "libstubs.so")
+
+
+@pytest.mark.skipif(not os.path.exists(STUBS), reason="oracle/_ref/libstubs.so not built (needs /root/reference)")
+def test_decoder_steps_against_the_reference_stubs(oracle):
+    """The stubs that are complete functions pin their step: toRgb on every (Y, Cb, Cr) whose three results lie in [0, 255]
+    (outside, the stub's double -> uint8_t store is undefined; the decoder clamps), fromZigZag, abs_dc."""
+    import ctypes as C
+    L = C.CDLL(STUBS)
+    n = 64 * 64
+    ycc = (C.c_uint8 * (3 * n)).in_dll(L, "YCbCr")
+    rgb = (C.c_uint8 * (3 * n)).in_dll(L, "rgb")
+    ycc_np = np.ctypeslib.as_array(ycc).reshape(3, n)
+    rgb_np = np.ctypeslib.as_array(rgb).reshape(3, n)
+    oracle.lib.orc_to_bgr.argtypes = [C.POINTER(C.c_uint8)] * 3 + [C.c_int, C.POINTER(C.c_uint8)]
+    rng = np.random.default_rng(4)
+    checked = 0
+    for rep in range(64):
+        if rep < 16:                                   # structured: all Y against a slice of (Cb, Cr)
+            yy, cc = np.meshgrid(np.arange(256), np.arange(16), indexing="ij")
+            Y = yy.ravel().astype(np.uint8)
+            Cb = ((cc.ravel() * 16 + rep) % 256).astype(np.uint8)
+            Cr = ((cc.ravel() * 16 + 5 * rep + 3) % 256).astype(np.uint8)
+        else:
+            Y = rng.integers(0, 256, n, dtype=np.uint8)
+            Cb, Cr = (rng.integers(128 - 56, 128 + 56, n).astype(np.uint8) for _ in range(2))     # photographic chroma: mostly in range
+        ycc_np[0], ycc_np[1], ycc_np[2] = Y, Cb, Cr
+        L.toRgb()
+        mine = np.zeros((n, 3), np.uint8)
+        ya, ca, ra = (np.ascontiguousarray(a) for a in (Y, Cb, Cr))
+        oracle.lib.orc_to_bgr(ya.ctypes.data_as(C.POINTER(C.c_uint8)), ca.ctypes.data_as(C.POINTER(C.c_uint8)), ra.ctypes.data_as(C.POINTER(C.c_uint8)), n,
+                              mine.ctypes.data_as(C.POINTER(C.c_uint8)))
+        y, cb, cr = Y.astype(np.float64), Cb.astype(np.float64) - 128, Cr.astype(np.float64) - 128
+        r, g, b = y + 1.4 * cr, y - 0.343 * cb - 0.711 * cr, y + 1.765 * cb
+        ok = (r >= 0) & (r < 256) & (g >= 0) & (g < 256) & (b >= 0) & (b < 256)
+        assert np.array_equal(mine[ok, 2], rgb_np[0][ok]) and np.array_equal(mine[ok, 1], rgb_np[1][ok]) and np.array_equal(mine[ok, 0], rgb_np[2][ok])
+        checked += int(ok.sum())
+    assert checked > 120000
+    # fromZigZag (:1311-1314): out[scan_order[i]] = in[i]
+    L.fromZigZag.argtypes = [C.POINTER(C.c_int16)] * 2
+    src = np.arange(100, 164, dtype=np.int16)
+    dst = np.zeros(64, np.int16)
+    L.fromZigZag(src.ctypes.data_as(C.POINTER(C.c_int16)), dst.ctypes.data_as(C.POINTER(C.c_int16)))
+    zz = np.ctypeslib.as_array((C.c_int * 64).in_dll(oracle.lib, "orc_zigzag"))
+    assert np.array_equal(dst[zz], src)
+    # abs_dc (:1316-1319): DC = running sum of the differences (the stub works on int8; small values)
+    L.abs_dc.argtypes = [C.POINTER(C.c_int8)]
+    q = np.zeros(n, np.int8)
+    diffs = rng.integers(-3, 4, n // 64).astype(np.int8)
+    q[::64] = diffs
+    L.abs_dc(q.ctypes.data_as(C.POINTER(C.c_int8)))
+    assert np.array_equal(q[::64].astype(int), np.cumsum(diffs.astype(int)))
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 @pytest.fixture(scope="module")
 def enc():

@@ -159,7 +159,8 @@ __global__ void __launch_bounds__(256) k_dec_parse(const uint8_t* __restrict__ s
 //                 256-byte ring of big-endian words.  Past the scan's last byte the stream continues with 1-bits: fill_last_byte
 //                 (encoder.c:425-432) pads with ones and never stuffs, so a final 0xFF reads as the next marker's first byte.
 //   window        lane i looks at the 32 bits that start i bits behind the read position
-//   result        total bits | run << 6 | (size == 0) << 10 | invalid << 11 | value << 16, for the AC and for the DC reading
+//   result        total bits | advance inside the block << 6 | stores a coefficient << 13 | invalid << 14 | value << 16, for the
+//                 AC and for the DC reading
 //   walk          position 0 is a token start; the token there tells where the next one starts (all state warp-uniform)
 // The block under construction lives in shared memory and leaves as one 128-byte store (no zeroed planes needed).
 struct DecWarp {
@@ -194,10 +195,14 @@ __device__ __forceinline__ uint32_t dec_token(const DecWarp& sm, int c, uint32_t
     sym = sm.val[c][(sm.off[c][l] + (int)(c16 >> (7 - l))) & 255];
   }
   const int sz = c ? sym & 15 : sym & 31, run = c ? sym >> 4 : 0;
-  bad |= (!c && sym > 15) || (c && sz == 0 && run != 0 && run != 15) || len + sz > 31;
+  const bool special = c && sz == 0;            // ZRL (run 15, encoder.c:470-476) or EOB (run 0, :496-500)
+  bad |= (!c && sym > 15) || (special && run != 0 && run != 15) || len + sz > 31;
   const uint32_t raw = sz ? (win << len) >> (32 - sz) : 0u;
   const int v = dec_extend(raw, sz & 15);
-  return (uint32_t)((len + sz) & 63) | ((uint32_t)run << 6) | ((sz == 0 ? 1u : 0u) << 10) | (bad << 11) | ((uint32_t)v << 16);
+  // what the walk needs, ready to use: bits 0..5 token length, 6..12 how far the position inside the block advances (run + 1;
+  // 16 for a ZRL; 64 for an EOB: the block is full), 13 "a coefficient is stored" (at the new position - 1), 14 invalid
+  const uint32_t dk = special ? (run == 15 ? 16u : 64u) : (uint32_t)run + 1u;
+  return (uint32_t)((len + sz) & 63) | (dk << 6) | ((special ? 0u : 1u) << 13) | (bad << 14) | ((uint32_t)v << 16);
 }
 
 // planes of frame f: Y (w*h), Cb, Cr (w*h/4 each) int16; dcabs: one int16 per block in the same order
@@ -280,17 +285,15 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
       const uint32_t Rd = __shfl_sync(FULL, r_dc, (int)pos), Ra = __shfl_sync(FULL, r_ac, (int)pos);
       const bool is_dc = k == 0;
       const uint32_t R = is_dc ? Rd : Ra;
-      const int v = (int)R >> 16, run = (int)(R >> 6) & 15;
-      const bool zero_size = (R & 0x400u) != 0;              // AC: ZRL / EOB (encoder.c:470-476, :496-500); DC: a zero difference
-      const int kc = is_dc ? 0 : k + run;                    // where the value goes
-      const bool store = is_dc || !zero_size;
-      bad |= (R & 0x800u) | (store && kc > 63 ? 0x800u : 0u);
-      if (lane == 0 && store) reinterpret_cast<int16_t*>(sm.blk)[kc & 63] = (int16_t)v;
-      if (is_dc) {                                           // encoder.c:434-448
-        pred += v;
+      const int k2 = k + (int)((R >> 6) & 127u);             // DC: 0 -> 1 (encoder.c:434-448); AC: past the run and the coefficient
+      const bool store = (R & 0x2000u) != 0;
+      bad |= (R & 0x4000u) | (store && k2 > 64 ? 0x4000u : 0u) | ((R & 63u) == 0 ? 0x4000u : 0u);
+      if (lane == 0 && store) reinterpret_cast<int16_t*>(sm.blk)[(k2 - 1) & 63] = (int16_t)((int)R >> 16);
+      if (is_dc) {
+        pred += (int)R >> 16;
         if (lane == 0) dca[b] = (int16_t)pred;
       }
-      k = store ? kc + 1 : (run == 15 ? k + 16 : 64);
+      k = k2;
       pos += R & 63u;
       if (k >= 64) {                                         // the block is complete: one 128-byte store, and a clean slate
         __syncwarp();
@@ -300,7 +303,6 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
         b++;
         k = 0;
       }
-      if ((R & 63u) == 0) bad |= 0x800u;                     // (cannot happen for a valid token: guards the loop against hostile tables)
       if (bad) break;
     }
     if (bad) { rc = JB_DEC_BAD_CODE; break; }

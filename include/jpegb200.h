@@ -27,7 +27,8 @@ int jpegb200_create(jpegb200_ctx **ctx, int device);
 void jpegb200_destroy(jpegb200_ctx *ctx);
 const char *jpegb200_last_error(void);
 
-/* frames_per_wave: jobs that share one chain of launches (default 32; the persistent kernels want a few thousand tiles per wave);
+/* frames_per_wave: jobs that share one chain of launches (default: chosen per call from the frame size - 64 frames of 1920x1280
+ * device-resident, 16 on the host path, scaled by pixels; the persistent kernels want a few thousand tiles per wave);
  * lanes: independent streams/workspaces the waves rotate over (default 3). */
 int jpegb200_configure(jpegb200_ctx *ctx, int frames_per_wave, int lanes);
 

@@ -177,7 +177,7 @@ __global__ void k_fill_jobs(JbJob* jobs, int n, const uint8_t* src0, size_t fram
 
 struct jpegb200_ctx {
   int device = 0;
-  int frames_per_wave = 32;
+  int frames_per_wave = 0;    // 0 = automatic (wave_frames below); jpegb200_configure sets it
   int exact_dct = 0;          // 1 = literal FP64 chain for every block (the on-device checker of the fast path)
   int overlap_waves = 0;      // set by the batched entry points when several waves will be in flight on different lanes
   int split_streams = 1;      // token path: run the kernels after k_pixels_to_tokens on the lane's high-priority stream
@@ -392,6 +392,15 @@ void jpegb200_destroy(jpegb200_ctx* c) {
   delete c;
 }
 
+// Frames per wave when the caller has not configured one: what the sweeps of DESIGN.md 5.5 found for 1920x1280 (64 frames per
+// wave device-resident, 16 on the host path, where smaller waves keep the PCIe pipeline full), scaled by the frame size.
+static int wave_frames(const jpegb200_ctx* c, int w, int h, bool host_path) {
+  if (c->frames_per_wave > 0) return c->frames_per_wave;
+  const double target = (host_path ? 16.0 : 64.0) * 1920.0 * 1280.0;
+  const double g = target / ((double)w * (double)h);
+  return g < 1.0 ? 1 : g > 1024.0 ? 1024 : (int)(g + 0.5);
+}
+
 int jpegb200_configure(jpegb200_ctx* c, int frames_per_wave, int lanes) {
   if (!c) return fail("null ctx");
   if (frames_per_wave < 1 || frames_per_wave > 4096 || lanes < 1 || lanes > 16) return fail("bad configuration");
@@ -468,7 +477,7 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   CK(cudaSetDevice(c->device));
   cudaStream_t user = (cudaStream_t)stream;
   const JobDims jd = job_dims(w, h, slot);
-  const int G = c->frames_per_wave;
+  const int G = wave_frames(c, w, h, false);
   WaveDims wd;
   const size_t g = (size_t)std::min(G, n);
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
@@ -512,7 +521,7 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   const size_t src_frame = fmt == JPEGB200_FMT_BGR888 ? frame : fmt == JPEGB200_FMT_RGB565 ? (size_t)2 * w * h : (size_t)w * h;
   const size_t dslot = (slot + 15) & ~(size_t)15;
   const JobDims jd = job_dims(w, h, slot);
-  const int G = c->frames_per_wave;
+  const int G = wave_frames(c, w, h, true);
   const size_t g = (size_t)std::min(G, n);
   WaveDims wd;
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;

@@ -115,7 +115,7 @@ struct JbWs {
   JbHuff* huff;         // per job: 4 tables in the same order
   uint32_t* enc;        // per job: 4 x 256 packed (code << 5 | len)
   uint32_t* scratch;    // un-stuffed scan bits, big-endian bytes
-  uint32_t* tile_ff;    // per tile: 0xFF count, then (after k_layout) exclusive prefix inside the segment
+  uint32_t* tile_ff;    // per tile: 0xFF count, then (after layout_job) exclusive prefix inside the segment
   uint32_t* fix_count;  // per wave: number of entries in fix_list (zeroed with the state block)
   uint2* fix_list;      // per wave: (job, block id inside the job) of blocks the fast DCT could not decide
   uint32_t* tok;        // token path: token pool

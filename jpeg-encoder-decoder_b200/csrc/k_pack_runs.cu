@@ -3,14 +3,16 @@
 //   k_runs_prepare    per job: the first DC token of every run (encoder.c:168-177 predicts across the whole plane, a run only
 //                     knows its own blocks) with its histogram entry; exclusive prefix of the runs' token counts inside each
 //                     scan = where each run goes in scan order
-//   k_compact_tokens  per batch of 16 consecutive runs (one warp): copies the runs' tokens into scan order (ws.tok2) and adds their code bits
-//                     (code length + magnitude bits [+ ZRL codes]) to the totals of the token chunks they land in
-//                     The CTA that finishes a job last then scans (scan_tchunks): exclusive prefix of the chunk bits inside
-//                     each of the three scans, scan placement in the job's scratch area, clearing of the words two chunks share
+//   k_compact_tokens  per batch of 16 consecutive runs (one warp): copies the runs' tokens into scan order (ws.tok2), resolved to
+//                     (code word, length), and adds their code bits (code length + magnitude bits [+ ZRL codes]) to the totals
+//                     of the token chunks they land in
+//   k_scan_tchunks    per job: exclusive prefix of the chunk bits inside each of the three scans, scan placement in the job's
+//                     scratch area, clearing of the words two chunks share (JB_FUSE_SCAN = 1 runs it in the CTA of
+//                     k_compact_tokens that finishes the job last instead: measured slower, profiles/r2b_summary.md)
 //   k_pack_tchunks    per chunk of 256 tokens (one warp): 8 consecutive tokens per lane are concatenated in registers, a warp
 //                     scan gives the bit offsets, the chunk's bits are assembled in shared memory and flushed as big-endian
 //                     words (the first and the last word of a chunk are OR-ed into place)
-// Byte stuffing, headers and layout stay with k_count_ff / k_layout / k_stuff (k_entropy.cu).
+// Byte stuffing, headers and layout stay with k_count_ff (+ layout_job) / k_stuff (k_entropy.cu).
 #include "jpegb200_internal.cuh"
 #include "walk.cuh"
 

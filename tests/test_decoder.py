@@ -221,3 +221,23 @@ def test_encode_decode_round_trip_on_the_device_full_size(enc, frames):
     err = d_bgr[::2].float() - d_in[::2].float()          # the natural frames
     psnr = 10 * torch.log10(255.0 ** 2 / (err ** 2).mean())
     assert psnr > 23.0, float(psnr)                       # 24.7 dB: this quantiser on the tiled photograph (the CPU test sees 25.3 dB on one tile)
+
+
+@pytest.mark.gpu
+def test_decode_tester_c_caller(tmp_path, oracle, golden):
+    """tools/decode_tester (plain C against include/jpegb200.h) on the golden streams of the unmodified reference: the PPMs it
+    writes hold the oracle decoder's pixels."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "decode_tester")
+    assert os.path.exists(exe), "tools/decode_tester is built by __graft_entry__.build()"
+    files = [os.path.join(GOLD, k + ".jpg") for k in ("sample_640x640_bgr", "sample_640x640_diffs_bgr")]
+    files = [f for f in files if os.path.exists(f)]
+    assert files
+    r = subprocess.run([exe, "640", "640", str(tmp_path / "out")] + files, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "%d of %d streams decoded" % (len(files), len(files)) in r.stdout, (r.stdout, r.stderr)
+    for i, f in enumerate(files):
+        ppm = (tmp_path / ("out%d.ppm" % i)).read_bytes()
+        hdr = b"P6\n640 640\n255\n"
+        assert ppm.startswith(hdr)
+        want = oracle.decode(open(f, "rb").read(), 640, 640)["bgr"][:, :, ::-1]
+        assert ppm[len(hdr):] == want.tobytes()

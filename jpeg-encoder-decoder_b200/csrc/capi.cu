@@ -193,7 +193,7 @@ struct jpegb200_ctx {
   DevBuf cmp_frame, cmp_sub, cmp_saved, cmp_saved_in, cmp_bits, cmp_outs, cmp_rout, cmp_misc, cmp_arena;
   PinBuf cmp_host;
   // decoding side: per-stream descriptors, scratch planes / absolute DCs / samples, staging of the host variant
-  DevBuf dec_frames, dec_planes, dec_dcabs, dec_samples, dec_in, dec_sizes, dec_out, dec_planes_out;
+  DevBuf dec_frames, dec_planes, dec_dcabs, dec_samples, dec_in, dec_sizes, dec_out, dec_planes_out, dec_scratch;
   bool have_saved = false;
   int saved_w = 0, saved_h = 0;
 };
@@ -386,7 +386,7 @@ void jpegb200_destroy(jpegb200_ctx* c) {
   cudaDeviceSynchronize();
   for (auto& l : c->lanes) l.release();
   for (DevBuf* b : {&c->cmp_frame, &c->cmp_sub, &c->cmp_saved, &c->cmp_saved_in, &c->cmp_bits, &c->cmp_outs, &c->cmp_rout, &c->cmp_misc, &c->cmp_arena}) b->release();
-  for (DevBuf* b : {&c->dec_frames, &c->dec_planes, &c->dec_dcabs, &c->dec_samples, &c->dec_in, &c->dec_sizes, &c->dec_out, &c->dec_planes_out}) b->release();
+  for (DevBuf* b : {&c->dec_frames, &c->dec_planes, &c->dec_dcabs, &c->dec_samples, &c->dec_in, &c->dec_sizes, &c->dec_out, &c->dec_planes_out, &c->dec_scratch}) b->release();
   c->cmp_host.release();
   if (c->fork) cudaEventDestroy(c->fork);
   delete c;
@@ -616,8 +616,21 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
     d_planes = (int16_t*)c->dec_planes.p;
   }
   if (d_bgr && (e = c->dec_samples.ensure((size_t)n * (npix + npix / 2))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
-  jb_launch_decode(d_streams, slot, d_sizes, n, w, h, c->dec_frames.p, d_planes, (int16_t*)c->dec_dcabs.p, (uint8_t*)c->dec_samples.p, d_bgr, frame_stride, d_status, st);
-  c->launches += d_bgr ? 4 : 2;
+  // scratch of the sub-sequence decoder (JPEGB200_DEC_SEQUENTIAL=1: development switch, the warp-per-scan decoder for every scan)
+  static int sequential = -1;
+  if (sequential < 0) { const char* ev = getenv("JPEGB200_DEC_SEQUENTIAL"); sequential = ev ? atoi(ev) : 0; }
+  void* scratch[8] = {};
+  if (!sequential) {
+    size_t part[8], total = 0;
+    jb_dec_scratch_bytes(slot, n, part);
+    for (int i = 0; i < 8; i++) { part[i] = (part[i] + 255) & ~(size_t)255; total += part[i]; }
+    if ((e = c->dec_scratch.ensure(total)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
+    size_t off = 0;
+    for (int i = 0; i < 8; i++) { scratch[i] = (uint8_t*)c->dec_scratch.p + off; off += part[i]; }
+  }
+  jb_launch_decode(d_streams, slot, d_sizes, n, w, h, c->dec_frames.p, d_planes, (int16_t*)c->dec_dcabs.p, (uint8_t*)c->dec_samples.p, d_bgr, frame_stride, d_status,
+                   sequential ? nullptr : scratch, st);
+  c->launches += (d_bgr ? 4 : 2) + (sequential ? 0 : 5 + 6);
   if (d_status) c->launches++;
   CK(cudaGetLastError());
   return 0;

@@ -206,13 +206,15 @@ __device__ __forceinline__ uint32_t dec_token(const DecWarp& sm, int c, uint32_t
 }
 
 // planes of frame f: Y (w*h), Cb, Cr (w*h/4 each) int16; dcabs: one int16 per block in the same order
+// `only` (may be null): per scan, non-zero = decode it here (the scans the sub-sequence decoder below gave up on).
 __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __restrict__ streams, size_t slot, int nframes, int w, int h, JbDecFrame* frames,
-                                                          int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
+                                                          int16_t* __restrict__ planes, int16_t* __restrict__ dcabs, const uint32_t* __restrict__ only) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
   __shared__ DecWarp sm_all[DS_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * DS_WARPS + warp;                  // the Y scans (ten times the chroma scans' length) come first
   if (t >= 3 * nframes) return;
+  if (only && !only[t]) return;
   const int comp = t / nframes, f = t - comp * nframes;
   JbDecFrame& fr = frames[f];
   if (fr.status) return;
@@ -309,6 +311,234 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
     bp += pos;
   }
   if (rc && lane == 0) atomicCAS(&fr.status, 0, rc);
+}
+
+// ---- entropy decoding in parallel INSIDE a scan: sub-sequences that synchronise themselves ---------------------------------
+// (Klein & Wiseman's observation that Huffman decoders started at a wrong bit re-synchronise after a few codes; used for JPEG
+// on GPUs by Weissenberger & Schmidt.)  A scan's clean stream is cut into sub-sequences of 1024 bits, one THREAD each:
+//   k_dec_unstuff   one warp per scan: the scan's bytes without the stuffed zeros, at an aligned place of its own
+//   k_dec_sub<0>    every thread decodes from the first bit of its sub-sequence as if a token started there (inside a block,
+//                   not at a DC) and records where the first token behind its sub-sequence starts and at which position of a
+//                   block: its EXIT STATE.  Thread 0 of a scan starts from the truth.
+//   k_dec_sub<1>    every thread whose predecessor's exit state differs from the start state it used decodes again from that
+//                   state.  Truth spreads from thread 0 at least one sub-sequence per pass, in practice everywhere after one
+//                   or two: a wrong start re-synchronises within a block or two (35 bits each), so most exit states are right
+//                   from the beginning.  A pass in which no thread had to decode again proves every state: each one follows
+//                   from its predecessor's, and the first is exact.  The passes also count the blocks a thread completes.
+//   k_dec_base      per scan: prefix of those counts = the block every thread starts in; scans that did not settle in the
+//                   fixed number of passes, or whose blocks do not add up, are left to the warp-per-scan decoder above
+//   k_dec_sub<2>    decodes once more from the proven states and writes the coefficients (zeroed planes)
+//   k_dec_dcabs     per scan: running sum of the DC differences (abs_dc, utils/func_tester.c:1316-1319)
+// State word: clean bit position | position inside the block << 26.
+constexpr int SUB_BITS = 1024, SUB_WORDS = SUB_BITS / 32, SUB_CTA = 128, SUB_ROWS = SUB_CTA + 1;
+
+struct JbDecScratch {          // all device pointers; S, used, ends, base: n * subs_per_frame entries
+  uint8_t* clean;              // n x (slot + 128) bytes
+  uint32_t* cbits;             // 3 n: clean bits per scan (scan t = comp * n + frame)
+  uint32_t *S, *used, *ends, *base;
+  uint32_t* changed;           // (passes + 1) x 3 n
+  uint32_t* fallback;          // 3 n
+  uint32_t subs_per_frame;
+};
+__device__ __forceinline__ uint32_t dec_clean_off(const JbDecFrame& fr, int comp) { return ((fr.scan_start[comp] + 15u) & ~15u) + 16u * (uint32_t)comp; }
+__device__ __forceinline__ uint32_t dec_sub_off(const JbDecFrame& fr, int comp) { return dec_clean_off(fr, comp) / 128u + 2u * (uint32_t)comp; }
+
+__global__ void __launch_bounds__(DS_WARPS * 32) k_dec_unstuff(const uint8_t* __restrict__ streams, size_t slot, int nframes, const JbDecFrame* __restrict__ frames, JbDecScratch sc) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * DS_WARPS + warp;
+  if (t >= 3 * nframes) return;
+  const int comp = t / nframes, f = t - comp * nframes;
+  const JbDecFrame& fr = frames[f];
+  if (fr.status) { if (lane == 0) sc.cbits[t] = 0; return; }
+  const uint8_t* stream = streams + (size_t)f * slot;
+  const uintptr_t a0 = (uintptr_t)(stream + fr.scan_start[comp]);
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)15);
+  const uint32_t start = (uint32_t)(a0 & 15), stop = start + (fr.scan_end[comp] - fr.scan_start[comp]);
+  uint8_t* out = sc.clean + (size_t)f * (slot + 128) + dec_clean_off(fr, comp);
+  uint32_t produced = 0, prev_byte = 0;
+  for (uint32_t rword = 0; rword * 4u < stop; rword += 32) {
+    const uint32_t p0 = (rword + lane) * 4u;
+    const uint32_t wv = p0 < stop ? __ldg(base + rword + lane) : 0u;           // (a word that starts inside the scan lies inside the slot)
+    uint32_t by[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) by[j] = (wv >> (8 * j)) & 0xFFu;
+    uint32_t before = __shfl_up_sync(FULL, by[3], 1);
+    if (lane == 0) before = prev_byte;
+    uint32_t keep = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t pr = j ? by[j - 1] : before;
+      const bool inside = p0 + j >= start && p0 + j < stop;
+      keep |= (inside && !(by[j] == 0x00u && pr == 0xFFu) ? 1u : 0u) << j;      // 0xFF 0x00 -> 0xFF (encoder.c:405-408)
+    }
+    const uint32_t cnt = (uint32_t)__popc(keep);
+    uint32_t inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(FULL, inc, o);
+      if (lane >= o) inc += n;
+    }
+    uint32_t dst = produced + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if ((keep >> j) & 1u) out[dst++] = (uint8_t)by[j];
+    produced += __shfl_sync(FULL, inc, 31);
+    prev_byte = __shfl_sync(FULL, by[3], 31);
+  }
+  // the stream continues with 1-bits (fill_last_byte never stuffs its pad byte, encoder.c:425-432): pad to a 16-byte boundary + 16
+  for (uint32_t k = produced + lane; k < ((produced + 15u) & ~15u) + 16u; k += 32) out[k] = 0xFF;
+  if (lane == 0) sc.cbits[t] = produced * 8u;
+}
+
+// MODE 0: speculate from the sub-sequence's first bit; 1: decode again where the predecessor's exit state is news; 2: write.
+template <int MODE>
+__global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, size_t slot, JbDecFrame* frames, JbDecScratch sc, uint32_t* changed /*3n, this pass*/,
+                                                    int16_t* __restrict__ planes) {
+  __shared__ DecWarp tab;                              // (ring and blk unused here)
+  __shared__ uint32_t rows[SUB_ROWS * (SUB_WORDS + 1)];  // the CTA's 129 sub-sequences, big-endian words, one word of padding per row
+  __shared__ int s_work;
+  const int t = blockIdx.y, comp = t / nframes, f = t - comp * nframes, tid = threadIdx.x;
+  JbDecFrame& fr = frames[f];
+  if (fr.status) return;
+  if (MODE == 2 && sc.fallback[t]) return;
+  const uint32_t total_bits = sc.cbits[t], nsub = max(1u, (total_bits + SUB_BITS - 1) / SUB_BITS);
+  const uint32_t i0 = blockIdx.x * SUB_CTA, i = i0 + tid;
+  if (i0 >= nsub) return;
+  const size_t sbase = (size_t)f * sc.subs_per_frame + dec_sub_off(fr, comp);
+  uint32_t* S = sc.S + sbase;
+  uint32_t* used = sc.used + sbase;
+  // start state
+  uint32_t st = 0;
+  bool work = i < nsub;
+  if (work) {
+    if (MODE == 0) st = i ? (i * SUB_BITS) | (1u << 26) : 0u;
+    else st = i ? S[i - 1] : 0u;
+    if (MODE == 1) work = st != used[i];
+  }
+  if (MODE == 1) {                                     // nothing new for any thread of the CTA: the common case from the second pass on
+    if (tid == 0) s_work = 0;
+    __syncthreads();
+    if (work) s_work = 1;
+    __syncthreads();
+    if (!s_work) return;
+  }
+  {
+    const JbDecTab& dc = fr.tab[0][fr.td[comp]];
+    const JbDecTab& ac = fr.tab[1][fr.ta[comp]];
+    for (int q = tid; q < 256; q += SUB_CTA) { tab.look[0][q] = dc.look[q]; tab.look[1][q] = ac.look[q]; tab.val[0][q] = dc.val[q]; tab.val[1][q] = ac.val[q]; }
+    if (tid < 8) { tab.limit[0][tid] = dc.limit16[9 + tid]; tab.limit[1][tid] = ac.limit16[9 + tid]; tab.off[0][tid] = dc.valoff[9 + tid]; tab.off[1][tid] = ac.valoff[9 + tid]; }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.clean + (size_t)f * (slot + 128) + dec_clean_off(fr, comp)) + (size_t)i0 * SUB_WORDS;
+    const uint32_t nwords = (total_bits + 31) / 32 + 4;                                // the padding behind the stream is valid memory
+    for (uint32_t q = tid; q < SUB_ROWS * SUB_WORDS; q += SUB_CTA) {
+      const uint32_t wv = i0 * SUB_WORDS + q < nwords ? __ldg(src + q) : 0xFFFFFFFFu;
+      rows[(q >> 5) * (SUB_WORDS + 1) + (q & 31)] = __byte_perm(wv, 0, 0x0123);
+    }
+  }
+  __syncthreads();
+  if (!work) return;
+  const uint32_t limit = min((i + 1) * SUB_BITS, total_bits);
+  const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
+  const size_t npix = (size_t)w * h;
+  int16_t* plane = MODE == 2 ? planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4) : nullptr;
+  uint32_t pos = st & 0x3FFFFFFu, blk = MODE == 2 ? sc.base[sbase + i] : 0u, ends = 0, bad = 0;
+  int k = (int)(st >> 26);
+  while (pos < limit && (MODE != 2 || blk < nblocks)) {
+    const uint32_t q = pos - i0 * SUB_BITS, wq = q >> 5;
+    const uint32_t w0 = rows[(wq >> 5) * (SUB_WORDS + 1) + (wq & 31)], w1 = rows[((wq + 1) >> 5) * (SUB_WORDS + 1) + ((wq + 1) & 31)];
+    const uint32_t win = __funnelshift_l(w1, w0, q & 31u);
+    const uint32_t R = dec_token(tab, k == 0 ? 0 : 1, win);
+    if ((R & 0x4000u) || (R & 63u) == 0) {             // no token here: a wrong guess (modes 0, 1) moves on by one bit; with proven states it is the stream
+      if (MODE == 2) { bad = 1; break; }
+      pos++;
+      continue;
+    }
+    int k2 = k + (int)((R >> 6) & 127u);
+    if (R & 0x2000u) {
+      if (k2 > 64) { if (MODE == 2) { bad = 1; break; } k2 = 64; }
+      if (MODE == 2) plane[(size_t)blk * 64 + (k2 - 1)] = (int16_t)((int)R >> 16);
+    }
+    pos += R & 63u;
+    k = k2;
+    if (k >= 64) { k = 0; ends++; blk++; }
+  }
+  if (MODE == 2) {
+    if (bad) atomicCAS(&fr.status, 0, JB_DEC_BAD_CODE);
+    return;
+  }
+  const uint32_t exit_state = pos | ((uint32_t)k << 26);
+  if (MODE == 0 || exit_state != S[i] || st != used[i]) {
+    if (MODE == 1 && exit_state != S[i]) changed[t] = 1;
+    S[i] = exit_state;
+  }
+  used[i] = st;
+  sc.ends[sbase + i] = ends;
+}
+
+// Per scan: the block every sub-sequence starts in; give up on scans that did not settle or do not add up.
+__global__ void __launch_bounds__(256) k_dec_base(int nframes, int w, int h, JbDecFrame* frames, JbDecScratch sc, const uint32_t* __restrict__ changed_last) {
+  __shared__ uint32_t wsum[8], carry_s;
+  const int t = blockIdx.x, comp = t / nframes, f = t - comp * nframes, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const JbDecFrame& fr = frames[f];
+  if (fr.status) { if (tid == 0) sc.fallback[t] = 0; return; }
+  const uint32_t total_bits = sc.cbits[t], nsub = max(1u, (total_bits + SUB_BITS - 1) / SUB_BITS);
+  const size_t sbase = (size_t)f * sc.subs_per_frame + dec_sub_off(fr, comp);
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < nsub; b0 += 256) {
+    const uint32_t i = b0 + tid, v = i < nsub ? sc.ends[sbase + i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wex = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { wex += q < warp ? wsum[q] : 0u; tot += wsum[q]; }
+    if (i < nsub) sc.base[sbase + i] = carry_s + wex + inc - v;
+    __syncthreads();
+    if (tid == 0) carry_s += tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
+    sc.fallback[t] = (changed_last[t] != 0 || carry_s < nblocks) ? 1u : 0u;    // (more block ends than blocks: bits behind the last block)
+  }
+}
+
+// abs_dc: the running sum of the DC differences of a plane.
+__global__ void __launch_bounds__(256) k_dec_dcabs(int nframes, int w, int h, const JbDecFrame* __restrict__ frames, const int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
+  __shared__ int wsum[8], carry_s;
+  const int t = blockIdx.x, comp = t / nframes, f = t - comp * nframes, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (frames[f].status) return;
+  const size_t npix = (size_t)w * h;
+  const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
+  const int16_t* plane = planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4);
+  int16_t* dca = dcabs + (size_t)f * (npix / 64 * 3 / 2) + (comp == 0 ? 0 : comp == 1 ? npix / 64 : npix / 64 + npix / 256);
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t b0 = 0; b0 < nblocks; b0 += 256) {
+    const uint32_t b = b0 + tid;
+    const int v = b < nblocks ? plane[(size_t)b * 64] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int wex = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) { wex += q < warp ? wsum[q] : 0; tot += wsum[q]; }
+    if (b < nblocks) dca[b] = (int16_t)(carry_s + wex + inc);
+    __syncthreads();
+    if (tid == 0) carry_s += tot;
+    __syncthreads();
+  }
 }
 
 // 8 threads per block, 16 blocks per CTA.  Block ids run over Y, Cb, Cr of one frame (blockIdx.y = frame).
@@ -415,14 +645,44 @@ __global__ void k_dec_status(const JbDecFrame* frames, int n, int32_t* status) {
 
 size_t jb_dec_frame_bytes() { return sizeof(JbDecFrame); }
 
+constexpr int DEC_SYNC_PASSES = 6;
+// Scratch of the sub-sequence decoder for n streams in slots of `slot` bytes: bytes of each part (clean, cbits, S, used, ends, base, changed, fallback).
+void jb_dec_scratch_bytes(size_t slot, int n, size_t out[8]) {
+  const size_t subs = (slot + 128) / 128 + 8;
+  out[0] = (size_t)n * (slot + 128);
+  out[1] = (size_t)3 * n * 4;
+  out[2] = out[3] = out[4] = out[5] = (size_t)n * subs * 4;
+  out[6] = (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4;
+  out[7] = (size_t)3 * n * 4;
+}
+
 // d_frames: n x jb_dec_frame_bytes(); d_planes: n x (w*h*3/2) int16; d_dcabs: n x (w*h/64*3/2) int16;
-// d_samples: n x (w*h*3/2) bytes; d_bgr may be null (planes only); d_status may be null.
+// d_samples: n x (w*h*3/2) bytes; d_bgr may be null (planes only); d_status may be null; scratch: the eight parts above in one
+// 256-byte aligned allocation each (null: warp-per-scan decoder only).
 void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_sizes, int n, int w, int h, void* d_frames, int16_t* d_planes, int16_t* d_dcabs,
-                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, cudaStream_t st) {
+                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, void* const scratch[8], cudaStream_t st) {
   JbDecFrame* fr = reinterpret_cast<JbDecFrame*>(d_frames);
   const size_t npix = (size_t)w * h;
   k_dec_parse<<<n, 256, 0, st>>>(d_streams, slot, d_sizes, w, h, fr);
-  k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs);
+  const bool parallel = scratch && slot * 8 < ((size_t)1 << 26);          // the state word holds 26 bits of position
+  if (parallel) {
+    JbDecScratch sc;
+    sc.clean = (uint8_t*)scratch[0]; sc.cbits = (uint32_t*)scratch[1]; sc.S = (uint32_t*)scratch[2]; sc.used = (uint32_t*)scratch[3];
+    sc.ends = (uint32_t*)scratch[4]; sc.base = (uint32_t*)scratch[5]; sc.changed = (uint32_t*)scratch[6]; sc.fallback = (uint32_t*)scratch[7];
+    sc.subs_per_frame = (uint32_t)((slot + 128) / 128 + 8);
+    cudaMemsetAsync(sc.changed, 0, (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4, st);
+    cudaMemsetAsync(d_planes, 0, (size_t)n * (npix + npix / 2) * sizeof(int16_t), st);
+    k_dec_unstuff<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, fr, sc);
+    const dim3 grid((unsigned)((sc.subs_per_frame + SUB_CTA - 1) / SUB_CTA), (unsigned)(3 * n));
+    k_dec_sub<0><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed, nullptr);
+    for (int p = 1; p <= DEC_SYNC_PASSES; p++) k_dec_sub<1><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed + (size_t)p * 3 * n, nullptr);
+    k_dec_base<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc, sc.changed + (size_t)DEC_SYNC_PASSES * 3 * n);
+    k_dec_sub<2><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, nullptr, d_planes);
+    k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs, sc.fallback);
+    k_dec_dcabs<<<3 * n, 256, 0, st>>>(n, w, h, fr, d_planes, d_dcabs);
+  } else {
+    k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs, nullptr);
+  }
   if (d_bgr) {
     const uint32_t nb = (uint32_t)(npix / 64 * 3 / 2);
     k_dec_idct<<<dim3((nb + 15) / 16, n), 128, 0, st>>>(w, h, fr, d_planes, d_dcabs, d_samples);

@@ -100,6 +100,13 @@ int jpegb200_unpack(jpegb200_ctx *ctx, const uint8_t *d_src, int fmt, int n, int
 enum { JPEGB200_DEC_NOT_JPEG = -1, JPEGB200_DEC_BAD_MARKER = -2, JPEGB200_DEC_TRUNCATED = -3, JPEGB200_DEC_UNSUPPORTED = -4, JPEGB200_DEC_BAD_CODE = -5 };
 int jpegb200_decode_batch(jpegb200_ctx *ctx, const uint8_t *d_streams, size_t slot, const uint32_t *d_sizes, int n, int w, int h,
                           uint8_t *d_bgr, size_t frame_stride, int16_t *d_planes, int32_t *d_status, void *stream);
+/* Entropy decoding runs in parallel inside a scan (sub-sequences of 1024 bits that synchronise themselves, proven by a pass
+ * without changes) and falls back to one warp per scan where that does not settle; on = 1 forces the warp-per-scan decoder
+ * everywhere (tests compare the two). */
+int jpegb200_set_decode_sequential(jpegb200_ctx *ctx, int on);
+/* Test hook (synchronises): stats8[0] scans of the last decode call that went through the sub-sequence decoder, [1] scans it
+ * left to the warp-per-scan decoder, [2..7] scans in which synchronisation pass 1..6 still changed a state. */
+int jpegb200_debug_decode_stats(jpegb200_ctx *ctx, uint32_t *stats8);
 /* Same work with HOST buffers (synchronous); h_planes and h_status may be NULL. */
 int jpegb200_decode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_streams, size_t slot, const uint32_t *h_sizes, int n, int w, int h,
                                uint8_t *h_bgr, int16_t *h_planes, int32_t *h_status);

@@ -101,6 +101,8 @@ def load_library() -> C.CDLL:
     # the reference's own entry points (include/encoder.h, include/brain.h)
     L.jpegb200_decode_batch.argtypes = [vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp]
     L.jpegb200_decode_batch_host.argtypes = [vp, vp, C.c_size_t, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.jpegb200_set_decode_sequential.argtypes = [vp, C.c_int]
+    L.jpegb200_debug_decode_stats.argtypes = [vp, u32p]
     L.jpegb200_set_dims.argtypes = [C.c_int, C.c_int]
     L.jpegb200_set_dims.restype = None
     L.rgb_to_dct.argtypes = [u8p, i16p, i16p, i16p, Area]
@@ -316,6 +318,14 @@ class Encoder:
                          d_status: int = 0, stream: int = 0):
         self._check(self.lib.jpegb200_decode_batch(self.ctx, d_streams, slot, d_sizes, n, w, h, d_bgr or None, frame_stride, d_planes or None, d_status or None,
                                                    stream or None))
+
+    def set_decode_sequential(self, on: bool):
+        self._check(self.lib.jpegb200_set_decode_sequential(self.ctx, int(on)))
+
+    def decode_stats(self) -> dict:
+        st = (C.c_uint32 * 8)()
+        self._check(self.lib.jpegb200_debug_decode_stats(self.ctx, st))
+        return dict(scans=st[0], fallback=st[1], changed_per_pass=list(st[2:8]))
 
     def decode_streams(self, jpgs: list, w: int, h: int, planes: bool = False):
         """jpgs: byte strings of w x h streams.  Returns (bgr (N,h,w,3) uint8, status (N,) int32[, planes (N, w*h*3/2) int16])."""

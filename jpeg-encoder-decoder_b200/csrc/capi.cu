@@ -194,6 +194,9 @@ struct jpegb200_ctx {
   PinBuf cmp_host;
   // decoding side: per-stream descriptors, scratch planes / absolute DCs / samples, staging of the host variant
   DevBuf dec_frames, dec_planes, dec_dcabs, dec_samples, dec_in, dec_sizes, dec_out, dec_planes_out, dec_scratch;
+  int dec_sequential = 0;     // 1: the warp-per-scan decoder for every scan (jpegb200_set_decode_sequential)
+  int dec_last_n = 0;         // streams of the last call that went through the sub-sequence decoder
+  void *dec_changed = nullptr, *dec_fallback = nullptr;
   bool have_saved = false;
   int saved_w = 0, saved_h = 0;
 };
@@ -616,9 +619,9 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
     d_planes = (int16_t*)c->dec_planes.p;
   }
   if (d_bgr && (e = c->dec_samples.ensure((size_t)n * (npix + npix / 2))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
-  // scratch of the sub-sequence decoder (JPEGB200_DEC_SEQUENTIAL=1: development switch, the warp-per-scan decoder for every scan)
-  static int sequential = -1;
-  if (sequential < 0) { const char* ev = getenv("JPEGB200_DEC_SEQUENTIAL"); sequential = ev ? atoi(ev) : 0; }
+  // scratch of the sub-sequence decoder
+  const int sequential = c->dec_sequential;
+  c->dec_last_n = 0;
   void* scratch[8] = {};
   if (!sequential) {
     size_t part[8], total = 0;
@@ -627,12 +630,40 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
     if ((e = c->dec_scratch.ensure(total)) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
     size_t off = 0;
     for (int i = 0; i < 8; i++) { scratch[i] = (uint8_t*)c->dec_scratch.p + off; off += part[i]; }
+    c->dec_last_n = n;
+    c->dec_changed = scratch[6];
+    c->dec_fallback = scratch[7];
   }
   jb_launch_decode(d_streams, slot, d_sizes, n, w, h, c->dec_frames.p, d_planes, (int16_t*)c->dec_dcabs.p, (uint8_t*)c->dec_samples.p, d_bgr, frame_stride, d_status,
                    sequential ? nullptr : scratch, st);
   c->launches += (d_bgr ? 4 : 2) + (sequential ? 0 : 5 + 6);
   if (d_status) c->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+int jpegb200_set_decode_sequential(jpegb200_ctx* c, int on) {
+  if (!c) return fail("null context");
+  c->dec_sequential = on ? 1 : 0;
+  return 0;
+}
+
+// stats[0] = scans of the last jpegb200_decode_batch call that went through the sub-sequence decoder, [1] = scans it left to the
+// warp-per-scan decoder, [2 + p] = scans in which synchronisation pass p + 1 still changed an exit state (p = 0 .. 5).  Synchronises.
+int jpegb200_debug_decode_stats(jpegb200_ctx* c, uint32_t* stats8) {
+  if (!c || !stats8) return fail("null argument");
+  for (int i = 0; i < 8; i++) stats8[i] = 0;
+  if (!c->dec_last_n) return 0;
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  const size_t scans = (size_t)3 * c->dec_last_n;
+  std::vector<uint32_t> ch(7 * scans), fb(scans);
+  CK(cudaMemcpy(ch.data(), c->dec_changed, ch.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(fb.data(), c->dec_fallback, fb.size() * 4, cudaMemcpyDeviceToHost));
+  stats8[0] = (uint32_t)scans;
+  for (size_t i = 0; i < scans; i++) stats8[1] += fb[i] ? 1u : 0u;
+  for (int p = 1; p <= 6; p++)
+    for (size_t i = 0; i < scans; i++) stats8[1 + p] += ch[(size_t)p * scans + i] ? 1u : 0u;
   return 0;
 }
 

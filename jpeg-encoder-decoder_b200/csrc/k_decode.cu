@@ -8,11 +8,13 @@
 //   k_dec_parse    one CTA per stream: thread 0 reads the marker segments up to the first scan (quantisers, the four
 //                  Huffman tables with an 8-bit look-ahead table each, SOF0 / SOS checks), all threads then look for the
 //                  markers that end the scans
-//   k_dec_scan     one WARP per scan: entropy decoding is a serial chain per scan (no restart intervals: every code's position
-//                  depends on all codes before it), so the lanes decode the 32 tokens that would start at the next 32 bit
-//                  positions and a warp-uniform walk follows the real chain through them.  Writes the planes block by block
-//                  (zig-zag order, DC still a difference: exactly the planes rgb_to_dct leaves, encoder.c:158-178) and the
-//                  absolute DC of every block
+//   k_dec_unstuff / k_dec_sub<0,1,2> / k_dec_base / k_dec_dcabs
+//                  entropy decoding in parallel inside a scan: sub-sequences of 1024 bits, one thread each, that synchronise
+//                  themselves; a pass without a change proves every start state (see the comment in front of them)
+//   k_dec_scan     the fallback for scans that do not settle (periodic streams: flat chroma), one WARP per scan: the lanes
+//                  decode the 32 tokens that would start at the next 32 bit positions, a warp-uniform walk follows the chain
+//                  Both write the planes rgb_to_dct leaves (zig-zag blocks, DC still a difference, encoder.c:158-178) and
+//                  the absolute DC of every block
 //   k_dec_idct     8 threads per block: de-quantise, separable inverse transform in FP64 in a fixed order, samples
 //   k_dec_colour   one thread per 4 x 2 pixels: chroma replicated 2 x 2, toRgb in FP64, B,G,R bytes
 #include "jpegb200_internal.cuh"

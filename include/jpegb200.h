@@ -89,7 +89,7 @@ int jpegb200_unpack(jpegb200_ctx *ctx, const uint8_t *d_src, int fmt, int n, int
  * Huffman tables; encoder.c:549-644) back to coefficient planes and B,G,R frames.  The reference has only stubs for this
  * direction (utils/func_tester.c:1261-1319); the arithmetic they fix (toRgb's constants, 2 x 2 replicated chroma, de-quantise
  * + inverse of the encoder's transform with its cosine table, DC = running sum) is what is computed, in FP64 in a fixed
- * order.  Entropy decoding is serial per scan; the batch supplies the parallelism (one thread per scan).
+ * order.  Entropy decoding runs in parallel inside every scan (self-synchronising sub-sequences).
  *   d_streams   stream i at d_streams + i*slot, d_sizes[i] bytes (the layout jpegb200_encode_batch leaves); d_streams and slot
  *               multiples of 16
  *   d_bgr       frame i at d_bgr + i*frame_stride (multiple of 4), rows w*3 bytes apart; NULL = planes only

@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_unstuff(const uint8_t* __
 // MODE 0: speculate from the sub-sequence's first bit; 1: decode again where the predecessor's exit state is news; 2: write.
 template <int MODE>
 __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, size_t slot, JbDecFrame* frames, JbDecScratch sc, uint32_t* changed /*3n, this pass*/,
-                                                    int16_t* __restrict__ planes) {
+                                                    int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
   __shared__ DecWarp tab;                              // (ring and blk unused here)
   __shared__ uint32_t rows[SUB_ROWS * (SUB_WORDS + 1)];  // the CTA's 129 sub-sequences, big-endian words, one word of padding per row
   __shared__ int s_work;
@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, 
   const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
   const size_t npix = (size_t)w * h;
   int16_t* plane = MODE == 2 ? planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4) : nullptr;
+  int16_t* dca = MODE == 2 ? dcabs + (size_t)f * (npix / 64 * 3 / 2) + (comp == 0 ? 0 : comp == 1 ? npix / 64 : npix / 64 + npix / 256) : nullptr;
   uint32_t pos = st & 0x3FFFFFFu, blk = MODE == 2 ? sc.base[sbase + i] : 0u, ends = 0, bad = 0;
   int k = (int)(st >> 26);
   while (pos < limit && (MODE != 2 || blk < nblocks)) {
@@ -458,7 +459,10 @@ __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, 
     int k2 = k + (int)((R >> 6) & 127u);
     if (R & 0x2000u) {
       if (k2 > 64) { if (MODE == 2) { bad = 1; break; } k2 = 64; }
-      if (MODE == 2) plane[(size_t)blk * 64 + (k2 - 1)] = (int16_t)((int)R >> 16);
+      if (MODE == 2) {
+        plane[(size_t)blk * 64 + (k2 - 1)] = (int16_t)((int)R >> 16);
+        if (k == 0) dca[blk] = (int16_t)((int)R >> 16);          // the DC difference, also in a compact array for k_dec_dcabs
+      }
     }
     pos += R & 63u;
     k = k2;
@@ -511,20 +515,20 @@ __global__ void __launch_bounds__(256) k_dec_base(int nframes, int w, int h, JbD
   }
 }
 
-// abs_dc: the running sum of the DC differences of a plane.
-__global__ void __launch_bounds__(256) k_dec_dcabs(int nframes, int w, int h, const JbDecFrame* __restrict__ frames, const int16_t* __restrict__ planes, int16_t* __restrict__ dcabs) {
+// abs_dc: the running sum of the DC differences of a plane, in place on the compact array k_dec_sub<2> filled (a zero
+// difference is never stored: the array is cleared before).  Scans of the warp-per-scan decoder already hold absolute values.
+__global__ void __launch_bounds__(256) k_dec_dcabs(int nframes, int w, int h, const JbDecFrame* __restrict__ frames, const uint32_t* __restrict__ fallback, int16_t* __restrict__ dcabs) {
   __shared__ int wsum[8], carry_s;
   const int t = blockIdx.x, comp = t / nframes, f = t - comp * nframes, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (frames[f].status) return;
+  if (frames[f].status || fallback[t]) return;
   const size_t npix = (size_t)w * h;
   const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
-  const int16_t* plane = planes + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4);
   int16_t* dca = dcabs + (size_t)f * (npix / 64 * 3 / 2) + (comp == 0 ? 0 : comp == 1 ? npix / 64 : npix / 64 + npix / 256);
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (uint32_t b0 = 0; b0 < nblocks; b0 += 256) {
     const uint32_t b = b0 + tid;
-    const int v = b < nblocks ? plane[(size_t)b * 64] : 0;
+    const int v = b < nblocks ? dca[b] : 0;
     int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -574,28 +578,49 @@ __global__ void __launch_bounds__(128) k_dec_idct(int w, int h, const JbDecFrame
       F[u] = (double)(c * (int)q[i * 8 + u]);
     }
   }
+  // Columns u in which no block of the warp has a coefficient, and rows v that are empty in all of them, are skipped: their
+  // terms are +-0.0 for every lane, and adding +-0.0 never changes a sum that started from +0.0 (r2: half of a 1024-stream
+  // call was this kernel; a block of photographic content has 5 of its 63 AC coefficients).
+  uint32_t nz = 0;
+#pragma unroll
+  for (int u = 0; u < 8; u++) nz |= (F[u] != 0.0 ? 1u : 0u) << u;
+  const uint32_t cols = __reduce_or_sync(0xFFFFFFFFu, nz);
+  const uint32_t rowb = __ballot_sync(0xFFFFFFFFu, nz != 0);
+  const uint32_t rows = (rowb | (rowb >> 8) | (rowb >> 16) | (rowb >> 24)) & 0xFFu;
   // t[v][x] = sum_u (F[v][u] c(u)) cos[x][u], u ascending from 0.0   (this thread: v = i)
+  {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int x = 0; x < 8; x++) {
-    double s = 0.0;
+    for (int u = 0; u < 8; u++) {
+      if (!((cols >> u) & 1u)) continue;                       // warp-uniform
+      const double fu = u == 0 ? __dmul_rn(F[0], JB_INV_SQRT2) : F[u];
 #pragma unroll
-    for (int u = 0; u < 8; u++) s = __dadd_rn(s, __dmul_rn(u == 0 ? __dmul_rn(F[0], JB_INV_SQRT2) : F[u], JB_COS(x, u)));
-    tb[g][i * 8 + x] = s;
+      for (int x = 0; x < 8; x++) acc[x] = __dadd_rn(acc[x], __dmul_rn(fu, JB_COS(x, u)));
+    }
+#pragma unroll
+    for (int x = 0; x < 8; x++) tb[g][i * 8 + x] = acc[x];
   }
   __syncthreads();
   if (!live) return;
   // s[y][x] = sum_v (t[v][x] c(v)) cos[y][v]   (this thread: y = i)
   uint32_t px[8];
-#pragma unroll
-  for (int x = 0; x < 8; x++) {
-    double s = 0.0;
+  {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int v = 0; v < 8; v++) {
-      const double tv = tb[g][v * 8 + x];
-      s = __dadd_rn(s, __dmul_rn(v == 0 ? __dmul_rn(tv, JB_INV_SQRT2) : tv, s_cos[i * 8 + v]));
+      if (!((rows >> v) & 1u)) continue;                       // warp-uniform
+      const double cv = s_cos[i * 8 + v];
+#pragma unroll
+      for (int x = 0; x < 8; x++) {
+        const double tv = tb[g][v * 8 + x];
+        acc[x] = __dadd_rn(acc[x], __dmul_rn(v == 0 ? __dmul_rn(tv, JB_INV_SQRT2) : tv, cv));
+      }
     }
-    const double p = floor(__dadd_rn(__dadd_rn(__dmul_rn(s, 0.25), 128.0), 0.5));
-    px[x] = (uint32_t)(p < 0.0 ? 0.0 : p > 255.0 ? 255.0 : p);
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      const double p = floor(__dadd_rn(__dadd_rn(__dmul_rn(acc[x], 0.25), 128.0), 0.5));
+      px[x] = (uint32_t)(p < 0.0 ? 0.0 : p > 255.0 ? 255.0 : p);
+    }
   }
   const int pw = comp ? w / 2 : w, bw = pw / 8;
   uint8_t* dst = samples + (size_t)f * (npix + npix / 2) + (comp == 0 ? 0 : comp == 1 ? npix : npix + npix / 4) + (size_t)((b / bw) * 8 + i) * pw + (b % bw) * 8;
@@ -674,14 +699,15 @@ void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_s
     sc.subs_per_frame = (uint32_t)((slot + 128) / 128 + 8);
     cudaMemsetAsync(sc.changed, 0, (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4, st);
     cudaMemsetAsync(d_planes, 0, (size_t)n * (npix + npix / 2) * sizeof(int16_t), st);
+    cudaMemsetAsync(d_dcabs, 0, (size_t)n * (npix / 64 * 3 / 2) * sizeof(int16_t), st);
     k_dec_unstuff<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, fr, sc);
     const dim3 grid((unsigned)((sc.subs_per_frame + SUB_CTA - 1) / SUB_CTA), (unsigned)(3 * n));
-    k_dec_sub<0><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed, nullptr);
-    for (int p = 1; p <= DEC_SYNC_PASSES; p++) k_dec_sub<1><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed + (size_t)p * 3 * n, nullptr);
+    k_dec_sub<0><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed, nullptr, nullptr);
+    for (int p = 1; p <= DEC_SYNC_PASSES; p++) k_dec_sub<1><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed + (size_t)p * 3 * n, nullptr, nullptr);
     k_dec_base<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc, sc.changed + (size_t)DEC_SYNC_PASSES * 3 * n);
-    k_dec_sub<2><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, nullptr, d_planes);
+    k_dec_sub<2><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, nullptr, d_planes, d_dcabs);
     k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs, sc.fallback);
-    k_dec_dcabs<<<3 * n, 256, 0, st>>>(n, w, h, fr, d_planes, d_dcabs);
+    k_dec_dcabs<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc.fallback, d_dcabs);
   } else {
     k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs, nullptr);
   }

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
 // ---- entropy decoding in parallel INSIDE a scan: sub-sequences that synchronise themselves ---------------------------------
 // (Klein & Wiseman's observation that Huffman decoders started at a wrong bit re-synchronise after a few codes; used for JPEG
 // on GPUs by Weissenberger & Schmidt.)  A scan's clean stream is cut into sub-sequences of 1024 bits, one THREAD each:
-//   k_dec_unstuff   one warp per scan: the scan's bytes without the stuffed zeros, at an aligned place of its own
+//   k_dec_unstuff   one CTA per scan: the scan's bytes without the stuffed zeros, at an aligned place of its own
 //   k_dec_sub<0>    every thread decodes from the first bit of its sub-sequence as if a token started there (inside a block,
 //                   not at a DC) and records where the first token behind its sub-sequence starts and at which position of a
 //                   block: its EXIT STATE.  Thread 0 of a scan starts from the truth.
@@ -345,52 +345,70 @@ struct JbDecScratch {          // all device pointers; S, used, ends, base: n * 
 __device__ __forceinline__ uint32_t dec_clean_off(const JbDecFrame& fr, int comp) { return ((fr.scan_start[comp] + 15u) & ~15u) + 16u * (uint32_t)comp; }
 __device__ __forceinline__ uint32_t dec_sub_off(const JbDecFrame& fr, int comp) { return dec_clean_off(fr, comp) / 128u + 2u * (uint32_t)comp; }
 
-__global__ void __launch_bounds__(DS_WARPS * 32) k_dec_unstuff(const uint8_t* __restrict__ streams, size_t slot, int nframes, const JbDecFrame* __restrict__ frames, JbDecScratch sc) {
+// One CTA of 256 threads per scan, 1024 raw bytes per trip (one word per thread), the next trip's word already in flight.
+__global__ void __launch_bounds__(256) k_dec_unstuff(const uint8_t* __restrict__ streams, size_t slot, int nframes, const JbDecFrame* __restrict__ frames, JbDecScratch sc) {
   constexpr uint32_t FULL = 0xFFFFFFFFu;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * DS_WARPS + warp;
-  if (t >= 3 * nframes) return;
+  __shared__ uint32_t wsum[2][8], s_last[2];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int comp = t / nframes, f = t - comp * nframes;
   const JbDecFrame& fr = frames[f];
-  if (fr.status) { if (lane == 0) sc.cbits[t] = 0; return; }
+  if (fr.status) { if (tid == 0) sc.cbits[t] = 0; return; }
   const uint8_t* stream = streams + (size_t)f * slot;
   const uintptr_t a0 = (uintptr_t)(stream + fr.scan_start[comp]);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)15);
   const uint32_t start = (uint32_t)(a0 & 15), stop = start + (fr.scan_end[comp] - fr.scan_start[comp]);
   uint8_t* out = sc.clean + (size_t)f * (slot + 128) + dec_clean_off(fr, comp);
   uint32_t produced = 0, prev_byte = 0;
-  for (uint32_t rword = 0; rword * 4u < stop; rword += 32) {
-    const uint32_t p0 = (rword + lane) * 4u;
-    const uint32_t wv = p0 < stop ? __ldg(base + rword + lane) : 0u;           // (a word that starts inside the scan lies inside the slot)
+  uint32_t wnext = (uint32_t)tid * 4u < stop ? __ldg(base + tid) : 0u;           // (a word that starts inside the scan lies inside the slot)
+  for (uint32_t rword = 0, trip = 0; rword * 4u < stop; rword += 256, trip++) {
+    const uint32_t p0 = (rword + tid) * 4u;
+    const uint32_t wv = wnext;
+    wnext = (rword + 256 + tid) * 4u < stop ? __ldg(base + rword + 256 + tid) : 0u;
     uint32_t by[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) by[j] = (wv >> (8 * j)) & 0xFFu;
+    if (tid == 255) s_last[trip & 1] = by[3];
     uint32_t before = __shfl_up_sync(FULL, by[3], 1);
-    if (lane == 0) before = prev_byte;
     uint32_t keep = 0;
+    // (the byte in front of a warp's first word comes from the previous warp: resolved after the barrier)
+    uint32_t inc;
+    {
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t pr = j ? by[j - 1] : before;
-      const bool inside = p0 + j >= start && p0 + j < stop;
-      keep |= (inside && !(by[j] == 0x00u && pr == 0xFFu) ? 1u : 0u) << j;      // 0xFF 0x00 -> 0xFF (encoder.c:405-408)
+      for (int j = 1; j < 4; j++) {
+        const bool inside = p0 + j >= start && p0 + j < stop;
+        keep |= (inside && !(by[j] == 0x00u && by[j - 1] == 0xFFu) ? 1u : 0u) << j;     // 0xFF 0x00 -> 0xFF (encoder.c:405-408)
+      }
+      // byte 0 needs the byte before the word
+      const uint32_t lastw = __shfl_sync(FULL, by[3], 31);
+      __shared__ uint32_t s_wlast[2][8];
+      if (lane == 0) s_wlast[trip & 1][warp] = lastw;
+      __syncthreads();
+      if (lane == 0) before = warp ? s_wlast[trip & 1][warp - 1] : prev_byte;
+      const bool inside0 = p0 >= start && p0 < stop;
+      keep |= (inside0 && !(by[0] == 0x00u && before == 0xFFu) ? 1u : 0u);
+      const uint32_t cnt = (uint32_t)__popc(keep);
+      inc = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (lane == 31) wsum[trip & 1][warp] = inc;
+      __syncthreads();
+      uint32_t wex = 0, tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) { wex += q < warp ? wsum[trip & 1][q] : 0u; tot += wsum[trip & 1][q]; }
+      uint32_t dst = produced + wex + inc - cnt;
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if ((keep >> j) & 1u) out[dst++] = (uint8_t)by[j];
+      produced += tot;
+      prev_byte = s_last[trip & 1];
     }
-    const uint32_t cnt = (uint32_t)__popc(keep);
-    uint32_t inc = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t n = __shfl_up_sync(FULL, inc, o);
-      if (lane >= o) inc += n;
-    }
-    uint32_t dst = produced + inc - cnt;
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-      if ((keep >> j) & 1u) out[dst++] = (uint8_t)by[j];
-    produced += __shfl_sync(FULL, inc, 31);
-    prev_byte = __shfl_sync(FULL, by[3], 31);
   }
   // the stream continues with 1-bits (fill_last_byte never stuffs its pad byte, encoder.c:425-432): pad to a 16-byte boundary + 16
-  for (uint32_t k = produced + lane; k < ((produced + 15u) & ~15u) + 16u; k += 32) out[k] = 0xFF;
-  if (lane == 0) sc.cbits[t] = produced * 8u;
+  for (uint32_t k = produced + tid; k < ((produced + 15u) & ~15u) + 16u; k += 256) out[k] = 0xFF;
+  if (tid == 0) sc.cbits[t] = produced * 8u;
 }
 
 // MODE 0: speculate from the sub-sequence's first bit; 1: decode again where the predecessor's exit state is news; 2: write.
@@ -700,7 +718,7 @@ void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_s
     cudaMemsetAsync(sc.changed, 0, (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4, st);
     cudaMemsetAsync(d_planes, 0, (size_t)n * (npix + npix / 2) * sizeof(int16_t), st);
     cudaMemsetAsync(d_dcabs, 0, (size_t)n * (npix / 64 * 3 / 2) * sizeof(int16_t), st);
-    k_dec_unstuff<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, fr, sc);
+    k_dec_unstuff<<<3 * n, 256, 0, st>>>(d_streams, slot, n, fr, sc);
     const dim3 grid((unsigned)((sc.subs_per_frame + SUB_CTA - 1) / SUB_CTA), (unsigned)(3 * n));
     k_dec_sub<0><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed, nullptr, nullptr);
     for (int p = 1; p <= DEC_SYNC_PASSES; p++) k_dec_sub<1><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed + (size_t)p * 3 * n, nullptr, nullptr);

@@ -102,7 +102,7 @@ int jpegb200_decode_batch(jpegb200_ctx *ctx, const uint8_t *d_streams, size_t sl
                           uint8_t *d_bgr, size_t frame_stride, int16_t *d_planes, int32_t *d_status, void *stream);
 /* Entropy decoding runs in parallel inside a scan (sub-sequences of 1024 bits that synchronise themselves, proven by a pass
  * without changes) and falls back to one warp per scan where that does not settle; on = 1 forces the warp-per-scan decoder
- * everywhere (tests compare the two). */
+ * everywhere, on = 2 runs the sub-sequence decoder but treats every scan as not settled (tests compare all three). */
 int jpegb200_set_decode_sequential(jpegb200_ctx *ctx, int on);
 /* Test hook (synchronises): stats8[0] scans of the last decode call that went through the sub-sequence decoder, [1] scans it
  * left to the warp-per-scan decoder, [2..7] scans in which synchronisation pass 1..6 still changed a state. */

@@ -319,7 +319,8 @@ class Encoder:
         self._check(self.lib.jpegb200_decode_batch(self.ctx, d_streams, slot, d_sizes, n, w, h, d_bgr or None, frame_stride, d_planes or None, d_status or None,
                                                    stream or None))
 
-    def set_decode_sequential(self, on: bool):
+    def set_decode_sequential(self, on):
+        """False / 0: sub-sequence decoder with fallback; True / 1: warp-per-scan decoder; 2: sub-sequence decoder, every scan through the fallback."""
         self._check(self.lib.jpegb200_set_decode_sequential(self.ctx, int(on)))
 
     def decode_stats(self) -> dict:

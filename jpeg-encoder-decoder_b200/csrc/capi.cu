@@ -194,7 +194,7 @@ struct jpegb200_ctx {
   PinBuf cmp_host;
   // decoding side: per-stream descriptors, scratch planes / absolute DCs / samples, staging of the host variant
   DevBuf dec_frames, dec_planes, dec_dcabs, dec_samples, dec_in, dec_sizes, dec_out, dec_planes_out, dec_scratch;
-  int dec_sequential = 0;     // 1: the warp-per-scan decoder for every scan (jpegb200_set_decode_sequential)
+  int dec_sequential = 0;     // 1: the warp-per-scan decoder for every scan, 2: through the fallback of the sub-sequence decoder (jpegb200_set_decode_sequential)
   int dec_last_n = 0;         // streams of the last call that went through the sub-sequence decoder
   void *dec_changed = nullptr, *dec_fallback = nullptr;
   bool have_saved = false;
@@ -620,7 +620,7 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
   }
   if (d_bgr && (e = c->dec_samples.ensure((size_t)n * (npix + npix / 2))) != cudaSuccess) return fail("cudaMalloc: %s", cudaGetErrorString(e));
   // scratch of the sub-sequence decoder
-  const int sequential = c->dec_sequential;
+  const int sequential = c->dec_sequential == 1;
   c->dec_last_n = 0;
   void* scratch[8] = {};
   if (!sequential) {
@@ -635,7 +635,7 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
     c->dec_fallback = scratch[7];
   }
   jb_launch_decode(d_streams, slot, d_sizes, n, w, h, c->dec_frames.p, d_planes, (int16_t*)c->dec_dcabs.p, (uint8_t*)c->dec_samples.p, d_bgr, frame_stride, d_status,
-                   sequential ? nullptr : scratch, st);
+                   sequential ? nullptr : scratch, c->dec_sequential == 2, st);
   c->launches += (d_bgr ? 4 : 2) + (sequential ? 0 : 5 + 6);
   if (d_status) c->launches++;
   CK(cudaGetLastError());
@@ -644,7 +644,7 @@ int jpegb200_decode_batch(jpegb200_ctx* c, const uint8_t* d_streams, size_t slot
 
 int jpegb200_set_decode_sequential(jpegb200_ctx* c, int on) {
   if (!c) return fail("null context");
-  c->dec_sequential = on ? 1 : 0;
+  c->dec_sequential = on == 2 ? 2 : (on ? 1 : 0);
   return 0;
 }
 

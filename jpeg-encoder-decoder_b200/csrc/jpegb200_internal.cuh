@@ -211,7 +211,7 @@ void jb_launch_pack_tchunks(const JbWs& ws, int njobs, uint32_t max_tchunks, cud
 size_t jb_dec_frame_bytes();
 void jb_dec_scratch_bytes(size_t slot, int n, size_t out[8]);
 void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_sizes, int n, int w, int h, void* d_frames, int16_t* d_planes, int16_t* d_dcabs,
-                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, void* const scratch[8], cudaStream_t st);
+                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, void* const scratch[8], int give_up, cudaStream_t st);
 
 // input formats (k_formats.cu): fmt 1 = RGB565, 2 = GRAYSCALE -> B,G,R
 bool jb_launch_unpack(const uint8_t* d_src, int fmt, size_t npix, uint8_t* d_bgr, cudaStream_t st);

@@ -17,6 +17,8 @@
 //                  the absolute DC of every block
 //   k_dec_idct     8 threads per block: de-quantise, separable inverse transform in FP64 in a fixed order, samples
 //   k_dec_colour   one thread per 4 x 2 pixels: chroma replicated 2 x 2, toRgb in FP64, B,G,R bytes
+#include <cstdio>
+
 #include "jpegb200_internal.cuh"
 #include "tables.cuh"
 
@@ -319,9 +321,11 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
 // (Klein & Wiseman's observation that Huffman decoders started at a wrong bit re-synchronise after a few codes; used for JPEG
 // on GPUs by Weissenberger & Schmidt.)  A scan's clean stream is cut into sub-sequences of 1024 bits, one THREAD each:
 //   k_dec_unstuff   one CTA per scan: the scan's bytes without the stuffed zeros, at an aligned place of its own
-//   k_dec_sub<0>    every thread decodes from the first bit of its sub-sequence as if a token started there (inside a block,
-//                   not at a DC) and records where the first token behind its sub-sequence starts and at which position of a
-//                   block: its EXIT STATE.  Thread 0 of a scan starts from the truth.
+//   k_dec_sub<0>    every thread decodes from the first bit of its sub-sequence as if a BLOCK started there and records where the
+//                   first token behind its sub-sequence starts and at which position of a block: its EXIT STATE.  Thread 0 of a
+//                   scan starts from the truth.  (Guessing "inside a block" instead never settles on the flat chroma of grey
+//                   frames: their scan is the periodic stream "DC 0, EOB" of two one-bit codes, every even bit is a block
+//                   start, and a decoder that starts out of phase with it stays out of phase.)
 //   k_dec_sub<1>    every thread whose predecessor's exit state differs from the start state it used decodes again from that
 //                   state.  Truth spreads from thread 0 at least one sub-sequence per pass, in practice everywhere after one
 //                   or two: a wrong start re-synchronises within a block or two (35 bits each), so most exit states are right
@@ -335,14 +339,17 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_dec_scan(const uint8_t* __res
 constexpr int SUB_BITS = 1024, SUB_WORDS = SUB_BITS / 32, SUB_CTA = 128, SUB_ROWS = SUB_CTA + 1;
 
 struct JbDecScratch {          // all device pointers; S, used, ends, base: n * subs_per_frame entries
-  uint8_t* clean;              // n x (slot + 128) bytes
+  uint8_t* clean;              // n x (slot + 192) bytes
   uint32_t* cbits;             // 3 n: clean bits per scan (scan t = comp * n + frame)
   uint32_t *S, *used, *ends, *base;
   uint32_t* changed;           // (passes + 1) x 3 n
   uint32_t* fallback;          // 3 n
   uint32_t subs_per_frame;
 };
-__device__ __forceinline__ uint32_t dec_clean_off(const JbDecFrame& fr, int comp) { return ((fr.scan_start[comp] + 15u) & ~15u) + 16u * (uint32_t)comp; }
+// Where a scan's clean stream lives inside its frame's part of sc.clean: 48 bytes further on per scan, so that the up to 31 bytes
+// of 1-bit padding behind one scan's clean stream end before the next scan's begins (16 bytes per scan were too few: the padding
+// of a flat Cb scan overwrote the first bytes of its Cr scan, 64 blocks of which then decoded as garbage).
+__device__ __forceinline__ uint32_t dec_clean_off(const JbDecFrame& fr, int comp) { return ((fr.scan_start[comp] + 15u) & ~15u) + 48u * (uint32_t)comp; }
 __device__ __forceinline__ uint32_t dec_sub_off(const JbDecFrame& fr, int comp) { return dec_clean_off(fr, comp) / 128u + 2u * (uint32_t)comp; }
 
 // One CTA of 256 threads per scan, 1024 raw bytes per trip (one word per thread), the next trip's word already in flight.
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(256) k_dec_unstuff(const uint8_t* __restrict__
   const uintptr_t a0 = (uintptr_t)(stream + fr.scan_start[comp]);
   const uint32_t* base = reinterpret_cast<const uint32_t*>(a0 & ~(uintptr_t)15);
   const uint32_t start = (uint32_t)(a0 & 15), stop = start + (fr.scan_end[comp] - fr.scan_start[comp]);
-  uint8_t* out = sc.clean + (size_t)f * (slot + 128) + dec_clean_off(fr, comp);
+  uint8_t* out = sc.clean + (size_t)f * (slot + 192) + dec_clean_off(fr, comp);
   uint32_t produced = 0, prev_byte = 0;
   uint32_t wnext = (uint32_t)tid * 4u < stop ? __ldg(base + tid) : 0u;           // (a word that starts inside the scan lies inside the slot)
   for (uint32_t rword = 0, trip = 0; rword * 4u < stop; rword += 256, trip++) {
@@ -432,7 +439,7 @@ __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, 
   uint32_t st = 0;
   bool work = i < nsub;
   if (work) {
-    if (MODE == 0) st = i ? (i * SUB_BITS) | (1u << 26) : 0u;
+    if (MODE == 0) st = i * SUB_BITS;                  // guess: a block starts here (exact for thread 0)
     else st = i ? S[i - 1] : 0u;
     if (MODE == 1) work = st != used[i];
   }
@@ -448,7 +455,7 @@ __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, 
     const JbDecTab& ac = fr.tab[1][fr.ta[comp]];
     for (int q = tid; q < 256; q += SUB_CTA) { tab.look[0][q] = dc.look[q]; tab.look[1][q] = ac.look[q]; tab.val[0][q] = dc.val[q]; tab.val[1][q] = ac.val[q]; }
     if (tid < 8) { tab.limit[0][tid] = dc.limit16[9 + tid]; tab.limit[1][tid] = ac.limit16[9 + tid]; tab.off[0][tid] = dc.valoff[9 + tid]; tab.off[1][tid] = ac.valoff[9 + tid]; }
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.clean + (size_t)f * (slot + 128) + dec_clean_off(fr, comp)) + (size_t)i0 * SUB_WORDS;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sc.clean + (size_t)f * (slot + 192) + dec_clean_off(fr, comp)) + (size_t)i0 * SUB_WORDS;
     const uint32_t nwords = (total_bits + 31) / 32 + 4;                                // the padding behind the stream is valid memory
     for (uint32_t q = tid; q < SUB_ROWS * SUB_WORDS; q += SUB_CTA) {
       const uint32_t wv = i0 * SUB_WORDS + q < nwords ? __ldg(src + q) : 0xFFFFFFFFu;
@@ -500,7 +507,7 @@ __global__ void __launch_bounds__(SUB_CTA) k_dec_sub(int nframes, int w, int h, 
 }
 
 // Per scan: the block every sub-sequence starts in; give up on scans that did not settle or do not add up.
-__global__ void __launch_bounds__(256) k_dec_base(int nframes, int w, int h, JbDecFrame* frames, JbDecScratch sc, const uint32_t* __restrict__ changed_last) {
+__global__ void __launch_bounds__(256) k_dec_base(int nframes, int w, int h, JbDecFrame* frames, JbDecScratch sc, const uint32_t* __restrict__ changed_last, int give_up) {
   __shared__ uint32_t wsum[8], carry_s;
   const int t = blockIdx.x, comp = t / nframes, f = t - comp * nframes, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const JbDecFrame& fr = frames[f];
@@ -529,7 +536,7 @@ __global__ void __launch_bounds__(256) k_dec_base(int nframes, int w, int h, JbD
   }
   if (tid == 0) {
     const uint32_t nblocks = (uint32_t)((w / 8) * (h / 8) / (comp ? 4 : 1));
-    sc.fallback[t] = (changed_last[t] != 0 || carry_s < nblocks) ? 1u : 0u;    // (more block ends than blocks: bits behind the last block)
+    sc.fallback[t] = (give_up || changed_last[t] != 0 || carry_s < nblocks) ? 1u : 0u;    // (more block ends than blocks: bits behind the last block)
   }
 }
 
@@ -693,8 +700,8 @@ size_t jb_dec_frame_bytes() { return sizeof(JbDecFrame); }
 constexpr int DEC_SYNC_PASSES = 6;
 // Scratch of the sub-sequence decoder for n streams in slots of `slot` bytes: bytes of each part (clean, cbits, S, used, ends, base, changed, fallback).
 void jb_dec_scratch_bytes(size_t slot, int n, size_t out[8]) {
-  const size_t subs = (slot + 128) / 128 + 8;
-  out[0] = (size_t)n * (slot + 128);
+  const size_t subs = (slot + 192) / 128 + 8;
+  out[0] = (size_t)n * (slot + 192);
   out[1] = (size_t)3 * n * 4;
   out[2] = out[3] = out[4] = out[5] = (size_t)n * subs * 4;
   out[6] = (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4;
@@ -703,9 +710,9 @@ void jb_dec_scratch_bytes(size_t slot, int n, size_t out[8]) {
 
 // d_frames: n x jb_dec_frame_bytes(); d_planes: n x (w*h*3/2) int16; d_dcabs: n x (w*h/64*3/2) int16;
 // d_samples: n x (w*h*3/2) bytes; d_bgr may be null (planes only); d_status may be null; scratch: the eight parts above in one
-// 256-byte aligned allocation each (null: warp-per-scan decoder only).
+// 256-byte aligned allocation each (null: warp-per-scan decoder only); give_up: test switch, every scan is treated as not settled.
 void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_sizes, int n, int w, int h, void* d_frames, int16_t* d_planes, int16_t* d_dcabs,
-                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, void* const scratch[8], cudaStream_t st) {
+                      uint8_t* d_samples, uint8_t* d_bgr, size_t frame_stride, int32_t* d_status, void* const scratch[8], int give_up, cudaStream_t st) {
   JbDecFrame* fr = reinterpret_cast<JbDecFrame*>(d_frames);
   const size_t npix = (size_t)w * h;
   k_dec_parse<<<n, 256, 0, st>>>(d_streams, slot, d_sizes, w, h, fr);
@@ -714,7 +721,7 @@ void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_s
     JbDecScratch sc;
     sc.clean = (uint8_t*)scratch[0]; sc.cbits = (uint32_t*)scratch[1]; sc.S = (uint32_t*)scratch[2]; sc.used = (uint32_t*)scratch[3];
     sc.ends = (uint32_t*)scratch[4]; sc.base = (uint32_t*)scratch[5]; sc.changed = (uint32_t*)scratch[6]; sc.fallback = (uint32_t*)scratch[7];
-    sc.subs_per_frame = (uint32_t)((slot + 128) / 128 + 8);
+    sc.subs_per_frame = (uint32_t)((slot + 192) / 128 + 8);
     cudaMemsetAsync(sc.changed, 0, (size_t)(DEC_SYNC_PASSES + 1) * 3 * n * 4, st);
     cudaMemsetAsync(d_planes, 0, (size_t)n * (npix + npix / 2) * sizeof(int16_t), st);
     cudaMemsetAsync(d_dcabs, 0, (size_t)n * (npix / 64 * 3 / 2) * sizeof(int16_t), st);
@@ -722,7 +729,7 @@ void jb_launch_decode(const uint8_t* d_streams, size_t slot, const uint32_t* d_s
     const dim3 grid((unsigned)((sc.subs_per_frame + SUB_CTA - 1) / SUB_CTA), (unsigned)(3 * n));
     k_dec_sub<0><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed, nullptr, nullptr);
     for (int p = 1; p <= DEC_SYNC_PASSES; p++) k_dec_sub<1><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, sc.changed + (size_t)p * 3 * n, nullptr, nullptr);
-    k_dec_base<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc, sc.changed + (size_t)DEC_SYNC_PASSES * 3 * n);
+    k_dec_base<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc, sc.changed + (size_t)DEC_SYNC_PASSES * 3 * n, give_up);
     k_dec_sub<2><<<grid, SUB_CTA, 0, st>>>(n, w, h, slot, fr, sc, nullptr, d_planes, d_dcabs);
     k_dec_scan<<<(3 * n + DS_WARPS - 1) / DS_WARPS, DS_WARPS * 32, 0, st>>>(d_streams, slot, n, w, h, fr, d_planes, d_dcabs, sc.fallback);
     k_dec_dcabs<<<3 * n, 256, 0, st>>>(n, w, h, fr, sc.fallback, d_dcabs);

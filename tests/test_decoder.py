@@ -217,6 +217,32 @@ def test_gpu_decoder_reports_bad_streams_without_stopping_the_batch(enc, oracle,
 
 
 @pytest.mark.gpu
+def test_gpu_decoder_survives_garbage_scans(enc, oracle, frames):
+    """Valid headers and markers, random bytes inside the scans: every decoder mode must come back (a status or garbage
+    pixels, never a fault) and the good streams of the same batch must be untouched."""
+    rng = np.random.default_rng(33)
+    good = oracle.encode(frames.sample_bgr("640"))["jpg"].tobytes()
+    want = oracle.decode(good, 640, 640)["bgr"]
+    sos = [i for i in range(len(good) - 1) if good[i] == 0xFF and good[i + 1] == 0xDA]
+    assert len(sos) == 3
+    bad = []
+    for k in range(6):
+        b = bytearray(good)
+        lo, hi = sos[k % 3] + 10, (sos[k % 3 + 1] if k % 3 < 2 else len(good) - 2)
+        junk = rng.integers(0, 255, hi - lo, dtype=np.uint8)            # never 0xFF: the markers stay where they are
+        if k >= 3:
+            junk[:] = (0x00, 0x55, 0xAA)[k - 3]                          # periodic junk
+        b[lo:hi] = junk.tobytes()
+        bad.append(bytes(b))
+    for mode in (0, 2, 1):
+        enc.set_decode_sequential(mode)
+        bgr, status = enc.decode_streams([good] + bad + [good], 640, 640)
+        assert status[0] == 0 and status[-1] == 0, (mode, status)
+        assert np.array_equal(bgr[0], want) and np.array_equal(bgr[-1], want), mode
+    enc.set_decode_sequential(0)
+
+
+@pytest.mark.gpu
 def test_encode_decode_round_trip_on_the_device_full_size(enc, frames):
     """64 frames of 1920 x 1280 stay on the device: encode (token path) -> decode; the decoder's planes must be the planes
     the plane path of the encoder materialises for the same frames, and the pixels must be close to the input."""

@@ -157,7 +157,12 @@ __device__ __forceinline__ void scan_tchunks(const JbWs& ws, uint32_t jobid, con
 #endif
 constexpr int CP_BATCH = JB_CP_BATCH;      // runs per batch
 constexpr int CP_STEP = JB_CP_STEP;        // 32-token slices whose loads are in flight together
-__global__ void __launch_bounds__(PR_WARPS * 32) k_compact_tokens(JbWs ws) {
+// CTAs per SM the register allocation must allow (r2: 1 (46 registers) 255, 5: 261, 6: 262, 7: 250 Gpix/s together with the same
+// setting for k_pack_tchunks; more resident warps hide the token loads, until the registers spill)
+#ifndef JB_COMPACT_MIN_CTAS
+#define JB_COMPACT_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(PR_WARPS * 32, JB_COMPACT_MIN_CTAS) k_compact_tokens(JbWs ws) {
   __shared__ uint32_t enc[2][512];
   const JbJob job = ws.jobs[blockIdx.y];
   const uint32_t nrc = jb_runs_chroma(job.w, job.h);
@@ -338,7 +343,10 @@ __device__ __forceinline__ void concat_store_z4(uint32_t* stage, const uint32_t 
   }
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32) k_pack_tchunks(JbWs ws) {
+#ifndef JB_PACK_MIN_CTAS
+#define JB_PACK_MIN_CTAS 6
+#endif
+__global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunks(JbWs ws) {
   __shared__ uint32_t stage_all[PR_WARPS][PR_STAGE_WORDS];
   const JbJob job = ws.jobs[blockIdx.y];
   const JbJobState* st = ws.state + blockIdx.y;

@@ -10,6 +10,9 @@
 
 namespace {
 
+#ifndef JB_F32X2
+#define JB_F32X2 1        // packed FP32 (FADD2 / FMUL2 / FFMA2) in the AAN butterflies and the colour divisions; 0 = scalar (r1 / r2 code)
+#endif
 constexpr int TR_STRIDE = 72;            // doubles per block in the transpose buffer (64 + 8 pad)
 
 __device__ __forceinline__ double u8_to_double(uint32_t v) {       // exact (double)v for 0 <= v < 2^32
@@ -259,6 +262,23 @@ __device__ __forceinline__ void ycc_row8n(const uint32_t (&w)[6], uint32_t (&yb)
     numer4<114, 587, 299, NF_BASE_Y>(w[3 * h], w[3 * h + 1], w[3 * h + 2], ny);
     numer4<15625, -10352, -5273, NF_BASE_C>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nb);
     numer4<-2541, -13084, 15625, NF_BASE_C>(w[3 * h], w[3 * h + 1], w[3 * h + 2], nr);
+#if JB_F32X2
+    // two values per FFMA2.RZ (sm_100 packed FP32: the same IEEE result per half, half the issue slots)
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const float2 fy = __ffma2_rz(make_float2(__uint_as_float(ny[k]), __uint_as_float(ny[k + 1])), make_float2(INV1000_UP, INV1000_UP), make_float2(8380219.0f, 8380219.0f));
+      const float2 fb = __ffma2_rz(make_float2(__uint_as_float(nb[k]), __uint_as_float(nb[k + 1])), make_float2(INV31250_DN, INV31250_DN), make_float2(8388336.0f, 8388336.0f));
+      const float2 fr = __ffma2_rz(make_float2(__uint_as_float(nr[k]), __uint_as_float(nr[k + 1])), make_float2(INV31250_DN, INV31250_DN), make_float2(8388336.0f, 8388336.0f));
+      yb[4 * h + k] = __float_as_uint(fy.x); yb[4 * h + k + 1] = __float_as_uint(fy.y);
+      cbb[4 * h + k] = __float_as_uint(fb.x); cbb[4 * h + k + 1] = __float_as_uint(fb.y);
+      crb[4 * h + k] = __float_as_uint(fr.x); crb[4 * h + k + 1] = __float_as_uint(fr.y);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      scr_y = min(scr_y, ny[k] - yb[4 * h + k] * 1000u);
+      scr_c = max(scr_c, max(nb[k] - cbb[4 * h + k] * 31250u, nr[k] - crb[4 * h + k] * 31250u));
+    }
+#else
 #pragma unroll
     for (int k = 0; k < 4; k++) {
       yb[4 * h + k] = __float_as_uint(__fmaf_rz(__uint_as_float(ny[k]), INV1000_UP, 8380219.0f));
@@ -267,6 +287,7 @@ __device__ __forceinline__ void ycc_row8n(const uint32_t (&w)[6], uint32_t (&yb)
       scr_y = min(scr_y, ny[k] - yb[4 * h + k] * 1000u);
       scr_c = max(scr_c, max(nb[k] - cbb[4 * h + k] * 31250u, nr[k] - crb[4 * h + k] * 31250u));
     }
+#endif
   }
 }
 
@@ -290,6 +311,58 @@ __device__ __forceinline__ void aan8(float& d0, float& d1, float& d2, float& d3,
   d1 = __fadd_rn(z11, z4);
   d7 = __fsub_rn(z11, z4);
 }
+
+#if JB_F32X2
+// The same butterfly on sm_100's packed FP32 instructions (FADD2 / FMUL2 / FFMA2: two IEEE operations per issue slot; the kernel
+// is issue-bound with the FMA pipe a third busy).  Every operation below is the operation of aan8 on the same operands, so the
+// results are bit-identical.
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 f2fma(float2 a, float c, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }
+// two independent transforms, one in each half
+__device__ __forceinline__ void aan8x2(float2 (&d)[8]) {
+  using namespace jbfast;
+  const float2 t0 = f2add(d[0], d[7]), t7 = f2sub(d[0], d[7]), t1 = f2add(d[1], d[6]), t6 = f2sub(d[1], d[6]);
+  const float2 t2 = f2add(d[2], d[5]), t5 = f2sub(d[2], d[5]), t3 = f2add(d[3], d[4]), t4 = f2sub(d[3], d[4]);
+  const float2 t10 = f2add(t0, t3), t13 = f2sub(t0, t3), t11 = f2add(t1, t2), t12 = f2sub(t1, t2);
+  d[0] = f2add(t10, t11);
+  d[4] = f2sub(t10, t11);
+  const float2 s = f2add(t12, t13);
+  d[2] = f2fma(s, C707, t13);
+  d[6] = f2fma(s, -C707, t13);
+  const float2 a10 = f2add(t4, t5), a11 = f2add(t5, t6), a12 = f2add(t6, t7);
+  const float2 z5 = __fmul2_rn(f2sub(a10, a12), make_float2(C382, C382));
+  const float2 z2 = f2fma(a10, C541, z5), z4 = f2fma(a12, C1306, z5);
+  const float2 z11 = f2fma(a11, C707, t7), z13 = f2fma(a11, -C707, t7);
+  d[5] = f2add(z13, z2);
+  d[3] = f2sub(z13, z2);
+  d[1] = f2add(z11, z4);
+  d[7] = f2sub(z11, z4);
+}
+// one transform whose inputs arrive in pairs p0 = (d0, d1), p1 = (d7, d6), p2 = (d3, d2), p3 = (d4, d5) (the halves of the
+// row pass, which pairs the rows that way): the first two butterfly stages and the last one run packed, 22 issue slots for 30
+__device__ __forceinline__ void aan8_pairs(float2 p0, float2 p1, float2 p2, float2 p3, float& o0, float& o1, float& o2, float& o3, float& o4,
+                                           float& o5, float& o6, float& o7) {
+  using namespace jbfast;
+  const float2 e0 = f2add(p0, p1), od0 = f2sub(p0, p1);    // (t0, t1), (t7, t6)
+  const float2 e1 = f2add(p2, p3), od1 = f2sub(p2, p3);    // (t3, t2), (t4, t5)
+  const float2 g = f2add(e0, e1), h = f2sub(e0, e1);       // (t10, t11), (t13, t12)
+  o0 = __fadd_rn(g.x, g.y);
+  o4 = __fsub_rn(g.x, g.y);
+  const float s = __fadd_rn(h.y, h.x);
+  o2 = __fmaf_rn(s, C707, h.x);
+  o6 = __fmaf_rn(s, -C707, h.x);
+  const float a10 = __fadd_rn(od1.x, od1.y), a11 = __fadd_rn(od1.y, od0.y), a12 = __fadd_rn(od0.y, od0.x);
+  const float z5 = __fmul_rn(__fsub_rn(a10, a12), C382);
+  float2 zz, zo;
+  zz.x = __fmaf_rn(a10, C541, z5);       // z2
+  zz.y = __fmaf_rn(a12, C1306, z5);      // z4
+  zo.y = __fmaf_rn(a11, C707, od0.x);    // z11
+  zo.x = __fmaf_rn(a11, -C707, od0.x);   // z13
+  const float2 su = f2add(zo, zz), di = f2sub(zo, zz);
+  o5 = su.x; o1 = su.y; o3 = di.x; o7 = di.y;
+}
+#endif
 
 // Spread the low 16 bits of x to the even bit positions.
 __device__ __forceinline__ uint32_t spread16(uint32_t x) {
@@ -341,6 +414,31 @@ __device__ __forceinline__ void pack_all(const uint32_t (&q)[64], uint32_t (&out
 // be decided by the bracket: bit v of the result is set when natural row v (coefficients 8v..8v+7) holds one.
 __device__ __forceinline__ uint32_t block_fast_regs(const uint4 (&smp)[4], int comp, float magic, uint32_t (&out)[32], uint64_t* mask, int* dcq) {
   float d[64];
+#if JB_F32X2
+  {
+    // row pass, two rows per instruction: P[k][j] = column j of rows (0,1), (7,6), (3,2), (4,5) — the pairs aan8_pairs wants
+    float2 P[4][8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int src = k == 0 ? 0 : k == 1 ? 3 : k == 2 ? 1 : 2;       // smp[src] holds sample rows 2 src, 2 src + 1
+      const bool swap = k == 1 || k == 2;                            // .x = the odd row
+      const uint4 v = smp[src];
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const uint32_t sel = 0x7404u + 0x10u * (uint32_t)(j & 3);
+        const float ev = __uint_as_float(__byte_perm(w[j >> 2], 0x47000000u, sel));        // row 2 src
+        const float od = __uint_as_float(__byte_perm(w[2 + (j >> 2)], 0x47000000u, sel));  // row 2 src + 1
+        P[k][j] = swap ? make_float2(od, ev) : make_float2(ev, od);
+      }
+      aan8x2(P[k]);
+    }
+    // column pass: natural index 8 v + u
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      aan8_pairs(P[0][u], P[1][u], P[2][u], P[3][u], d[u], d[8 + u], d[16 + u], d[24 + u], d[32 + u], d[40 + u], d[48 + u], d[56 + u]);
+  }
+#else
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const uint4 v = smp[k];
@@ -357,6 +455,7 @@ __device__ __forceinline__ uint32_t block_fast_regs(const uint4 (&smp)[4], int c
   for (int y = 0; y < 8; y++) aan8(d[8 * y], d[8 * y + 1], d[8 * y + 2], d[8 * y + 3], d[8 * y + 4], d[8 * y + 5], d[8 * y + 6], d[8 * y + 7]);
 #pragma unroll
   for (int x = 0; x < 8; x++) aan8(d[x], d[8 + x], d[16 + x], d[24 + x], d[32 + x], d[40 + x], d[48 + x], d[56 + x]);
+#endif
   // DC through the literal chain (encoder.c:104-108): d[0] - 64*(2^15 + 128) is the exact integer sum of (sample - 128)
   {
     const double S = (double)__fadd_rn(d[0], -2105344.0f);

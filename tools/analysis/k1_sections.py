@@ -5,12 +5,13 @@ usage: k1_sections.py k1_src.csv k_tokens.o [tiles]      (line ranges below foll
 import collections, csv, glob, os, re, subprocess, sys, tempfile
 
 SECTIONS = [  # (label, file, first line, last line)
-    ("colour: numerators (IDP.2A)", "dct_core.cuh", 169, 190), ("colour: divisions, tie screens (ycc_row8n)", "dct_core.cuh", 191, 273),
+    ("colour: numerators (IDP.2A)", "dct_core.cuh", 172, 193), ("colour: divisions, tie screens (ycc_row8n)", "dct_core.cuh", 194, 293),
     ("colour: loads, packing, chroma sums, tie list", "k_tokens.cu", 188, 236), ("colour: tie replay", "k_tokens.cu", 97, 187),
-    ("colour: tie replay", "k_tokens.cu", 237, 267), ("colour: tie replay", "dct_core.cuh", 15, 54),
-    ("DCT: AAN butterflies", "dct_core.cuh", 274, 294), ("DCT: quantisation brackets", "dct_core.cuh", 295, 321),
-    ("DCT: zig-zag packing, mask", "dct_core.cuh", 322, 341), ("DCT: unpack, DC chain, block glue", "dct_core.cuh", 342, 400),
-    ("fetch (bulk copies, mbarrier)", "dct_core.cuh", 143, 168), ("fetch (bulk copies, mbarrier)", "k_tokens.cu", 299, 323),
+    ("colour: tie replay", "k_tokens.cu", 237, 267), ("colour: tie replay", "dct_core.cuh", 15, 56),
+    ("DCT: AAN butterflies", "dct_core.cuh", 294, 366), ("DCT: quantisation brackets", "dct_core.cuh", 376, 392),
+    ("DCT: zig-zag packing, mask", "dct_core.cuh", 367, 375), ("DCT: zig-zag packing, mask", "dct_core.cuh", 393, 409),
+    ("DCT: unpack, DC chain, block glue", "dct_core.cuh", 410, 500),
+    ("fetch (bulk copies, mbarrier)", "dct_core.cuh", 146, 171), ("fetch (bulk copies, mbarrier)", "k_tokens.cu", 299, 323),
     ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 268, 298), ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 324, 417),
     ("token stage: run/offset prefix, DC + EOB tokens", "k_tokens.cu", 418, 503), ("token stage: walk start (search, descent)", "k_tokens.cu", 504, 563),
     ("token stage: AC walk loop", "k_tokens.cu", 564, 596), ("token stage: flush, run records", "k_tokens.cu", 597, 640)]
@@ -34,13 +35,22 @@ def main():
     tiles = float(sys.argv[3]) if len(sys.argv) > 3 else 38400.0
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(obj)], cwd=tmp, check=True, stdout=subprocess.DEVNULL)
-    dis = subprocess.run(["nvdisasm", "-g", "-c", glob.glob(os.path.join(tmp, "*.cubin"))[0]], capture_output=True, text=True).stdout
-    lines, cur, fn = [], None, None
+    # -gi: every instruction is preceded by its inline chain, innermost first; an instruction is attributed to the innermost frame
+    # that lies in this repo's sources (the packed-FP32 and atomic intrinsics live in CUDA headers)
+    dis = subprocess.run(["nvdisasm", "-gi", "-c", glob.glob(os.path.join(tmp, "*.cubin"))[0]], capture_output=True, text=True).stdout
+    OURS = ("dct_core.cuh", "k_tokens.cu", "walk.cuh", "jpegb200_internal.cuh")
+    lines, cur, fn, in_chain, chain_done = [], None, None, False, False
     for line in dis.split("\n"):
         m = re.search(r'//## File "([^"]+)", line (\d+)', line)
         if m:
-            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            ent = (os.path.basename(m.group(1)), int(m.group(2)))
+            if not in_chain:
+                cur, chain_done = ent, ent[0] in OURS
+            elif not chain_done and ent[0] in OURS:
+                cur, chain_done = ent, True
+            in_chain = True
             continue
+        in_chain = False
         m = re.match(r"\.text\.(\S+):", line)
         if m:
             fn, cur = m.group(1), None

@@ -39,6 +39,15 @@ int jpegb200_set_exact_dct(jpegb200_ctx *ctx, int on);
  * (pixels -> token stream + histograms in one kernel, bit packer streams tokens; no coefficient planes in memory);
  * 0 = plane path (materialised int16 planes, the kernels the stage functions use).  Same bytes either way. */
 int jpegb200_set_token_path(jpegb200_ctx *ctx, int on);
+/* Token pools of the batched token path (encode_batch, encode_batch_host[_fmt]): tokens per 8x8 block the per-lane pools are
+ * sized for.  0 or 65 (default) = the worst case, DC + 63 coefficients + EOB for every block: 1.9 GB per lane for 64 frames of
+ * 1920x1280, nothing can overflow.  Photographic frames at these quantisers hold 6-7 tokens per block, uniform noise 24.  With a
+ * budget b the pools shrink to b / 65 of that; a frame that needs more is detected on the device, never written out of
+ * bounds, and reported with size 0: jpegb200_encode_batch leaves it at that (raise the budget and encode the frame again),
+ * jpegb200_encode_batch_host[_fmt] re-encodes such frames with the worst-case pool, one frame per wave, before it returns, so
+ * its results do not depend on the budget.  Synchronises the device and frees the pools (they are re-allocated by the next
+ * call).  Region and stage calls always use the worst case. */
+int jpegb200_set_token_budget(jpegb200_ctx *ctx, int tokens_per_block);
 /* Diagnostics: blocks that the last wave of `lane` sent to the literal chain (plane path). */
 int jpegb200_debug_fix_count(jpegb200_ctx *ctx, int lane, uint32_t *count);
 

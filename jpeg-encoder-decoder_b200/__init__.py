@@ -25,7 +25,7 @@ ROOT = os.path.dirname(_HERE)
 
 C_ABI_SYMBOLS = [
     "jpegb200_create", "jpegb200_destroy", "jpegb200_last_error", "jpegb200_configure", "jpegb200_launch_count",
-    "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_debug_fix_count",
+    "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_set_token_budget", "jpegb200_debug_fix_count",
     "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_batch_host_multi", "jpegb200_encode_batch_host_fmt", "jpegb200_unpack", "jpegb200_encode_regions",
     "jpegb200_stage_dct", "jpegb200_stage_huffman", "jpegb200_stage_write", "jpegb200_debug_build_tables",
     "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode", "jpegb200_compare_encode_batch",
@@ -79,6 +79,7 @@ def load_library() -> C.CDLL:
     L.jpegb200_configure.argtypes = [vp, C.c_int, C.c_int]
     L.jpegb200_set_exact_dct.argtypes = [vp, C.c_int]
     L.jpegb200_set_token_path.argtypes = [vp, C.c_int]
+    L.jpegb200_set_token_budget.argtypes = [vp, C.c_int]
     L.jpegb200_debug_fix_count.argtypes = [vp, C.c_int, u32p]
     L.jpegb200_launch_count.argtypes = [vp]
     L.jpegb200_launch_count.restype = C.c_uint64
@@ -246,6 +247,10 @@ class Encoder:
 
     def set_token_path(self, on: bool):
         self._check(self.lib.jpegb200_set_token_path(self.ctx, int(on)))
+
+    def set_token_budget(self, tokens_per_block: int):
+        """Size the token pools of the batched path for `tokens_per_block` (0 / 65 = worst case; include/jpegb200.h)."""
+        self._check(self.lib.jpegb200_set_token_budget(self.ctx, int(tokens_per_block)))
 
     def fix_count(self, lane: int = 0) -> int:
         n = C.c_uint32(0)

@@ -130,6 +130,7 @@ struct Lane {
     ws.tchunk_bits = (uint32_t*)tchunk_bits.p;
     ws.tchunk_base = (uint32_t*)tchunk_base.p;
     ws.fixtok_list = (uint4*)fixtok.p;
+    ws.tok_cap = 0xFFFFFFFFu;               // worst-case pool unless a batched entry point says otherwise
     return cudaSuccess;
   }
   void release() {
@@ -182,6 +183,7 @@ struct jpegb200_ctx {
   int overlap_waves = 0;      // set by the batched entry points when several waves will be in flight on different lanes
   int split_streams = 1;      // token path: run the kernels after k_pixels_to_tokens on the lane's high-priority stream
   int token_path = 1;         // batched entry points: 1 = k_pixels_to_tokens + k_pack_runs, 0 = coefficient planes (k_dct.cu + chunk kernels)
+  int tok_budget = 0;         // batched entry points: tokens per block the pools are sized for; 0 = worst case (jpegb200_set_token_budget)
   std::vector<Lane> lanes;
   cudaEvent_t fork = nullptr;
   uint64_t launches = 0;
@@ -428,6 +430,16 @@ int jpegb200_set_token_path(jpegb200_ctx* c, int on) {
   return 0;
 }
 
+int jpegb200_set_token_budget(jpegb200_ctx* c, int tokens_per_block) {
+  if (!c) return fail("null ctx");
+  if (tokens_per_block < 0 || tokens_per_block > 65) return fail("token budget %d outside 0..65", tokens_per_block);
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  c->tok_budget = tokens_per_block == 65 ? 0 : tokens_per_block;
+  for (Lane& l : c->lanes) { l.tok.release(); l.tok2.release(); l.tchunk_bits.release(); l.tchunk_base.release(); }   // re-allocated at the new size
+  return 0;
+}
+
 int jpegb200_debug_fix_count(jpegb200_ctx* c, int lane, uint32_t* count) {
   if (!c || !count || lane < 0 || lane >= (int)c->lanes.size()) return fail("bad argument");
   CK(cudaSetDevice(c->device));
@@ -479,19 +491,23 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   if (frame_stride < (size_t)3 * w * h) return fail("frame_stride smaller than a frame");
   CK(cudaSetDevice(c->device));
   cudaStream_t user = (cudaStream_t)stream;
-  const JobDims jd = job_dims(w, h, slot);
+  const bool tokens = c->token_path && !c->exact_dct;
+  const uint32_t budget = tokens ? (uint32_t)c->tok_budget : 0u;
+  const JobDims jd = jb_job_dims(w, h, slot, budget);
   const int G = wave_frames(c, w, h, false);
   WaveDims wd;
   const size_t g = (size_t)std::min(G, n);
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
   wd.toks = g * jd.toks; wd.runs = g * jd.runs; wd.tchunks = g * jd.tchunks;
-  const bool tokens = c->token_path && !c->exact_dct;
   wd.planes = !tokens;
   if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
   const int nwaves = (n + G - 1) / G;
   const int nl = std::min<int>((int)c->lanes.size(), nwaves);
-  for (int i = 0; i < nl; i++) CK(c->lanes[i].ensure(wd));
+  for (int i = 0; i < nl; i++) {
+    CK(c->lanes[i].ensure(wd));
+    if (budget) c->lanes[i].ws.tok_cap = jd.toks - 3u * JB_TCHUNK;
+  }
   c->overlap_waves = nl >= 2;
   CK(cudaEventRecord(c->fork, user));
   for (int i = 0; i < nl; i++) CK(cudaStreamWaitEvent(c->lanes[i].stream, c->fork, 0));
@@ -523,14 +539,15 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   const size_t frame = (size_t)3 * w * h;
   const size_t src_frame = fmt == JPEGB200_FMT_BGR888 ? frame : fmt == JPEGB200_FMT_RGB565 ? (size_t)2 * w * h : (size_t)w * h;
   const size_t dslot = (slot + 15) & ~(size_t)15;
-  const JobDims jd = job_dims(w, h, slot);
+  const bool tokens = c->token_path && !c->exact_dct;
+  const uint32_t budget = tokens ? (uint32_t)c->tok_budget : 0u;
+  const JobDims jd = jb_job_dims(w, h, slot, budget);
   const int G = wave_frames(c, w, h, true);
   const size_t g = (size_t)std::min(G, n);
   WaveDims wd;
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
   wd.toks = g * jd.toks; wd.runs = g * jd.runs; wd.tchunks = g * jd.tchunks;
-  const bool tokens = c->token_path && !c->exact_dct;
   wd.planes = !tokens;
   if (wd.coefs > 0xFFFFFFFFull || wd.scratch_words > 0xFFFFFFFFull || wd.toks > 0xFFFFFFFFull) return fail("wave too large; lower frames_per_wave");
   const int nwaves = (n + G - 1) / G;
@@ -538,6 +555,7 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   for (int i = 0; i < nl; i++) {
     Lane& l = c->lanes[i];
     CK(l.ensure(wd));
+    if (budget) l.ws.tok_cap = jd.toks - 3u * JB_TCHUNK;
     CK(l.in.ensure(g * frame));
     if (fmt != JPEGB200_FMT_BGR888) CK(l.in_packed.ensure(g * src_frame));
     CK(l.out.ensure(g * dslot));
@@ -580,6 +598,20 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   }
   for (int i = 0; i < nl; i++) if (retire(c->lanes[i])) return -1;
   for (int i = 0; i < nl; i++) CK(cudaStreamSynchronize(c->lanes[i].stream));
+  if (budget) {
+    // Frames that came back empty may have overflowed the token budget: once more, one frame per wave, with the worst-case pool
+    // (a single frame's worst case is smaller than a wave at any budget, so no buffer grows).  A frame that does not fit its
+    // slot comes back empty again.
+    const int saved_budget = c->tok_budget, saved_fpw = c->frames_per_wave;
+    int rc = 0;
+    for (int i = 0; i < n && !rc; i++) {
+      if (h_sizes[i]) continue;
+      c->tok_budget = 0; c->frames_per_wave = 1;
+      rc = jpegb200_encode_batch_host_fmt(c, h_bgr + (size_t)i * src_frame, fmt, 1, w, h, h_out + (size_t)i * slot, slot, h_sizes + i);
+    }
+    c->tok_budget = saved_budget; c->frames_per_wave = saved_fpw;
+    if (rc) return -1;
+  }
   return 0;
 }
 

@@ -63,7 +63,7 @@ struct JbJobState {
   uint32_t ctas_counted;     // CTAs of k_count_ff that are done with the job (the last one lays the file out)
 };
 
-enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4 };
+enum { JB_ERR_SCRATCH = 1, JB_ERR_SLOT = 2, JB_ERR_CODELEN = 4, JB_ERR_TOKENS = 8 };   // TOKENS: the job's part of the token pool was too small (jpegb200_set_token_budget)
 
 // ---- token path ------------------------------------------------------------------------------------------------
 // k_pixels_to_tokens walks the crop in tiles of JB_TILE_MCUS consecutive MCUs (raster order).  The blocks of one
@@ -127,6 +127,7 @@ struct JbWs {
   uint4* fixtok_list;   // token path: (job, block id inside the job, index of its first token, reserved tokens) of undecided blocks
   const uint32_t* tile_first;   // device-built job lists (k_region_jobs) only, else null: first tile of every job in the wave's tile numbering
   const uint32_t* live;         // device-built job lists only: [0] job slots in use, [1] output bytes placed, [2] tiles
+  uint32_t tok_cap;             // token path: tokens that fit a job's part of ws.tok (0xFFFFFFFF: sized for the worst case, never checked against)
 };
 
 __host__ __device__ inline uint32_t jb_nby(int w, int h) { return (uint32_t)(w * h) / 64u; }
@@ -155,7 +156,8 @@ __host__ __device__ inline JbSeg jb_seg(const JbJob& j, int s) {
 struct JbJobDims {
   uint32_t coefs, blocks, chunks, scratch_words, tiles_per_seg, toks, runs, tchunks;
 };
-__host__ __device__ inline JbJobDims jb_job_dims(int w, int h, size_t slot) {
+// tok_budget: tokens per block the pools are sized for (0 = the worst case of 65; jpegb200_set_token_budget)
+__host__ __device__ inline JbJobDims jb_job_dims(int w, int h, size_t slot, uint32_t tok_budget = 0) {
   JbJobDims d;
   const uint32_t nby = jb_nby(w, h), nbc = jb_nbc(w, h);
   d.coefs = 64u * (nby + 2 * nbc);
@@ -166,7 +168,12 @@ __host__ __device__ inline JbJobDims jb_job_dims(int w, int h, size_t slot) {
   words = (words + 3) & ~(size_t)3;
   d.scratch_words = (uint32_t)words;
   d.tiles_per_seg = (uint32_t)((slot + JB_STUFF_TILE - 1) / JB_STUFF_TILE + 1);
-  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS + 3u * JB_TCHUNK;     // + the alignment of the three scans in scan order
+  d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS;
+  if (tok_budget) {                      // at least one round: a round that overflows is dumped at the start of the job's part
+    const uint32_t want = d.blocks * tok_budget < (uint32_t)JB_ROUND_TOKENS ? (uint32_t)JB_ROUND_TOKENS : d.blocks * tok_budget;
+    if (want < d.toks) d.toks = want;
+  }
+  d.toks += 3u * JB_TCHUNK;              // + the alignment of the three scans in scan order
   d.runs = 4u * jb_runs_chroma(w, h);
   d.tchunks = d.toks / JB_TCHUNK + 1u;
   return d;

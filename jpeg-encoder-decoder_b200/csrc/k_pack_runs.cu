@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256) k_runs_prepare(JbWs ws) {
   __shared__ uint32_t wsum[9];
   const JbJob job = ws.jobs[blockIdx.x];
   JbJobState* st = ws.state + blockIdx.x;
+  if (st->error & JB_ERR_TOKENS) return;        // the job overflowed its token budget: its run records are not valid
   const uint32_t nrc = jb_runs_chroma(job.w, job.h), nr = 4u * nrc;
   const JbRun* runs = ws.runs + job.run_off;
   if (threadIdx.x < 32) h[threadIdx.x] = 0;
@@ -164,6 +165,7 @@ constexpr int CP_STEP = JB_CP_STEP;        // 32-token slices whose loads are in
 #endif
 __global__ void __launch_bounds__(PR_WARPS * 32, JB_COMPACT_MIN_CTAS) k_compact_tokens(JbWs ws) {
   __shared__ uint32_t enc[2][512];
+  if (ws.state[blockIdx.y].error & JB_ERR_TOKENS) return;
   const JbJob job = ws.jobs[blockIdx.y];
   const uint32_t nrc = jb_runs_chroma(job.w, job.h);
   load_enc(ws, blockIdx.y, enc);
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_COMPACT_MIN_CTAS) k_compact_
 #if !JB_FUSE_SCAN
 __global__ void __launch_bounds__(256) k_scan_tchunks(JbWs ws) {
   __shared__ uint32_t s_wsum[9], s_word[4];
+  if (ws.state[blockIdx.x].error & JB_ERR_TOKENS) return;
   scan_tchunks(ws, blockIdx.x, ws.jobs[blockIdx.x], s_wsum, s_word);
 }
 #endif

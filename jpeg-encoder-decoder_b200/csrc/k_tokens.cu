@@ -268,7 +268,9 @@ __device__ __forceinline__ void tk_colour_half(TkSmemT<ALIGNED>& sm, const TkShi
   }
 }
 
-template <bool ALIGNED>
+// BUDGET: the token pool was sized by jpegb200_set_token_budget, so a round's claim is checked against the job's share (an
+// instantiation of its own: the default, worst-case pool pays nothing for the check)
+template <bool ALIGNED, bool BUDGET>
 __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) k_pixels_to_tokens(JbWs ws, int ntiles, int tiles_per_job, float magic, int strided) {
   constexpr int TK_WARPS = TkWarps<ALIGNED>::value;
   using TkSmem = TkSmemT<ALIGNED>;
@@ -488,8 +490,20 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
         __syncwarp();                                // the samples of every lane's block have been consumed: stage may be written
         s_mask[lane] = make_uint2(__brev((uint32_t)mask), __brev((uint32_t)(mask >> 32)));
         s_meta[lane] = acex | (excl << 16);
+        // A round that does not fit the job's part of the pool (only when the pool was sized by jpegb200_set_token_budget) flags
+        // the job and dumps its tokens at the start of that part: the job is lost — every later kernel skips it, its size reads 0.
+        auto place = [&]() {
+          const uint32_t c0 = __shfl_sync(FULL, claim, 0);
+          if constexpr (BUDGET) {
+            const bool ovf = c0 + total > ws.tok_cap;
+            if (ovf && lane == 0) atomicOr(&ws.state[p.job].error, (uint32_t)JB_ERR_TOKENS);
+            return job.tok_off + (ovf ? 0u : c0);
+          } else {
+            return job.tok_off + c0;
+          }
+        };
         uint32_t round_tok = 0;
-        if (total > TK_WINDOW) round_tok = job.tok_off + __shfl_sync(FULL, claim, 0);
+        if (total > TK_WINDOW) round_tok = place();
         uint32_t* dst = total <= TK_WINDOW ? stage : ws.tok + round_tok;        // generic pointer: shared or global
         {
           // a run's first DC is predicted across runs: k_runs_prepare fills it in (token 0 meanwhile)
@@ -598,7 +612,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
           }
         }
         if (total <= TK_WINDOW) {
-          round_tok = job.tok_off + __shfl_sync(FULL, claim, 0);
+          round_tok = place();
           uint32_t* gdst = ws.tok + round_tok;
           for (uint32_t k = lane; k < total; k += 32) gdst[k] = stage[k];
         }
@@ -624,14 +638,16 @@ void jb_init_grey_tokens(cudaStream_t st) { k_init_grey<<<1, 256, 0, st>>>(); }
 // n tiles per warp, so that the high-priority kernels of other lanes get SM slots as CTAs retire (multi-lane batches).
 void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h, bool rows_aligned, int tiles_per_warp, cudaStream_t st, bool strided) {
   // function attributes are per device: a process that drives several GPUs (jpegb200_encode_batch_host_multi) opts in on each
-  static int ctas_all[64][2] = {}, sms_all[64] = {};
+  static int ctas_all[64][4] = {}, sms_all[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   dev &= 63;
   int* ctas_per_sm = ctas_all[dev];
   int& sms = sms_all[dev];
-  const int v = rows_aligned ? 1 : 0;
-  auto kern = rows_aligned ? k_pixels_to_tokens<true> : k_pixels_to_tokens<false>;
+  const bool budget = ws.tok_cap != 0xFFFFFFFFu;
+  const int v = (rows_aligned ? 1 : 0) + (budget ? 2 : 0);
+  auto kern = rows_aligned ? (budget ? k_pixels_to_tokens<true, true> : k_pixels_to_tokens<true, false>)
+                           : (budget ? k_pixels_to_tokens<false, true> : k_pixels_to_tokens<false, false>);
   const int warps = rows_aligned ? TkWarps<true>::value : TkWarps<false>::value;
   const int smem = rows_aligned ? (int)sizeof(TkSmemT<true>) * warps : (int)sizeof(TkSmemT<false>) * warps;
   if (!ctas_per_sm[v]) {

@@ -241,6 +241,45 @@ def test_slot_too_small_reports_zero_size(enc, frames):
     assert int(d_sizes[0]) == 0
 
 
+def test_token_budget_overflow_is_detected_and_recovered(frames):
+    """jpegb200_set_token_budget: pools sized for 12 tokens per block hold the natural class (6-7) but not noise (24).  The device
+    path reports the frames that overflowed with size 0 and leaves the others byte-identical; the host path re-encodes them
+    with the worst-case pool, so its bytes do not depend on the budget."""
+    import torch
+    w, h = 320, 240
+    imgs = np.stack([frames.natural_frame(0, w, h), frames.noise_frame(0, w, h), frames.natural_frame(1, w, h), frames.noise_frame(1, w, h),
+                     frames.ramp_frame(2, w, h)])
+    e = pkg.Encoder(0)
+    try:
+        e.configure(2, 3)
+        want = e.encode_frames(imgs)
+        e.set_token_budget(12)
+        n, slot = len(imgs), w * h * 3
+        d_in = _torch_batch(imgs)
+        d_out = torch.zeros((n, slot), dtype=torch.uint8, device="cuda")
+        d_sizes = torch.full((n,), 7, dtype=torch.int32, device="cuda")
+        for _ in range(2):                                  # twice: the flags of a wave do not leak into the next one
+            e.encode_batch_ptr(d_in.data_ptr(), n, w, h, w * h * 3, d_out.data_ptr(), slot, d_sizes.data_ptr(), 0)
+            torch.cuda.synchronize()
+            sizes = d_sizes.cpu().numpy()
+            assert sizes[1] == 0 and sizes[3] == 0, sizes      # noise: 24 tokens per block
+            for k in (0, 2, 4):
+                assert d_out[k, : sizes[k]].cpu().numpy().tobytes() == want[k], k
+        assert e.encode_frames(imgs) == want                # host path: recovered
+        e.set_token_budget(32)                              # enough for noise
+        assert e.encode_frames(imgs) == want
+        e.encode_batch_ptr(d_in.data_ptr(), n, w, h, w * h * 3, d_out.data_ptr(), slot, d_sizes.data_ptr(), 0)
+        torch.cuda.synchronize()
+        sizes = d_sizes.cpu().numpy()
+        assert [d_out[k, : sizes[k]].cpu().numpy().tobytes() for k in range(n)] == want
+        e.set_token_budget(0)
+        assert e.encode_frames(imgs) == want
+        with pytest.raises(pkg.JpegB200Error, match="budget"):
+            e.set_token_budget(66)
+    finally:
+        e.close()
+
+
 def test_bad_dimensions_are_rejected(enc):
     with pytest.raises(pkg.JpegB200Error, match="multiples of 16"):
         enc.encode_batch_host(np.zeros((1, 20, 16, 3), np.uint8), 4096)

@@ -55,7 +55,7 @@ def main():
         if m:
             fn, cur = m.group(1), None
             continue
-        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line) and fn and "k_pixels_to_tokensILb1" in fn:
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/", line) and fn and "k_pixels_to_tokensILb1ELb0" in fn:
             lines.append(cur)
     rows = list(csv.reader(open(src_csv)))
     hdr = rows[1]

@@ -171,7 +171,7 @@ __host__ __device__ inline JbJobDims jb_job_dims(int w, int h, size_t slot, uint
   d.toks = jb_tiles(w, h) * 3u * JB_ROUND_TOKENS;
   if (tok_budget) {                      // at least one round: a round that overflows is dumped at the start of the job's part
     const uint32_t want = d.blocks * tok_budget < (uint32_t)JB_ROUND_TOKENS ? (uint32_t)JB_ROUND_TOKENS : d.blocks * tok_budget;
-    if (want < d.toks) d.toks = want;
+    if (((want + 3u) & ~3u) < d.toks) d.toks = (want + 3u) & ~3u;      // rounds claim multiples of four tokens
   }
   d.toks += 3u * JB_TCHUNK;              // + the alignment of the three scans in scan order
   d.runs = 4u * jb_runs_chroma(w, h);

@@ -453,8 +453,10 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
         const uint32_t hb = __ballot_sync(FULL, head);
         // the round claims its tokens' place in the job's pool (dense pool: the readers stream it); the answer is needed
         // only when the tokens leave shared memory
+        // (rounded up to four tokens: the flush below moves 16 bytes per lane; readers go by the run records, the gaps are never read)
+        const uint32_t total4 = (total + 3u) & ~3u;
         uint32_t claim = 0;
-        if (lane == 0) claim = atomicAdd(&ws.state[p.job].tok_cursor, total);
+        if (lane == 0) claim = atomicAdd(&ws.state[p.job].tok_cursor, total4);
         uint32_t run_rid = 0xFFFFFFFFu, run_ntok = 0, run_dc = 0;
         {
           const uint32_t above = lane == 31 ? 0u : hb & ~((2u << lane) - 1u);
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
         auto place = [&]() {
           const uint32_t c0 = __shfl_sync(FULL, claim, 0);
           if constexpr (BUDGET) {
-            const bool ovf = c0 + total > ws.tok_cap;
+            const bool ovf = c0 + total4 > ws.tok_cap;
             if (ovf && lane == 0) atomicOr(&ws.state[p.job].error, (uint32_t)JB_ERR_TOKENS);
             return job.tok_off + (ovf ? 0u : c0);
           } else {
@@ -614,7 +616,7 @@ __global__ void __launch_bounds__(TkWarps<ALIGNED>::value * 32, TK_CTAS_PER_SM) 
         if (total <= TK_WINDOW) {
           round_tok = place();
           uint32_t* gdst = ws.tok + round_tok;
-          for (uint32_t k = lane; k < total; k += 32) gdst[k] = stage[k];
+          for (uint32_t k = 4u * lane; k < total; k += 128u) *reinterpret_cast<uint4*>(gdst + k) = *reinterpret_cast<const uint4*>(stage + k);
         }
         if (run_rid != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(&ws.runs[job.run_off + run_rid]) = make_uint4(round_tok + excl, run_ntok, run_dc, 0u);
         if (defer) ws.fixtok_list[atomicAdd(ws.fix_count, 1u)] = make_uint4((uint32_t)p.job, blk, round_tok + excl, cnt);

@@ -6,15 +6,15 @@ import collections, csv, glob, os, re, subprocess, sys, tempfile
 
 SECTIONS = [  # (label, file, first line, last line)
     ("colour: numerators (IDP.2A)", "dct_core.cuh", 172, 193), ("colour: divisions, tie screens (ycc_row8n)", "dct_core.cuh", 194, 293),
-    ("colour: loads, packing, chroma sums, tie list", "k_tokens.cu", 188, 236), ("colour: tie replay", "k_tokens.cu", 97, 187),
-    ("colour: tie replay", "k_tokens.cu", 237, 267), ("colour: tie replay", "dct_core.cuh", 15, 56),
+    ("colour: loads, packing, chroma sums, tie list", "k_tokens.cu", 188, 238), ("colour: tie replay", "k_tokens.cu", 97, 187),
+    ("colour: tie replay", "k_tokens.cu", 239, 269), ("colour: tie replay", "dct_core.cuh", 15, 56),
     ("DCT: AAN butterflies", "dct_core.cuh", 294, 366), ("DCT: quantisation brackets", "dct_core.cuh", 376, 392),
     ("DCT: zig-zag packing, mask", "dct_core.cuh", 367, 375), ("DCT: zig-zag packing, mask", "dct_core.cuh", 393, 409),
     ("DCT: unpack, DC chain, block glue", "dct_core.cuh", 410, 500),
-    ("fetch (bulk copies, mbarrier)", "dct_core.cuh", 146, 171), ("fetch (bulk copies, mbarrier)", "k_tokens.cu", 299, 323),
-    ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 268, 298), ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 324, 417),
-    ("token stage: run/offset prefix, DC + EOB tokens", "k_tokens.cu", 418, 503), ("token stage: walk start (search, descent)", "k_tokens.cu", 504, 563),
-    ("token stage: AC walk loop", "k_tokens.cu", 564, 596), ("token stage: flush, run records", "k_tokens.cu", 597, 640)]
+    ("fetch (bulk copies, mbarrier)", "dct_core.cuh", 146, 171), ("fetch (bulk copies, mbarrier)", "k_tokens.cu", 301, 328),
+    ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 270, 300), ("tile bookkeeping, barrier, histogram flush", "k_tokens.cu", 329, 422),
+    ("token stage: run/offset prefix, DC + EOB tokens", "k_tokens.cu", 423, 522), ("token stage: walk start (search, descent)", "k_tokens.cu", 523, 582),
+    ("token stage: AC walk loop", "k_tokens.cu", 583, 615), ("token stage: flush, run records", "k_tokens.cu", 616, 640)]
 
 
 def label(f, ln):

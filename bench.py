@@ -16,6 +16,8 @@ encodes its own 1024 frames, no data-path collective — frames are independent,
 
   parity_checked : SHA-256 of frames 0/1/121/1023 of the timed batch's output against tests/golden/golden.json (outside
                  every timed region): the bytes that were timed are the reference's bytes
+  parity_live  : the streams the CPU arm produced in this run (the unmodified reference, 192 frames of the same batch by default)
+                 compared byte for byte (size + SHA-256) with the device's output of the last timed step
   sub_records  : the other workloads of BASELINE.json (noise and ramp classes, config 5 = 3840x2160, config 3 = the
                  comparator loop through jpegb200_compare_encode_batch beside the reference's loop on the host cores)
 
@@ -62,8 +64,9 @@ def _cpu_worker(args):
     else:
         chk, kind = cpu_checkers.Oracle(), "port"
     chk.time_encode(batch[:1], 1)          # touch code and buffers
-    sec, nbytes = chk.time_encode(batch, reps)
-    return sec, nbytes, count * reps, kind
+    sec, nbytes, streams = chk.time_encode(batch, reps, keep=True)
+    # (frame index, bytes, SHA-256) of every stream this process produced: the GPU's bytes are compared with them further down
+    return sec, nbytes, count * reps, kind, [(first + i, len(s), hashlib.sha256(s).hexdigest()) for i, s in enumerate(streams)]
 
 
 def cpu_arm(frames_per_proc: int, nproc: int, reps: int = 1):
@@ -75,7 +78,7 @@ def cpu_arm(frames_per_proc: int, nproc: int, reps: int = 1):
     wall = max(r[0] for r in res)
     nframes = sum(r[2] for r in res)
     per_core = [r[2] * FRAME_MPIX / r[0] for r in res]
-    return dict(value=nframes * FRAME_MPIX / wall, unit="Mpix/s", cores=nproc, kind=res[0][3],
+    return dict(value=nframes * FRAME_MPIX / wall, unit="Mpix/s", cores=nproc, kind=res[0][3], streams=[t for r in res for t in r[4]],
                 sample=f"{nframes} frames of the {KIND} {W}x{H} batch ({frames_per_proc} per process x {nproc} processes, "
                        f"{reps} pass), timed inside C around rgb_to_dct+init_huffman+write_jpg",
                 seconds=wall, per_core_mpix_s=float(np.median(per_core)), jpeg_bytes_per_frame=sum(r[1] for r in res) / nframes)
@@ -284,6 +287,18 @@ def main():
     k1_ms, k1_n = get_timing(enc)
     parity_checked = parity(a.kind, W, H, first, n, d_out, d_sizes.cpu().numpy())      # the output of the last timed step
     assert all(p["sha256_matches_reference"] for p in parity_checked), parity_checked
+    # ... and against the streams the CPU arm produced in this very run (the unmodified reference on this box's cores)
+    live_parity = None
+    if cpu is not None:
+        szs = d_sizes.cpu().numpy()
+        same, checked = 0, 0
+        for f, nb, digest in cpu["streams"]:
+            i = f - first
+            if 0 <= i < n:
+                checked += 1
+                same += int(int(szs[i]) == nb and hashlib.sha256(d_out[i, : int(szs[i])].cpu().numpy().tobytes()).hexdigest() == digest)
+        live_parity = {"frames_compared": checked, "byte_identical": same, "against": f"the CPU arm's own output in this run (kind: {cpu['kind']})"}
+        assert same == checked, live_parity
     # the same kernel timed alone (one lane: no other kernel shares the SMs), as a second reading for the roofline object:
     # in the timed region above its launches are time-sliced with the high-priority kernels of the other lanes
     enc.configure(a.frames_per_wave, 1)
@@ -540,7 +555,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic", "config": config, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                 "cpu_baseline": None if cpu is None else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "per_core_mpix_s", "single_thread_mpix_s")},
-                "clocks": clk.summary(), "jpeg_bytes_per_frame": jpeg_bytes / n, "parity_checked": parity_checked, "sub_records": sub_records}
+                "clocks": clk.summary(), "jpeg_bytes_per_frame": jpeg_bytes / n, "parity_checked": parity_checked, "parity_live": live_parity,
+                "sub_records": sub_records}
         print(json.dumps(line))
     enc.close()
     if world > 1:

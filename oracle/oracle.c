@@ -347,18 +347,33 @@ size_t orc_encode(const uint8_t *bgr, int frame_w, area_t a, uint8_t *jpg) {
 }
 
 double orc_time_encode(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int reps, size_t *bytes_out) {
+  return orc_time_encode_keep(frames, nframes, frame_stride, w, h, reps, bytes_out, NULL, 0, NULL);
+}
+/* The same, and the streams of the first pass are kept (frame f at keep + f * slot, size in sizes[f]; 0 when it does not fit)
+ * for bench.py's comparison with the device's bytes.  The clock runs around the encode calls only. */
+double orc_time_encode_keep(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int reps, size_t *bytes_out, uint8_t *keep,
+                            size_t slot, uint32_t *sizes) {
   uint8_t *jpg = malloc((size_t)3 * w * h);
   memset(jpg, 0, (size_t)3 * w * h);
   area_t a = {0, 0, w, h};
   size_t total = 0;
+  double sec = 0.0;
   struct timespec t0, t1;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int r = 0; r < reps; r++)
-    for (int f = 0; f < nframes; f++) total += orc_encode(frames + (size_t)f * frame_stride, w, a, jpg);
-  clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int f = 0; f < nframes; f++) {
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      size_t n = orc_encode(frames + (size_t)f * frame_stride, w, a, jpg);
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      sec += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+      total += n;
+      if (keep && r == 0) {
+        sizes[f] = n <= slot ? (uint32_t)n : 0u;
+        if (n <= slot) memcpy(keep + (size_t)f * slot, jpg, n);
+      }
+    }
   if (bytes_out) *bytes_out = total;
   free(jpg);
-  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return sec;
 }
 
 /* --------------------------------------------------------------------------

@@ -43,6 +43,8 @@ void orc_enlarge_adjust(area_t *a, int frame_w, int frame_h);                   
 
 /* bench helper: seconds for reps x nframes full-frame encodes */
 double orc_time_encode(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int reps, size_t *bytes_out);
+double orc_time_encode_keep(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int reps, size_t *bytes_out, uint8_t *keep,
+                            size_t slot, uint32_t *sizes);
 int orc_fmt2rgb888(const uint8_t *src, size_t src_len, int fmt, uint8_t *bgr);     /* esp32-camera 2.0.3 to_bmp.c, RGB565 / GRAYSCALE branches */
 double orc_time_loop(const uint8_t *frames, int nframes, size_t frame_stride, int w, int h, int *regions_out, size_t *bytes_out);
 

@@ -61,7 +61,15 @@ void ref_build_table(huff_code *hc) { init_huff_table(hc); }
 
 /* Wall-clock seconds for `reps` passes over `nframes` full frames laid out
  * `frame_stride` bytes apart.  Used by bench.py for the CPU baseline. */
+double ref_time_encode_keep(uint8_t *frames, int nframes, size_t frame_stride, int reps, size_t *bytes_out, uint8_t *keep, size_t slot,
+                            uint32_t *sizes);
 double ref_time_encode(uint8_t *frames, int nframes, size_t frame_stride, int reps, size_t *bytes_out) {
+  return ref_time_encode_keep(frames, nframes, frame_stride, reps, bytes_out, NULL, 0, NULL);
+}
+/* The same, and the streams of the first pass are kept (frame f at keep + f * slot, its size in sizes[f]; 0 when it does not
+ * fit) so that bench.py can compare the device's bytes with them.  The clock runs around the encode calls only. */
+double ref_time_encode_keep(uint8_t *frames, int nframes, size_t frame_stride, int reps, size_t *bytes_out, uint8_t *keep, size_t slot,
+                            uint32_t *sizes) {
   size_t npix = (size_t)ref_width * ref_height;
   int16_t *Y = malloc(npix * sizeof(int16_t));
   int16_t *Cb = malloc(npix / 4 * sizeof(int16_t));
@@ -72,15 +80,23 @@ double ref_time_encode(uint8_t *frames, int nframes, size_t frame_stride, int re
   memset(Y, 0, npix * 2);
   memset(jpg, 0, 3 * npix);
   size_t total = 0;
+  double sec = 0.0;
   struct timespec t0, t1;
-  clock_gettime(CLOCK_MONOTONIC, &t0);
   for (int r = 0; r < reps; r++)
-    for (int f = 0; f < nframes; f++)
-      total += ref_encode(frames + (size_t)f * frame_stride, 0, 0, ref_width, ref_height, Y, Cb, Cr, luma, chroma, jpg);
-  clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int f = 0; f < nframes; f++) {
+      clock_gettime(CLOCK_MONOTONIC, &t0);
+      size_t n = ref_encode(frames + (size_t)f * frame_stride, 0, 0, ref_width, ref_height, Y, Cb, Cr, luma, chroma, jpg);
+      clock_gettime(CLOCK_MONOTONIC, &t1);
+      sec += (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+      total += n;
+      if (keep && r == 0) {
+        sizes[f] = n <= slot ? (uint32_t)n : 0u;
+        if (n <= slot) memcpy(keep + (size_t)f * slot, jpg, n);
+      }
+    }
   if (bytes_out) *bytes_out = total;
   free(Y); free(Cb); free(Cr); free(jpg); free(luma); free(chroma);
-  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  return sec;
 }
 
 /* app_main's steady-state loop (main/main.c:137-162) over `nframes` frames, timed: subsample -> compare -> encode every

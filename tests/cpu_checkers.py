@@ -93,6 +93,9 @@ class Oracle(_Base):
         L.orc_diff_mask.argtypes = [C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]
         L.orc_time_encode.restype = C.c_double
+        L.orc_time_encode_keep.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_uint8), C.c_size_t,
+                                           C.POINTER(C.c_uint32)]
+        L.orc_time_encode_keep.restype = C.c_double
         L.orc_fmt2rgb888.argtypes = [C.POINTER(C.c_uint8), C.c_size_t, C.c_int, C.POINTER(C.c_uint8)]
         L.orc_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.orc_time_loop.restype = C.c_double
@@ -158,12 +161,17 @@ class Oracle(_Base):
         self.lib.orc_diff_mask(_u8(np.ascontiguousarray(sub)), _u8(np.ascontiguousarray(saved)), n, _u8(m))
         return m
 
-    def time_encode(self, frames, reps=1):
-        """frames: (N, H, W, 3) uint8.  Returns (seconds, jpeg_bytes)."""
+    def time_encode(self, frames, reps=1, keep=False):
+        """frames: (N, H, W, 3) uint8.  Returns (seconds, jpeg_bytes) or, with keep, (seconds, jpeg_bytes, [stream of every frame])."""
         N, H, W, _ = frames.shape
         nb = C.c_size_t(0)
-        s = self.lib.orc_time_encode(_u8(frames), N, H * W * 3, W, H, reps, C.byref(nb))
-        return s, nb.value
+        if not keep:
+            s = self.lib.orc_time_encode(_u8(frames), N, H * W * 3, W, H, reps, C.byref(nb))
+            return s, nb.value
+        slot = 3 * W * H
+        out, sizes = np.zeros((N, slot), np.uint8), np.zeros(N, np.uint32)
+        s = self.lib.orc_time_encode_keep(_u8(frames), N, H * W * 3, W, H, reps, C.byref(nb), _u8(out), slot, sizes.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return s, nb.value, [out[i, : sizes[i]].tobytes() for i in range(N)]
 
 
     def fmt2rgb888(self, packed: np.ndarray, fmt: int, npix: int) -> np.ndarray:
@@ -201,6 +209,8 @@ class Ref(_Base):
         L.ref_enlarge_adjust.argtypes = [C.POINTER(Area)]
         L.ref_time_encode.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
         L.ref_time_encode.restype = C.c_double
+        L.ref_time_encode_keep.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_uint32)]
+        L.ref_time_encode_keep.restype = C.c_double
         L.ref_time_loop.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_size_t)]
         L.ref_time_loop.restype = C.c_double
 
@@ -241,12 +251,17 @@ class Ref(_Base):
         self.lib.ref_enlarge_adjust(C.byref(a))
         return a.tup()
 
-    def time_encode(self, frames, reps=1):
+    def time_encode(self, frames, reps=1, keep=False):
         N, H, W, _ = frames.shape
         self.lib.ref_set_dims(W, H)
         nb = C.c_size_t(0)
-        s = self.lib.ref_time_encode(_u8(frames), N, H * W * 3, reps, C.byref(nb))
-        return s, nb.value
+        if not keep:
+            s = self.lib.ref_time_encode(_u8(frames), N, H * W * 3, reps, C.byref(nb))
+            return s, nb.value
+        slot = 3 * W * H
+        out, sizes = np.zeros((N, slot), np.uint8), np.zeros(N, np.uint32)
+        s = self.lib.ref_time_encode_keep(_u8(frames), N, H * W * 3, reps, C.byref(nb), _u8(out), slot, sizes.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return s, nb.value, [out[i, : sizes[i]].tobytes() for i in range(N)]
 
     def time_loop(self, frames):
         N, H, W, _ = frames.shape

@@ -126,6 +126,17 @@ def test_oracle_vs_ref_random_images(oracle, ref):
         assert a["jpg"].tobytes() == b["jpg"].tobytes(), it
 
 
+def test_timing_harness_keeps_the_streams_it_times(oracle, ref):
+    """bench.py compares the device's bytes with the streams its CPU arm produced while it was timed (parity_live)."""
+    rng = np.random.default_rng(77)
+    batch = np.stack([_rand_img(rng, 48, 64, k) for k in range(4)])
+    for chk in (oracle, ref):
+        sec, nbytes, streams = chk.time_encode(batch, 2, keep=True)
+        assert sec > 0 and len(streams) == 4 and nbytes == 2 * sum(len(s) for s in streams)
+        for k in range(4):
+            assert streams[k] == oracle.encode(batch[k])["jpg"].tobytes(), (chk.name, k)
+
+
 def test_oracle_vs_ref_crops(oracle, ref, frames):
     img = frames.sample_bgr("640_diffs")
     for area in [(2, 36, 112, 432), (358, 66, 256, 336), (0, 0, 16, 16), (624, 624, 16, 16), (3, 5, 48, 32), (101, 7, 528, 16)]:

@@ -97,6 +97,12 @@ __global__ void __launch_bounds__(256) k_runs_prepare(JbWs ws) {
       carry += total;
     }
     if (threadIdx.x == 0) { st->tok_total[s] = carry; st->tok_start[s] = start; }
+    // the rest of the scan's last token chunk reads as tokens without bits: k_pack_tchunks loads whole chunks and tests no token
+    // against the end of its scan
+    {
+      const uint32_t end = start + carry, pad = (0u - end) & (uint32_t)(JB_TCHUNK - 1);
+      for (uint32_t k = threadIdx.x; k < pad; k += 256) ws.tok2[job.tok_off + end + k] = 0;
+    }
     start = (start + carry + JB_TCHUNK - 1) & ~(uint32_t)(JB_TCHUNK - 1);
   }
 }
@@ -362,7 +368,6 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunk
     const int s = f < nchunk[0] ? 0 : (f < nchunk[0] + nchunk[1] ? 1 : 2);
     const uint32_t c = f - (s == 0 ? 0u : s == 1 ? nchunk[0] : nchunk[0] + nchunk[1]);
     const uint32_t cg = st->tok_start[s] / JB_TCHUNK + c;                      // chunk id inside the job
-    const uint32_t ntok = min((uint32_t)JB_TCHUNK, st->tok_total[s] - c * JB_TCHUNK);
     const uint32_t base_bits = ws.tchunk_base[job.tchunk_off + cg], total = ws.tchunk_bits[job.tchunk_off + cg];
     const uint32_t phase = base_bits & 31;
     uint32_t* gw = ws.scratch + job.scratch_off + st->seg_word[s] + (base_bits >> 5);   // word that holds the chunk's first bit
@@ -370,10 +375,8 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunk
     const uint32_t last_word = (phase + total - 1) >> 5;
     const uint4* tp = reinterpret_cast<const uint4*>(ws.tok2 + job.tok_off + (size_t)cg * JB_TCHUNK) + 2 * lane;
     uint32_t t8[PR_TOK];
-    {
-      uint4 a = make_uint4(0, 0, 0, 0), b = a;
-      if (lane * PR_TOK < ntok) a = __ldg(tp);
-      if (lane * PR_TOK + 4 < ntok) b = __ldg(tp + 1);
+    {                                       // the tail of a scan's last chunk holds zeros (k_runs_prepare)
+      const uint4 a = __ldg(tp), b = __ldg(tp + 1);
       t8[0] = a.x; t8[1] = a.y; t8[2] = a.z; t8[3] = a.w; t8[4] = b.x; t8[5] = b.y; t8[6] = b.z; t8[7] = b.w;
     }
     // resolved tokens (k_compact_tokens): code word << 5 | length; length 31 escapes to a raw token that carries ZRLs
@@ -381,8 +384,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_PACK_MIN_CTAS) k_pack_tchunk
     uint32_t word[PR_TOK], len[PR_TOK], zr = 0, nbits = 0, zrl_code = 0, zrl_len = 0;
 #pragma unroll
     for (int j = 0; j < PR_TOK; j++) {
-      const bool live = lane * PR_TOK + j < ntok;             // a partly filled vector carries stale tokens past the end
-      const uint32_t t = live ? t8[j] : 0u;
+      const uint32_t t = t8[j];
       word[j] = t >> 5;
       len[j] = t & 31u;
       if (len[j] == 31u) {                                    // rare: decode the raw token with the table in global memory

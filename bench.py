@@ -18,7 +18,8 @@ encodes its own 1024 frames, no data-path collective — frames are independent,
                  every timed region): the bytes that were timed are the reference's bytes
   parity_live  : the streams the CPU arm produced in this run (the unmodified reference, 192 frames of the same batch by default)
                  compared byte for byte (size + SHA-256) with the device's output of the last timed step
-  sub_records  : the other workloads of BASELINE.json (noise and ramp classes, config 5 = 3840x2160, config 3 = the
+  sub_records  : the other workloads of BASELINE.json (config 2 = the drop-in entry points one frame at a time, noise and ramp
+                 classes, config 5 = 3840x2160, config 3 = the
                  comparator loop through jpegb200_compare_encode_batch beside the reference's loop on the host cores)
 
 `--impl reference` times only that CPU arm (all host cores) and prints the same JSON shape.
@@ -82,6 +83,25 @@ def cpu_arm(frames_per_proc: int, nproc: int, reps: int = 1):
                 sample=f"{nframes} frames of the {KIND} {W}x{H} batch ({frames_per_proc} per process x {nproc} processes, "
                        f"{reps} pass), timed inside C around rgb_to_dct+init_huffman+write_jpg",
                 seconds=wall, per_core_mpix_s=float(np.median(per_core)), jpeg_bytes_per_frame=sum(r[1] for r in res) / nframes)
+
+
+def _cpu_dropin_worker(args):
+    import cpu_checkers
+    fr = frames_mod()
+    chk = cpu_checkers.Ref() if cpu_checkers.Ref.available() else cpu_checkers.Oracle()
+    out = {}
+    for name, img in (("sample_640x640_bgr", fr.sample_bgr("640")), ("tile_1920x1280_bgr", fr.tile_bgr(1920, 1280))):
+        batch = np.ascontiguousarray(img[None])
+        chk.time_encode(batch, 1)
+        sec, _ = chk.time_encode(batch, 3)
+        out[name] = sec / 3
+    return out, "reference" if cpu_checkers.Ref.available() else "port"
+
+
+def cpu_dropin_arm():
+    """One frame at a time through rgb_to_dct + init_huffman + write_jpg of the reference C, single thread (what app_main does)."""
+    with mp.get_context("fork").Pool(1) as pool:
+        return pool.map(_cpu_dropin_worker, [None])[0]
 
 
 def _cpu_loop_worker(args):
@@ -209,6 +229,8 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu and not a.no_sub:
         for (lw, lh, lf) in ((640, 640, 33), (1920, 1280, 9)):
             cpu_loops[(lw, lh)] = (cpu_loop_arm(lw, lh, lf, ncores), cpu_loop_arm(lw, lh, lf, 1))
+
+    cpu_dropin = cpu_dropin_arm() if rank == 0 and world == 1 and not a.no_cpu and not a.no_sub else None
 
     import torch
     import torch.distributed as dist
@@ -429,6 +451,34 @@ def main():
             torch.cuda.empty_cache()
             return rec
 
+        # config 2: the drop-in boundary itself - one frame at a time through the reference's three entry points as this library
+        # exports them (host buffers in and out on every call: planes back after rgb_to_dct, tables after init_huffman, the
+        # file after write_jpg), beside the reference C doing the same on one core
+        def dropin_record():
+            api = pkg.RefAPI()
+            enc_golden = json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json")))["encode"]
+            rows = []
+            for name, img in (("sample_640x640_bgr", fr.sample_bgr("640")), ("tile_1920x1280_bgr", fr.tile_bgr(1920, 1280))):
+                h_, w_, _ = img.shape
+                got = api.encode(img)
+                ok_ = hashlib.sha256(got["jpg"].tobytes()).hexdigest() == enc_golden[name]["sha256"]
+                assert ok_, ("drop-in entry points differ from the golden digest", name)
+                reps = 10
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    api.encode(img)
+                dt = (time.perf_counter() - t0) / reps
+                row = {"image": name, "ms_per_frame": 1000 * dt, "mpix_s": w_ * h_ / 1e6 / dt, "bytes": int(got["jpg"].size), "sha256_matches_reference": ok_}
+                if cpu_dropin:
+                    row["reference_ms_per_frame_one_core"] = 1000 * cpu_dropin[0][name]
+                rows.append(row)
+            return {"workload": "config 2: rgb_to_dct + init_huffman + write_jpg, the reference's own entry points exported by libjpegb200.so, one frame per call "
+                                "sequence, host buffers (through the ctypes binding; planes, tables and file returned to the host after every call)",
+                    "metric": "ms per frame", "value": rows[-1]["ms_per_frame"], "unit": "ms", "higher_is_better": False, "frames": rows,
+                    "cpu_baseline": None if not cpu_dropin else {"kind": cpu_dropin[1], "cores": 1, "unit": "ms", "value": rows[-1].get("reference_ms_per_frame_one_core"),
+                                                                 "sample": "the same two images, 3 passes each, timed inside C"}}
+
+        sub_records.append(dropin_record())
         sub_records.append(device_record("noise", 1920, 1280, 128, "config 4, class 'noise': 128 x 1920x1280 (splitmix64 bytes: every block busy, 632 KB per frame)"))
         sub_records.append(device_record("ramp", 1920, 1280, 128, "config 4, class 'ramp': 128 x 1920x1280 (R=G=B=(x+y+f)&255: every pixel on an exact-integer colour boundary)"))
         sub_records.append(device_record("natural", 3840, 2160, 256, "config 5: 256 x 3840x2160 natural"))

@@ -15,6 +15,7 @@
 // Byte stuffing, headers and layout stay with k_count_ff (+ layout_job) / k_stuff (k_entropy.cu).
 #include "jpegb200_internal.cuh"
 #include "walk.cuh"
+#include <type_traits>
 
 namespace {
 
@@ -221,17 +222,27 @@ __global__ void __launch_bounds__(PR_WARPS * 32, JB_COMPACT_MIN_CTAS) k_compact_
         }
         const uint32_t rem = n - k0;                    // tokens of the run from k0 on
         uint32_t* dp = tok2 + d + k0 + lane;
+        // a step spans at most two chunks; most lie inside one (warp-uniform test), and then no token asks which chunk it is in
+        const bool one_chunk = (d + k0 + min(rem, 32u * CP_STEP) - 1u) / JB_TCHUNK == cA;
+        auto slices = [&](auto single) {
 #pragma unroll
-        for (int j = 0; j < CP_STEP; j++) {
-          if (32u * j >= rem) break;                    // warp-uniform
-          const uint32_t tk = t[j], ent = e[(tk >> 15) & 0x1FFu], z = tk >> 24;
-          // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
-          if (32u * j + lane < rem) dp[32 * j] = z ? (tk << 5) | 31u : ent | ((tk & 0x7FFu) << 5);
-          const uint32_t len = (ent & 31u) + z * zrl_len;                               // a void token: no bits
-          const bool in_b = (d + k0 + 32u * j + lane) / JB_TCHUNK != cA;                // a step spans at most two chunks
-          accA += in_b ? 0u : len;
-          accB += in_b ? len : 0u;
-        }
+          for (int j = 0; j < CP_STEP; j++) {
+            if (32u * j >= rem) break;                    // warp-uniform
+            const uint32_t tk = t[j], ent = e[(tk >> 15) & 0x1FFu], z = tk >> 24;
+            // resolved token: code word << 5 | length; a token that carries ZRLs keeps its raw form behind the escape length 31
+            if (32u * j + lane < rem) dp[32 * j] = z ? (tk << 5) | 31u : ent | ((tk & 0x7FFu) << 5);
+            const uint32_t len = (ent & 31u) + z * zrl_len;                               // a void token: no bits
+            if constexpr (decltype(single)::value) {
+              accA += len;
+            } else {
+              const bool in_b = (d + k0 + 32u * j + lane) / JB_TCHUNK != cA;
+              accA += in_b ? 0u : len;
+              accB += in_b ? len : 0u;
+            }
+          }
+        };
+        if (one_chunk) slices(std::true_type());
+        else slices(std::false_type());
       }
       r = r2; k0 = k2; src = src2; n = n2; d = d2;
 #pragma unroll

@@ -75,6 +75,10 @@ struct Lane {
   DevBuf jobs, state_hist, coef, mask, dcraw, chunk_hist, chunk_bits, chunk_base, huff, enc, scratch, tile_ff, fix, tok, runs, run_base, tok2, tchunk_bits, tchunk_base, fixtok;
   DevBuf in, in_packed, out, sizes;      // host-path staging on the device (in_packed: frames in a packed camera format)
   PinBuf h_jobs, h_sizes;
+  PinBuf h_in, h_out;                    // pinned staging of the host path when the caller's buffers are pageable (stage_host_copies)
+  cudaEvent_t out_ready = nullptr;       // the streams of the last retired wave have landed in h_out
+  int out_first = -1;                    // that wave's first frame (-1: nothing to hand over)
+  std::vector<uint32_t> out_sizes;
   JbWs ws{};
   // host path bookkeeping of the wave in flight
   int pending_first = -1, pending_n = 0;
@@ -138,6 +142,9 @@ struct Lane {
       b->release();
     h_jobs.release();
     h_sizes.release();
+    h_in.release();
+    h_out.release();
+    if (out_ready) cudaEventDestroy(out_ready);
     if (done) cudaEventDestroy(done);
     if (sizes_ready) cudaEventDestroy(sizes_ready);
     if (pass1_done) cudaEventDestroy(pass1_done);
@@ -220,6 +227,7 @@ int make_lanes(jpegb200_ctx* c, int n) {
     CK(cudaEventCreateWithFlags(&l.pass2_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&l.sizes_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&l.out_ready, cudaEventDisableTiming));
   }
   return 0;
 }
@@ -526,6 +534,78 @@ int jpegb200_encode_batch(jpegb200_ctx* c, const uint8_t* d_bgr, int n, int w, i
   return 0;
 }
 
+// ---- pageable host buffers ------------------------------------------------------------------------------------------
+// A caller that comes from the reference hands over malloc'ed (pageable) memory.  cudaMemcpyAsync stages such copies through
+// the driver's own bounce buffer, one at a time and synchronously: 10.8 GB/s into the device instead of the 54 GB/s of pinned
+// memory (measured, tools/debug/pageable_e2e.py: 3.6 against 18.0 Gpix/s).  The host path therefore keeps a pinned staging buffer
+// per lane and moves the caller's bytes with a few host threads (streaming stores), overlapped with the other lanes' transfers
+// and kernels: 13.8 Gpix/s (41 GB/s) with 12 threads on a 16-core box.
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+static int copy_threads() {
+  static int n = 0;
+  if (!n) {
+    const char* e = getenv("JPEGB200_COPY_THREADS");
+    const int hw = (int)std::thread::hardware_concurrency();
+    n = e ? atoi(e) : 12;                      // measured on a 16-core box: 4 / 6 / 8 / 12 threads -> 21 / 32 / 36 / 41 GB/s into the device
+    if (!e && hw > 0 && n > 3 * hw / 4) n = 3 * hw / 4;
+    if (hw > 0 && n > hw) n = hw;
+    if (n < 1) n = 1;
+  }
+  return n;
+}
+// Large copies into the pinned staging buffer bypass the cache (no read-for-ownership of the destination lines, no eviction of
+// what the other threads work on): AVX2 streaming stores where the CPU has them, memcpy otherwise.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void copy_stream_avx2(uint8_t* d, const uint8_t* s, size_t n) {
+  const size_t head = std::min(n, (size_t)((32 - ((uintptr_t)d & 31)) & 31));
+  memcpy(d, s, head);
+  d += head; s += head; n -= head;
+  size_t i = 0;
+  for (; i + 128 <= n; i += 128) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(s + i)), b = _mm256_loadu_si256((const __m256i*)(s + i + 32));
+    const __m256i c2 = _mm256_loadu_si256((const __m256i*)(s + i + 64)), e = _mm256_loadu_si256((const __m256i*)(s + i + 96));
+    _mm256_stream_si256((__m256i*)(d + i), a);
+    _mm256_stream_si256((__m256i*)(d + i + 32), b);
+    _mm256_stream_si256((__m256i*)(d + i + 64), c2);
+    _mm256_stream_si256((__m256i*)(d + i + 96), e);
+  }
+  _mm_sfence();
+  memcpy(d + i, s + i, n - i);
+}
+static void copy_big(uint8_t* d, const uint8_t* s, size_t n, bool stream) {
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("JPEGB200_NO_STREAM_COPY");
+  if (stream && avx2 && n >= ((size_t)1 << 16)) copy_stream_avx2(d, s, n);
+  else memcpy(d, s, n);
+}
+#else
+static void copy_big(uint8_t* d, const uint8_t* s, size_t n, bool) { memcpy(d, s, n); }
+#endif
+// pieces[i] = (dst, src, bytes): copied by copy_threads() threads, whole pieces split further when there are few of them
+static void parallel_copy(const std::vector<std::pair<std::pair<uint8_t*, const uint8_t*>, size_t>>& pieces, bool stream = false) {
+  size_t total = 0;
+  for (auto& p : pieces) total += p.second;
+  const int T = total < ((size_t)4 << 20) ? 1 : copy_threads();
+  if (T == 1) { for (auto& p : pieces) memcpy(p.first.first, p.first.second, p.second); return; }
+  const size_t share = (total + T - 1) / T;
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++)
+    th.emplace_back([&, t]() {
+      size_t lo = (size_t)t * share, hi = std::min(total, lo + share), pos = 0;    // this thread's byte range of the concatenation
+      for (auto& p : pieces) {
+        const size_t a = std::max(lo, pos), b = std::min(hi, pos + p.second);
+        if (a < b) copy_big(p.first.first + (a - pos), p.first.second + (a - pos), b - a, stream);
+        pos += p.second;
+        if (pos >= hi) break;
+      }
+    });
+  for (auto& x : th) x.join();
+}
+
 int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int w, int h, uint8_t* h_out, size_t slot, uint32_t* h_sizes) {
   return jpegb200_encode_batch_host_fmt(c, h_bgr, JPEGB200_FMT_BGR888, n, w, h, h_out, slot, h_sizes);
 }
@@ -544,6 +624,7 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   const JobDims jd = jb_job_dims(w, h, slot, budget);
   const int G = wave_frames(c, w, h, true);
   const size_t g = (size_t)std::min(G, n);
+  const bool stage_in = is_pageable(h_bgr), stage_out = is_pageable(h_out);
   WaveDims wd;
   wd.njobs = g; wd.coefs = g * jd.coefs; wd.blocks = g * jd.blocks; wd.chunks = g * jd.chunks;
   wd.scratch_words = g * jd.scratch_words; wd.tiles = g * 3 * jd.tiles_per_seg;
@@ -561,18 +642,38 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
     CK(l.out.ensure(g * dslot));
     CK(l.sizes.ensure(g * sizeof(uint32_t)));
     CK(l.h_sizes.ensure(g * sizeof(uint32_t)));
+    if (stage_in) CK(l.h_in.ensure(g * src_frame));
+    if (stage_out) CK(l.h_out.ensure(g * dslot));
     l.pending_first = -1;
+    l.out_first = -1;
   }
   c->overlap_waves = nl >= 2;
+  // The streams of a retired wave wait in the lane's pinned h_out; hand them over to the caller's (pageable) memory.
+  auto hand_over = [&](Lane& l) -> int {
+    if (l.out_first < 0) return 0;
+    CK(cudaEventSynchronize(l.out_ready));
+    std::vector<std::pair<std::pair<uint8_t*, const uint8_t*>, size_t>> pieces;
+    for (size_t i = 0; i < l.out_sizes.size(); i++)
+      if (l.out_sizes[i]) pieces.push_back({{h_out + (size_t)(l.out_first + (int)i) * slot, (const uint8_t*)l.h_out.p + i * dslot}, l.out_sizes[i]});
+    parallel_copy(pieces);
+    l.out_first = -1;
+    return 0;
+  };
   // Retire the wave in flight on a lane: wait for its sizes, then fetch exactly the bytes produced.
   auto retire = [&](Lane& l) -> int {
     if (l.pending_first < 0) return 0;
     CK(cudaEventSynchronize(l.sizes_ready));
     const uint32_t* sz = (const uint32_t*)l.h_sizes.p;
+    if (stage_out && hand_over(l)) return -1;             // h_out still holds the wave before this one
     for (int i = 0; i < l.pending_n; i++) {
       h_sizes[l.pending_first + i] = sz[i];
-      if (sz[i]) CK(cudaMemcpyAsync(h_out + (size_t)(l.pending_first + i) * slot, (uint8_t*)l.out.p + (size_t)i * dslot, sz[i],
-                                    cudaMemcpyDeviceToHost, l.stream));
+      uint8_t* dst = stage_out ? (uint8_t*)l.h_out.p + (size_t)i * dslot : h_out + (size_t)(l.pending_first + i) * slot;
+      if (sz[i]) CK(cudaMemcpyAsync(dst, (uint8_t*)l.out.p + (size_t)i * dslot, sz[i], cudaMemcpyDeviceToHost, l.stream));
+    }
+    if (stage_out) {
+      CK(cudaEventRecord(l.out_ready, l.stream));
+      l.out_first = l.pending_first;
+      l.out_sizes.assign(sz, sz + l.pending_n);
     }
     l.pending_first = -1;
     return 0;
@@ -581,10 +682,15 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
     Lane& l = c->lanes[k % nl];
     if (retire(l)) return -1;
     const int first = k * G, cnt = std::min(G, n - first);
+    const uint8_t* h_src = h_bgr + (size_t)first * src_frame;
+    if (stage_in) {             // retire() above waited for the lane's previous wave: its copy out of h_in is done
+      parallel_copy({{{(uint8_t*)l.h_in.p, h_src}, (size_t)cnt * src_frame}}, true);
+      h_src = (const uint8_t*)l.h_in.p;
+    }
     if (fmt == JPEGB200_FMT_BGR888) {
-      CK(cudaMemcpyAsync(l.in.p, h_bgr + (size_t)first * frame, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
+      CK(cudaMemcpyAsync(l.in.p, h_src, (size_t)cnt * frame, cudaMemcpyHostToDevice, l.stream));
     } else {                    // 2 or 1 byte per pixel over PCIe, unpacked on the device (k_formats.cu)
-      CK(cudaMemcpyAsync(l.in_packed.p, h_bgr + (size_t)first * src_frame, (size_t)cnt * src_frame, cudaMemcpyHostToDevice, l.stream));
+      CK(cudaMemcpyAsync(l.in_packed.p, h_src, (size_t)cnt * src_frame, cudaMemcpyHostToDevice, l.stream));
       jb_launch_unpack((const uint8_t*)l.in_packed.p, fmt, (size_t)cnt * w * h, (uint8_t*)l.in.p, l.stream);
       c->launches++;
     }
@@ -598,6 +704,7 @@ int jpegb200_encode_batch_host_fmt(jpegb200_ctx* c, const uint8_t* h_bgr, int fm
   }
   for (int i = 0; i < nl; i++) if (retire(c->lanes[i])) return -1;
   for (int i = 0; i < nl; i++) CK(cudaStreamSynchronize(c->lanes[i].stream));
+  if (stage_out) for (int i = 0; i < nl; i++) if (hand_over(c->lanes[i])) return -1;
   if (budget) {
     // Frames that came back empty may have overflowed the token budget: once more, one frame per wave, with the worst-case pool
     // (a single frame's worst case is smaller than a wave at any budget, so no buffer grows).  A frame that does not fit its

@@ -1,0 +1,20 @@
+import importlib, time, numpy as np, torch, sys
+sys.path.insert(0, '/root/repo')
+pkg = importlib.import_module("jpeg-encoder-decoder_b200"); fr = importlib.import_module("jpeg-encoder-decoder_b200.frames")
+W,H,n=1920,1280,256
+tile=fr.tile_bgr(W,H)
+pin=torch.empty((n,H,W,3),dtype=torch.uint8,pin_memory=True)
+for i in range(n): pin[i]=torch.from_numpy(np.roll(tile,(16*(i%80),16*(i%120)),axis=(0,1)))
+page=pin.numpy().copy()
+slot=512*1024
+enc=pkg.Encoder(0,16,3)
+out_pin=torch.empty((n,slot),dtype=torch.uint8,pin_memory=True).numpy(); sizes=np.zeros(n,np.uint32)
+out_page=np.empty((n,slot),np.uint8)
+def run(src,dst):
+    enc.encode_batch_host(src,slot,out=dst,sizes=sizes)
+for name,src,dst in (("pinned",pin.numpy(),out_pin),("pageable",page,out_page),("pinned",pin.numpy(),out_pin),("pageable",page,out_page)):
+    run(src,dst)
+    t0=time.perf_counter(); 
+    for _ in range(3): run(src,dst)
+    dt=(time.perf_counter()-t0)/3
+    print(name, "%.1f ms  %.2f Gpix/s  %.1f GB/s in"%(1000*dt, n*W*H/dt/1e9, n*W*H*3/dt/1e9))

@@ -80,8 +80,8 @@ int jpegb200_encode_batch(jpegb200_ctx *ctx, const uint8_t *d_bgr, int n, int w,
  * lanes.  Synchronous: returns when h_out and h_sizes are complete.  Pinned (cudaMallocHost / cudaHostRegister) buffers
  * travel at the link's rate (54 GB/s, 18 Gpix/s measured).  Pageable buffers - plain malloc, what a caller of the reference
  * has - are detected (cudaPointerGetAttributes) and staged through per-lane pinned buffers by a few host threads with
- * streaming stores (JPEGB200_COPY_THREADS, default 12 capped at 3/4 of the cores): 13.8 Gpix/s where the direct copies of
- * pageable memory gave 3.6. */
+ * streaming stores (JPEGB200_COPY_THREADS, default 12 capped at 3/4 of the cores): 14.9 Gpix/s where the direct copies of
+ * pageable memory gave 3.6.  The stage functions below (the drop-in entry points) move their planes the same way. */
 int jpegb200_encode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_bgr, int n, int w, int h, uint8_t *h_out,
                                size_t slot, uint32_t *h_sizes);
 

@@ -677,10 +677,15 @@ static uint8_t* stage_take(jpegb200_ctx* c, size_t n) {
 }
 static bool stage_wanted(const void* h, size_t n) { return n >= ((size_t)1 << 20) && is_pageable(h); }
 static int h2d_host(jpegb200_ctx* c, void* d, const void* h, size_t n, cudaStream_t st, bool staged) {
-  if (staged) {
+  if (staged) {                  // in pieces of 8 MB: the DMA of a piece runs while the pool copies the next one
     uint8_t* p = stage_take(c, n);
-    parallel_copy({{{p, (const uint8_t*)h}, n}}, true);
-    h = p;
+    const size_t piece = (size_t)8 << 20;
+    for (size_t o = 0; o < n; o += piece) {
+      const size_t m = std::min(piece, n - o);
+      parallel_copy({{{p + o, (const uint8_t*)h + o}, m}}, true);
+      CK(cudaMemcpyAsync((uint8_t*)d + o, p + o, m, cudaMemcpyHostToDevice, st));
+    }
+    return 0;
   }
   CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st));
   return 0;
@@ -1140,7 +1145,12 @@ int jpegb200_subsample(jpegb200_ctx* c, const uint8_t* bgr, int fw, int fh, uint
   const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
   CK(c->cmp_frame.ensure(fb));
   CK(c->cmp_sub.ensure(sb));
-  CK(cudaMemcpyAsync(c->cmp_frame.p, bgr, fb, cudaMemcpyHostToDevice, st));
+  {                                  // (every host-buffer entry point returns synchronised: the bounce buffer is free)
+    const bool staged = stage_wanted(bgr, fb);
+    c->stage_off = 0;
+    if (staged) CK(c->stage.ensure(fb + 4096));
+    if (h2d_host(c, c->cmp_frame.p, bgr, fb, st, staged)) return -1;
+  }
   jb_launch_subsample((const uint8_t*)c->cmp_frame.p, fw, fh, (uint8_t*)c->cmp_sub.p, 1, fb, st);
   c->launches++;
   CK(cudaGetLastError());
@@ -1278,7 +1288,13 @@ int jpegb200_compare_encode_batch(jpegb200_ctx* c, const uint8_t* frames, int fr
   const uint8_t* d_frames = frames;
   if (!frames_on_device) {
     CK(c->cmp_frame.ensure((size_t)nframes * fb));
-    CK(cudaMemcpy2DAsync(c->cmp_frame.p, fb, frames, frame_stride, fb, (size_t)nframes, cudaMemcpyHostToDevice, st));
+    if (frame_stride == fb && stage_wanted(frames, (size_t)nframes * fb)) {       // pageable frames: through the pinned bounce buffer
+      c->stage_off = 0;
+      CK(c->stage.ensure((size_t)nframes * fb + 4096));
+      if (h2d_host(c, c->cmp_frame.p, frames, (size_t)nframes * fb, st, true)) return -1;
+    } else {
+      CK(cudaMemcpy2DAsync(c->cmp_frame.p, fb, frames, frame_stride, fb, (size_t)nframes, cudaMemcpyHostToDevice, st));
+    }
     d_frames = (const uint8_t*)c->cmp_frame.p;
     frame_stride = fb;
   }
@@ -1319,7 +1335,12 @@ int jpegb200_compare_encode(jpegb200_ctx* c, const uint8_t* h_frame, int fw, int
   cudaStream_t st = l.stream;
   const size_t fb = (size_t)3 * fw * fh, sb = fb / 16;
   CK(c->cmp_frame.ensure(fb));
-  CK(cudaMemcpyAsync(c->cmp_frame.p, h_frame, fb, cudaMemcpyHostToDevice, st));
+  {
+    const bool staged = stage_wanted(h_frame, fb);
+    c->stage_off = 0;
+    if (staged) CK(c->stage.ensure(fb + 4096));
+    if (h2d_host(c, c->cmp_frame.p, h_frame, fb, st, staged)) return -1;
+  }
   // arena: the regions of one frame after the margin-2 merge rarely overlap; twice the frame leaves room for those that do
   const size_t arena_bytes = 2 * ((size_t)fw * fh) + (size_t)JB_MAX_REGIONS * 4096 + jb_region_slot(fw, fh);
   if (compare_encode_device(c, (const uint8_t*)c->cmp_frame.p, fb, 1, fw, fh, JB_MAX_REGIONS, arena_bytes, seed != 0)) return -1;

@@ -18,3 +18,14 @@ for name,src,dst in (("pinned",pin.numpy(),out_pin),("pageable",page,out_page),(
     for _ in range(3): run(src,dst)
     dt=(time.perf_counter()-t0)/3
     print(name, "%.1f ms  %.2f Gpix/s  %.1f GB/s in"%(1000*dt, n*W*H/dt/1e9, n*W*H*3/dt/1e9))
+
+# the comparator loop (jpegb200_compare_encode_batch) with pinned and with pageable frames
+seq = fr.moving_sequence(33, W, H, 5)
+hs = torch.empty(seq.shape, dtype=torch.uint8, pin_memory=True); hs.copy_(torch.from_numpy(seq))
+for name, host in (("pinned", hs.numpy()), ("pageable", seq), ("pinned", hs.numpy()), ("pageable", seq)):
+    enc.compare_encode(host[0], seed=True); enc.compare_encode_batch(host[1:], max_regions=16)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        enc.compare_encode(host[0], seed=True); enc.compare_encode_batch(host[1:], max_regions=16)
+    dt = (time.perf_counter() - t0) / 3
+    print("comparator loop, 32 frames", name, "%.2f ms per call  %.0f frames/s" % (1000 * dt, 32 / dt))

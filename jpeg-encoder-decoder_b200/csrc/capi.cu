@@ -212,6 +212,7 @@ struct jpegb200_ctx {
   bool have_saved = false;
   // stage functions (the drop-in entry points): pinned bounce buffer for the caller's pageable planes and pixels
   PinBuf stage;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   size_t stage_off = 0;
   std::vector<std::pair<std::pair<uint8_t*, const uint8_t*>, size_t>> d2h_pending;
   int saved_w = 0, saved_h = 0;
@@ -409,6 +410,7 @@ void jpegb200_destroy(jpegb200_ctx* c) {
   for (DevBuf* b : {&c->dec_frames, &c->dec_planes, &c->dec_dcabs, &c->dec_samples, &c->dec_in, &c->dec_sizes, &c->dec_out, &c->dec_planes_out, &c->dec_scratch}) b->release();
   c->cmp_host.release();
   c->stage.release();
+  for (int k = 0; k < 2; k++) if (c->stage_ev[k]) cudaEventDestroy(c->stage_ev[k]);
   if (c->fork) cudaEventDestroy(c->fork);
   delete c;
 }
@@ -700,6 +702,28 @@ static int d2h_host(jpegb200_ctx* c, void* h, const void* d, size_t n, cudaStrea
   }
   return 0;
 }
+// A large result for pageable memory: device -> two pinned slots of 32 MB in turn -> the caller's memory by the pool, the DMA of a
+// piece under the copy-out of the piece before it.  Synchronises the stream.
+static int d2h_host_big(jpegb200_ctx* c, void* h, const void* d, size_t n, cudaStream_t st) {
+  const size_t piece = (size_t)32 << 20;
+  CK(c->stage.ensure(2 * piece));
+  for (int k = 0; k < 2; k++)
+    if (!c->stage_ev[k]) CK(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+  const size_t np = (n + piece - 1) / piece;
+  for (size_t i = 0; i <= np; i++) {
+    if (i < np) {
+      const size_t m = std::min(piece, n - i * piece);
+      CK(cudaMemcpyAsync((uint8_t*)c->stage.p + (i & 1) * piece, (const uint8_t*)d + i * piece, m, cudaMemcpyDeviceToHost, st));
+      CK(cudaEventRecord(c->stage_ev[i & 1], st));
+    }
+    if (i >= 1) {
+      const size_t j = i - 1, m = std::min(piece, n - j * piece);
+      CK(cudaEventSynchronize(c->stage_ev[j & 1]));
+      parallel_copy({{{(uint8_t*)h + j * piece, (const uint8_t*)c->stage.p + (j & 1) * piece}, m}});
+    }
+  }
+  return 0;
+}
 static void d2h_finish(jpegb200_ctx* c) {       // after the stream has been synchronised
   if (!c->d2h_pending.empty()) parallel_copy(c->d2h_pending);
   c->d2h_pending.clear();
@@ -936,8 +960,14 @@ int jpegb200_decode_batch_host(jpegb200_ctx* c, const uint8_t* h_streams, size_t
   if (jpegb200_decode_batch(c, (const uint8_t*)c->dec_in.p, slot, d_sizes, n, w, h, h_bgr ? (uint8_t*)c->dec_out.p : nullptr, frame,
                             h_planes ? (int16_t*)c->dec_planes_out.p : nullptr, d_status, st))
     return -1;
-  if (h_bgr) CK(cudaMemcpyAsync(h_bgr, c->dec_out.p, (size_t)n * frame, cudaMemcpyDeviceToHost, st));
-  if (h_planes) CK(cudaMemcpyAsync(h_planes, c->dec_planes_out.p, (size_t)n * planes, cudaMemcpyDeviceToHost, st));
+  if (h_bgr) {
+    if (stage_wanted(h_bgr, (size_t)n * frame)) { if (d2h_host_big(c, h_bgr, c->dec_out.p, (size_t)n * frame, st)) return -1; }
+    else CK(cudaMemcpyAsync(h_bgr, c->dec_out.p, (size_t)n * frame, cudaMemcpyDeviceToHost, st));
+  }
+  if (h_planes) {
+    if (stage_wanted(h_planes, (size_t)n * planes)) { if (d2h_host_big(c, h_planes, c->dec_planes_out.p, (size_t)n * planes, st)) return -1; }
+    else CK(cudaMemcpyAsync(h_planes, c->dec_planes_out.p, (size_t)n * planes, cudaMemcpyDeviceToHost, st));
+  }
   if (h_status) CK(cudaMemcpyAsync(h_status, d_status, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return 0;

@@ -29,3 +29,17 @@ for name, host in (("pinned", hs.numpy()), ("pageable", seq), ("pinned", hs.nump
         enc.compare_encode(host[0], seed=True); enc.compare_encode_batch(host[1:], max_regions=16)
     dt = (time.perf_counter() - t0) / 3
     print("comparator loop, 32 frames", name, "%.2f ms per call  %.0f frames/s" % (1000 * dt, 32 / dt))
+
+# decoding side with host buffers: 64 streams -> 64 frames (472 MB) into pageable memory
+jpgs = enc.encode_frames(page[:64])
+import ctypes as C
+slot_d = (max(len(j) for j in jpgs) + 15) & ~15
+buf = np.zeros((64, slot_d), np.uint8); szs = np.zeros(64, np.uint32)
+for i, j in enumerate(jpgs):
+    buf[i, :len(j)] = np.frombuffer(bytes(j), np.uint8); szs[i] = len(j)
+bgr = np.zeros((64, H, W, 3), np.uint8); status = np.zeros(64, np.int32)
+def dec():
+    enc._check(enc.lib.jpegb200_decode_batch_host(enc.ctx, buf.ctypes.data, slot_d, szs.ctypes.data, 64, W, H, bgr.ctypes.data, None, status.ctypes.data))
+dec()
+t0 = time.perf_counter(); dec(); dt = time.perf_counter() - t0
+print("decode 64 streams to pageable frames: %.1f ms (%.2f Gpix/s), status ok %s" % (1000 * dt, 64 * W * H / dt / 1e9, bool((np.asarray(status) == 0).all())))

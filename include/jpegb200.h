@@ -85,6 +85,12 @@ int jpegb200_encode_batch(jpegb200_ctx *ctx, const uint8_t *d_bgr, int n, int w,
 int jpegb200_encode_batch_host(jpegb200_ctx *ctx, const uint8_t *h_bgr, int n, int w, int h, uint8_t *h_out,
                                size_t slot, uint32_t *h_sizes);
 
+/* Page-lock / release caller memory (cudaHostRegister / cudaHostUnregister, for callers without the CUDA headers): buffers that are
+ * handed to the host entry points again and again - the reference's are static arrays (main/main.c:25-37) - then cross the link at
+ * its full rate without the staging copy.  Unpin before the memory is freed. */
+int jpegb200_pin_host(void *p, size_t bytes);
+int jpegb200_unpin_host(void *p);
+
 /* Input side (reference main/main.c:131-135 fills its B,G,R frame with fmt2rgb888 of
  * espressif/esp32-camera 2.0.3): frames in one of the camera's packed formats are unpacked on the device, so that they
  * cross PCIe at 2 or 1 byte per pixel.  Only the byte-shuffling branches of fmt2rgb888 are restated (k_formats.cu cites

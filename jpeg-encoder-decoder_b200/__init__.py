@@ -25,7 +25,7 @@ ROOT = os.path.dirname(_HERE)
 
 C_ABI_SYMBOLS = [
     "jpegb200_create", "jpegb200_destroy", "jpegb200_last_error", "jpegb200_configure", "jpegb200_launch_count",
-    "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_set_token_budget", "jpegb200_debug_fix_count",
+    "jpegb200_set_timing", "jpegb200_get_timing", "jpegb200_get_stage_timing", "jpegb200_set_exact_dct", "jpegb200_set_token_path", "jpegb200_set_token_budget", "jpegb200_pin_host", "jpegb200_unpin_host", "jpegb200_debug_fix_count",
     "jpegb200_encode_batch", "jpegb200_encode_batch_host", "jpegb200_encode_batch_host_multi", "jpegb200_encode_batch_host_fmt", "jpegb200_unpack", "jpegb200_encode_regions",
     "jpegb200_stage_dct", "jpegb200_stage_huffman", "jpegb200_stage_write", "jpegb200_debug_build_tables",
     "jpegb200_subsample", "jpegb200_compare", "jpegb200_enlarge_adjust", "jpegb200_compare_encode", "jpegb200_compare_encode_batch",
@@ -80,6 +80,8 @@ def load_library() -> C.CDLL:
     L.jpegb200_set_exact_dct.argtypes = [vp, C.c_int]
     L.jpegb200_set_token_path.argtypes = [vp, C.c_int]
     L.jpegb200_set_token_budget.argtypes = [vp, C.c_int]
+    L.jpegb200_pin_host.argtypes = [vp, C.c_size_t]
+    L.jpegb200_unpin_host.argtypes = [vp]
     L.jpegb200_debug_fix_count.argtypes = [vp, C.c_int, u32p]
     L.jpegb200_launch_count.argtypes = [vp]
     L.jpegb200_launch_count.restype = C.c_uint64
@@ -140,6 +142,17 @@ def _huff_dict(h: HuffCode) -> dict:
 
 class JpegB200Error(RuntimeError):
     pass
+
+
+def pin_host(a: np.ndarray):
+    """Page-lock a numpy array in place (jpegb200_pin_host); unpin_host(a) before it is dropped."""
+    if load_library().jpegb200_pin_host(C.c_void_p(a.ctypes.data), a.nbytes):
+        raise JpegB200Error(load_library().jpegb200_last_error().decode())
+
+
+def unpin_host(a: np.ndarray):
+    if load_library().jpegb200_unpin_host(C.c_void_p(a.ctypes.data)):
+        raise JpegB200Error(load_library().jpegb200_last_error().decode())
 
 
 class RefAPI:

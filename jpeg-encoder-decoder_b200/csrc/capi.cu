@@ -729,6 +729,17 @@ static void d2h_finish(jpegb200_ctx* c) {       // after the stream has been syn
   c->d2h_pending.clear();
 }
 
+int jpegb200_pin_host(void* p, size_t bytes) {
+  if (!p || !bytes) return fail("null argument");
+  CK(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return 0;
+}
+int jpegb200_unpin_host(void* p) {
+  if (!p) return fail("null argument");
+  CK(cudaHostUnregister(p));
+  return 0;
+}
+
 int jpegb200_encode_batch_host(jpegb200_ctx* c, const uint8_t* h_bgr, int n, int w, int h, uint8_t* h_out, size_t slot, uint32_t* h_sizes) {
   return jpegb200_encode_batch_host_fmt(c, h_bgr, JPEGB200_FMT_BGR888, n, w, h, h_out, slot, h_sizes);
 }

@@ -280,6 +280,24 @@ def test_token_budget_overflow_is_detected_and_recovered(frames):
         e.close()
 
 
+def test_pageable_pinned_and_registered_host_buffers_agree(enc, frames):
+    """Host entry points: pageable numpy memory goes through the pinned staging buffers and the copy pool, memory registered with
+    jpegb200_pin_host goes straight over the link; the bytes are the same."""
+    w, h = 640, 480
+    batch = np.stack([frames.natural_frame(k, w, h) for k in range(12)])          # 11 MB: above the staging threshold
+    enc.configure(4, 3)
+    want = enc.encode_frames(batch)
+    reg = batch.copy()
+    pkg.pin_host(reg)
+    try:
+        assert enc.encode_frames(reg) == want
+    finally:
+        pkg.unpin_host(reg)
+    bgr, status = enc.decode_streams(want, w, h)                                    # 11 MB back into pageable memory
+    assert (status == 0).all() and bgr.shape == batch.shape
+    enc.configure(8, 3)
+
+
 def test_bad_dimensions_are_rejected(enc):
     with pytest.raises(pkg.JpegB200Error, match="multiples of 16"):
         enc.encode_batch_host(np.zeros((1, 20, 16, 3), np.uint8), 4096)

@@ -12,7 +12,8 @@ out_pin=torch.empty((n,slot),dtype=torch.uint8,pin_memory=True).numpy(); sizes=n
 out_page=np.empty((n,slot),np.uint8)
 def run(src,dst):
     enc.encode_batch_host(src,slot,out=dst,sizes=sizes)
-for name,src,dst in (("pinned",pin.numpy(),out_pin),("pageable",page,out_page),("pinned",pin.numpy(),out_pin),("pageable",page,out_page)):
+reg=page.copy(); out_reg=np.empty((n,slot),np.uint8); pkg.pin_host(reg); pkg.pin_host(out_reg)
+for name,src,dst in (("pinned",pin.numpy(),out_pin),("pageable",page,out_page),("registered (jpegb200_pin_host)",reg,out_reg),("pageable",page,out_page)):
     run(src,dst)
     t0=time.perf_counter(); 
     for _ in range(3): run(src,dst)

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <condition_variable>
@@ -648,13 +649,18 @@ class CopyPool {
   bool stop_ = false;
 };
 static CopyPool& copy_pool() { static CopyPool p(copy_threads()); return p; }
+static pid_t g_pool_pid = 0;            // threads do not survive fork(): a child copies with its own thread only
 
 // pieces[i] = (dst, src, bytes): the concatenation is cut into one byte range per copy thread
 typedef std::vector<std::pair<std::pair<uint8_t*, const uint8_t*>, size_t>> CopyList;
 static void parallel_copy(const CopyList& pieces, bool stream = false) {
   size_t total = 0;
   for (auto& p : pieces) total += p.second;
-  if (total < ((size_t)1 << 20) || copy_threads() == 1) { for (auto& p : pieces) memcpy(p.first.first, p.first.second, p.second); return; }
+  if (!g_pool_pid) g_pool_pid = getpid();
+  if (total < ((size_t)1 << 20) || copy_threads() == 1 || getpid() != g_pool_pid) {
+    for (auto& p : pieces) copy_big(p.first.first, p.first.second, p.second, stream);
+    return;
+  }
   CopyPool& pool = copy_pool();
   const int T = pool.size();
   const size_t share = ((total + T - 1) / T + 63) & ~(size_t)63;

@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--shape", default=f"{W}x{H}", help="frame size WxH; 3840x2160 is SURVEY.md 8d config 5 (use --batch 256)")
     ap.add_argument("--frames-per-wave", type=int, default=64)
-    ap.add_argument("--lanes", type=int, default=3)
+    ap.add_argument("--lanes", type=int, default=4)
     ap.add_argument("--e2e-frames-per-wave", type=int, default=16, help="smaller waves keep the PCIe pipeline of the host path full")
     ap.add_argument("--e2e-lanes", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")

@@ -668,7 +668,11 @@ void jb_launch_pixels_to_tokens(const JbWs& ws, int njobs, int max_w, int max_h,
   if (cap < 1) cap = 1;
   static int iters_env = -2;             // development override: JPEGB200_TK_ITERS
   if (iters_env == -2) { const char* e = getenv("JPEGB200_TK_ITERS"); iters_env = e ? atoi(e) : -1; }
-  const int iters = iters_env >= 0 ? iters_env : tiles_per_warp;
+  int iters = iters_env >= 0 ? iters_env : tiles_per_warp;
+  // multi-lane batches: 12 tiles per warp when that still leaves a CTA and a half per SM (sweep of the last build, 1024 frames, 64 per
+  // wave: 3 lanes x 8 tiles 273.3, 4 lanes x 8: 274.7, 4 x 12: 277.5, 4 x 16: 277.6, 4 x 24: 275.1, 6 x 16: 278.6 Gpix/s), else the 8
+  // of the small waves of the host path
+  if (iters_env < 0 && tiles_per_warp > 0) iters = 2 * ntiles >= 3 * sms * warps * 12 ? 12 : tiles_per_warp;
   if (iters > 0) cap = (ntiles + warps * iters - 1) / (warps * iters);
   const int grid = want < cap ? want : cap;
   kern<<<grid, warps * 32, smem, st>>>(ws, ntiles, tiles_per_job, 12582912.0f, strided ? 1 : 0);
